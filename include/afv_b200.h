@@ -1,0 +1,154 @@
+/*
+ * afv_b200.h -- C-ABI of the B200-native active-finite-Voronoi (AFV) build / force / step path.
+ *
+ * This is the drop-in boundary for PyAFV's per-step hot path.  Every entry point takes plain pointers and
+ * sizes; no C++ or torch types cross it.  A handle owns all device memory and one CUDA stream; host pointers
+ * are borrowed for the duration of the call only.  A handle is not re-entrant.  Errors are negative return
+ * codes plus afv_last_error(); nothing throws across the ABI.  There is NO CPU fallback: every entry point
+ * fails with AFV_ERR_CUDA when no sm_100-class device is usable.
+ *
+ * Reference interfaces replaced (paths into wwang721/pyafv v0.4.16):
+ *   afv_create / afv_set_params / afv_set_positions / afv_set_preferred_areas
+ *       <- FiniteVoronoiSimulator.__init__            pyafv/finite_voronoi.py:57-93
+ *          update_positions / update_params / update_preferred_areas   :1153-1230
+ *   afv_build + afv_get_*
+ *       <- FiniteVoronoiSimulator.build()             pyafv/finite_voronoi.py:866-945, i.e. the whole of
+ *          _build_voronoi_with_extensions (:96-289, scipy/Qhull), _per_cell_geometry (:292-509),
+ *          backend_impl.build_point_edges / compute_vertex_derivatives (pyafv/cell_geom.pyx:128-289,307-547),
+ *          _assemble_forces (:512-754) and _get_connections (:1110-1150)
+ *   afv_step
+ *       <- the user-level Euler / active-Langevin loop  examples/active_FV.py:43-54, examples/relaxation.py:41-45
+ *   box_L > 0 (native periodic boundaries)
+ *       <- tile_pbc + build + [:N]                     pyafv/_connectutil.py:12-96
+ *   afv_extract_slab / afv_append_cells / afv_remove_outside (slab sharding primitives)
+ *       <- decompose_points / _build_domain / _merge_results   pyafv/parallel_voronoi.py:125-338,351-418,590-633
+ */
+#ifndef AFV_B200_H
+#define AFV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct AfvParams {
+    double r;      /* maximal cell radius (l)                         physical_params.py:72 */
+    double A0;     /* default preferred area                          :73 */
+    double P0;     /* preferred perimeter                             :74 */
+    double KA;     /* area elasticity                                 :75 */
+    double KP;     /* perimeter elasticity                            :76 */
+    double Lambda; /* tension of non-contacting (arc) edges           :77 */
+    double delta;  /* contact truncation threshold (already resolved; the host maps None -> 0.45 r, :92-93) */
+} AfvParams;
+
+typedef struct AfvContext *AfvHandle;
+
+/* return codes */
+#define AFV_OK 0
+#define AFV_ERR_CUDA (-1)     /* CUDA runtime error, or no usable device */
+#define AFV_ERR_ARG (-2)      /* invalid argument */
+#define AFV_ERR_CAPACITY (-3) /* a cell exceeded the ring / polygon capacity of every code path */
+#define AFV_ERR_STATE (-4)    /* call order (e.g. getter before build) */
+
+/* afv_build flags */
+#define AFV_BUILD_FORCES 1u      /* always implied */
+#define AFV_BUILD_CONNECT 2u     /* also produce the contact list (finite_voronoi.py:1110-1150) */
+#define AFV_BUILD_RINGS 4u       /* also produce the compact ragged rings (vertices / regions / edges_type) */
+
+/* fields for afv_device_ptr (device arrays in the CURRENT SORTED ORDER; afv_device_ptr(AFV_F_GID) maps a
+ * sorted slot back to the caller's cell index) */
+enum AfvField {
+    AFV_F_X = 0, AFV_F_Y = 1, AFV_F_THETA = 2, AFV_F_A0 = 3, AFV_F_GID = 4,
+    AFV_F_FX = 5, AFV_F_FY = 6, AFV_F_AREA = 7, AFV_F_PERIM = 8, AFV_F_ARCLEN = 9, AFV_F_COORD = 10,
+    AFV_F_OWNED = 11
+};
+
+/* ---- life cycle ---------------------------------------------------------------------------------- */
+/* device: CUDA ordinal.  box_L: 0 for open boundaries, else the side of the periodic square [0,L)^2
+ * (must be >= 4 r).  stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create one. */
+int afv_create(int device, const AfvParams *params, double box_L, void *stream, AfvHandle *out);
+void afv_destroy(AfvHandle h);
+/* last error text of the handle (or of the failed afv_create when h is NULL); never NULL */
+const char *afv_last_error(AfvHandle h);
+/* static description: "sm_100a; ring_stride=..; ..." */
+const char *afv_build_info(void);
+
+/* ---- state --------------------------------------------------------------------------------------- */
+int afv_set_params(AfvHandle h, const AfvParams *params);
+/* xy_host: (N,2) row-major float64.  If N differs from the current count, preferred areas are reset to
+ * params.A0 and theta to 0 (finite_voronoi.py:1177-1182).  Cell order is reset to the caller's order. */
+int afv_set_positions(AfvHandle h, const double *xy_host, int64_t N);
+int afv_set_preferred_areas(AfvHandle h, const double *a0_host, int64_t N);
+int afv_set_theta(AfvHandle h, const double *theta_host, int64_t N);
+int64_t afv_num_cells(AfvHandle h);
+
+/* ---- the hot path -------------------------------------------------------------------------------- */
+/* bin + sort + geometry + force for the current positions.  Results stay on the device. */
+int afv_build(AfvHandle h, unsigned flags);
+/* n_steps of: build, then r += (mu F + v0 (cos th, sin th)) dt, th += sqrt(2 Dr dt) xi   (examples/active_FV.py:43-54).
+ * noise_host: NULL -> xi from Philox4x32-10 keyed by (seed, cell id, step0 + s);
+ *             else (n_steps, N) float64 in the caller's cell order (parity runs with a recorded stream).
+ * Positions are wrapped into [0,L) when the handle is periodic.  The geometry left on the device afterwards is
+ * that of the LAST build, i.e. of the positions before the last update. */
+int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t seed, int64_t step0, int n_steps,
+             const double *noise_host);
+/* the xi the device generator produces for (seed, cell id, step): for host-side verification of the stream */
+double afv_philox_normal(uint64_t seed, int64_t cell_id, int64_t step);
+
+/* ---- results, in the caller's cell order ----------------------------------------------------------- */
+int afv_get_positions(AfvHandle h, double *xy_out /* (N,2) */);
+int afv_get_theta(AfvHandle h, double *out /* (N,) */);
+int afv_get_forces(AfvHandle h, double *out /* (N,2) */);
+int afv_get_areas(AfvHandle h, double *out);
+int afv_get_perimeters(AfvHandle h, double *out);
+int afv_get_arclens(AfvHandle h, double *out);
+int afv_get_coord_nums(AfvHandle h, int64_t *out);
+/* contact pairs (i<j): first query the count, then copy (K,2) int64 (unsorted rows) */
+int afv_get_num_connections(AfvHandle h, int64_t *K);
+int afv_get_connections(AfvHandle h, int64_t *pairs_out);
+/* compact rings: total entry count T; then region_off (N+1), edge_types (T) int8 (1 straight, 0 arc),
+ * vertices (T,2) absolute coordinates, clockwise per cell (finite_voronoi.py:441-459) */
+int afv_get_num_ring_entries(AfvHandle h, int64_t *T);
+int afv_get_rings(AfvHandle h, int64_t *region_off, int8_t *edge_types, double *vertices_xy);
+
+/* diagnostics of the last build: [0] cells that needed the large-capacity path, [1] ring look-ups that found
+ * no partner (inconsistent near-cocircular topology), [2] max ring length, [3] number of bins */
+int afv_get_diagnostics(AfvHandle h, int64_t out[4]);
+
+/* ---- measurement --------------------------------------------------------------------------------- */
+/* when enabled, every stage of build/step is bracketed by CUDA events on the handle's stream */
+int afv_set_profiling(AfvHandle h, int enabled);
+/* accumulated milliseconds and launch counts since the last reset:
+ * stage 0 bin+sort+reorder, 1 geometry kernel, 2 force(+step) kernel, 3 everything else */
+int afv_get_stage_times(AfvHandle h, double ms_out[4], int64_t launches_out[4], int reset);
+/* number of kernel launches issued by this handle since creation */
+int64_t afv_launch_count(AfvHandle h);
+/* pinned host memory for end-to-end runs */
+void *afv_host_alloc(int64_t bytes);
+void afv_host_free(void *p);
+/* sustained FP64 FMA throughput of the device in TFLOP/s (a DFMA micro-benchmark; roofline denominator) */
+int afv_measure_fp64_peak(AfvHandle h, double *tflops_out);
+
+/* ---- zero-copy + slab sharding primitives (one handle = one GPU = one x-slab) ---------------------- */
+void *afv_device_ptr(AfvHandle h, int field);
+void *afv_stream(AfvHandle h);
+int afv_synchronize(AfvHandle h);
+/* Replace the device state by (x, y, theta, A0, gid) rows given in DEVICE memory: n_owned owned cells followed
+ * by n_halo halo cells (halo cells take part in the geometry but receive no force / update).  rows: (n,5)
+ * float64 row-major with gid stored as a float64-exact integer. */
+int afv_set_cells_device(AfvHandle h, const double *rows_dev, int64_t n_owned, int64_t n_halo);
+/* Pack the OWNED cells with x in [x_lo, x_hi) into rows_dev_out (capacity rows), adding x_shift to x; returns the
+ * count (halo send when keep != 0; migration when keep == 0, in which case the cells are removed). */
+int afv_extract_slab(AfvHandle h, double x_lo, double x_hi, double x_shift, int keep, double *rows_dev_out,
+                     int64_t capacity, int64_t *count);
+/* drop all halo cells (called after a step, before migration) */
+int afv_drop_halo(AfvHandle h);
+/* append rows (device memory) as owned (is_halo = 0) or halo (is_halo = 1) cells */
+int afv_append_cells(AfvHandle h, const double *rows_dev, int64_t n, int is_halo);
+int64_t afv_num_owned(AfvHandle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFV_B200_H */

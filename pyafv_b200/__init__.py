@@ -1,0 +1,7 @@
+"""pyafv_b200 -- B200-native backend for PyAFV's per-step build / force / step path."""
+from .physical_params import PhysicalParams, target_delta
+from .finite_voronoi import FiniteVoronoiSimulator
+
+__version__ = "0.1.0"
+
+__all__ = ["PhysicalParams", "FiniteVoronoiSimulator", "target_delta"]

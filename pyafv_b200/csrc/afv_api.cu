@@ -1,0 +1,747 @@
+// C-ABI implementation (include/afv_b200.h): context, memory, stage scheduling on one CUDA stream.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/afv_b200.h"
+#include "afv_kernels.cuh"
+
+using namespace afv;
+
+namespace {
+
+thread_local std::string g_create_error = "";
+
+constexpr int TPB = 128;
+inline int nblk(int64_t n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct AfvContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    AfvParams prm{};
+    double L = 0.0;
+    int64_t n = 0, n_owned = 0, cap = 0;
+    bool gid_is_perm = true;  // gid is a permutation of 0..n-1 (single-GPU use); false after set_cells_device
+    // SoA state, double-buffered for the reorder
+    double *x[2] = {nullptr, nullptr}, *y[2] = {nullptr, nullptr}, *th[2] = {nullptr, nullptr}, *a0[2] = {nullptr, nullptr};
+    int64_t *gid[2] = {nullptr, nullptr};
+    unsigned char *owned[2] = {nullptr, nullptr};
+    int cur = 0;
+    // cell list
+    unsigned *keys = nullptr, *keys_sorted = nullptr;
+    int *iota = nullptr, *perm = nullptr, *bin_start = nullptr;
+    int nbins_cap = 0, key_bits = 0;
+    GridDesc *d_grid = nullptr;
+    double *bbox_part = nullptr;
+    void *cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
+    // results (sorted order)
+    double *fx = nullptr, *fy = nullptr, *area = nullptr, *perim = nullptr, *arcl = nullptr;
+    int *coord = nullptr;
+    unsigned char *ring_len = nullptr;
+    RingShared *rs = nullptr;
+    RingOwn *ro = nullptr;
+    int *flags = nullptr;         // device: [0] slow-path cells, [1] lookup misses, [2] max ring length, [3] hard overflows
+    int *ovf_cells = nullptr, *ovf_index = nullptr, *ovf_len = nullptr;
+    RingShared *ovf_rs = nullptr;
+    RingOwn *ovf_ro = nullptr;
+    int h_flags[4] = {0, 0, 0, 0};
+    // scratch
+    DevBuf scratch_a, scratch_b, noise_buf, conn_buf, ring_types, ring_xy, ring_off;
+    int *cnt = nullptr, *off = nullptr;  // per-cell counts / offsets (cap + 1)
+    int64_t n_conn = -1, n_ring = -1;
+    bool built = false;
+    // profiling
+    bool profiling = false;
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double stage_ms[4] = {0, 0, 0, 0};
+    int64_t stage_launches[4] = {0, 0, 0, 0};
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+            return AFV_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+#define CHECK_H(h)                                                                                       \
+    if (!(h)) return AFV_ERR_ARG;                                                                        \
+    {                                                                                                    \
+        cudaError_t e_ = cudaSetDevice((h)->device);                                                     \
+        if (e_ != cudaSuccess) { (h)->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e_); return AFV_ERR_CUDA; } \
+    }
+
+template <typename T>
+int dev_alloc(AfvHandle h, T **p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    CK(cudaMalloc((void **)p, count * sizeof(T)));
+    return AFV_OK;
+}
+
+int ensure_buf(AfvHandle h, DevBuf &b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return AFV_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.bytes = 0;
+    size_t want = std::max(bytes, (size_t)256);
+    CK(cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return AFV_OK;
+}
+
+void free_all(AfvHandle h) {
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(h->x[k]); cudaFree(h->y[k]); cudaFree(h->th[k]); cudaFree(h->a0[k]); cudaFree(h->gid[k]); cudaFree(h->owned[k]);
+        h->x[k] = h->y[k] = h->th[k] = h->a0[k] = nullptr; h->gid[k] = nullptr; h->owned[k] = nullptr;
+    }
+    cudaFree(h->keys); cudaFree(h->keys_sorted); cudaFree(h->iota); cudaFree(h->perm); cudaFree(h->bin_start);
+    cudaFree(h->cub_tmp); cudaFree(h->fx); cudaFree(h->fy); cudaFree(h->area); cudaFree(h->perim); cudaFree(h->arcl);
+    cudaFree(h->coord); cudaFree(h->ring_len); cudaFree(h->rs); cudaFree(h->ro); cudaFree(h->cnt); cudaFree(h->off);
+    cudaFree(h->ovf_index); h->ovf_index = nullptr;
+    h->keys = h->keys_sorted = nullptr; h->iota = h->perm = h->bin_start = nullptr; h->cub_tmp = nullptr;
+    h->fx = h->fy = h->area = h->perim = h->arcl = nullptr; h->coord = nullptr; h->ring_len = nullptr;
+    h->rs = nullptr; h->ro = nullptr; h->cnt = h->off = nullptr;
+    h->cap = 0;
+}
+
+// (re)allocate everything for `cap` cells, preserving the first `keep` cells of the current SoA state
+int reserve(AfvHandle h, int64_t want, int64_t keep) {
+    if (want <= h->cap) return AFV_OK;
+    if (want >= (int64_t)1 << 31) { h->err = "more than 2^31-1 cells per GPU are not supported"; return AFV_ERR_ARG; }
+    int64_t cap = std::max<int64_t>(want + want / 8, 1024);
+    cap = std::min<int64_t>(cap, ((int64_t)1 << 31) - 1);
+    // keep old state
+    double *ox = h->x[h->cur], *oy = h->y[h->cur], *ot = h->th[h->cur], *oa = h->a0[h->cur];
+    int64_t *og = h->gid[h->cur];
+    unsigned char *oo = h->owned[h->cur];
+    h->x[h->cur] = h->y[h->cur] = h->th[h->cur] = h->a0[h->cur] = nullptr; h->gid[h->cur] = nullptr; h->owned[h->cur] = nullptr;
+    free_all(h);
+    int rc = AFV_OK;
+    for (int k = 0; k < 2 && rc == AFV_OK; ++k) {
+        if ((rc = dev_alloc(h, &h->x[k], cap))) break;
+        if ((rc = dev_alloc(h, &h->y[k], cap))) break;
+        if ((rc = dev_alloc(h, &h->th[k], cap))) break;
+        if ((rc = dev_alloc(h, &h->a0[k], cap))) break;
+        if ((rc = dev_alloc(h, &h->gid[k], cap))) break;
+        if ((rc = dev_alloc(h, &h->owned[k], cap))) break;
+    }
+    if (rc == AFV_OK && keep > 0 && ox) {
+        h->cur = 0;
+        cudaMemcpyAsync(h->x[0], ox, keep * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->y[0], oy, keep * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->th[0], ot, keep * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->a0[0], oa, keep * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->gid[0], og, keep * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->owned[0], oo, keep, cudaMemcpyDeviceToDevice, h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(ox); cudaFree(oy); cudaFree(ot); cudaFree(oa); cudaFree(og); cudaFree(oo);
+    if (rc) return rc;
+    // bins: up to 2 per cell, power of two so that the sort width is fixed
+    int bits = 6;
+    while (((int64_t)1 << bits) < 2 * cap && bits < 31) ++bits;
+    h->key_bits = bits;
+    h->nbins_cap = (int)std::min<int64_t>((int64_t)1 << bits, ((int64_t)1 << 31) - 2);
+    if ((rc = dev_alloc(h, &h->keys, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->keys_sorted, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->iota, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->perm, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->bin_start, (size_t)h->nbins_cap + 2))) return rc;
+    if ((rc = dev_alloc(h, &h->fx, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->fy, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->area, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->perim, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->arcl, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->coord, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->ring_len, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->rs, (size_t)cap * RS))) return rc;
+    if ((rc = dev_alloc(h, &h->ro, (size_t)cap * RS))) return rc;
+    if ((rc = dev_alloc(h, &h->ovf_index, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->cnt, cap + 1))) return rc;
+    if ((rc = dev_alloc(h, &h->off, cap + 1))) return rc;
+    k_iota<<<nblk(cap), TPB, 0, h->stream>>>(h->iota, (int)cap);
+    // cub temp storage for the largest sort / scan we issue
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, h->keys, h->keys_sorted, h->iota, h->perm, (int)cap, 0, h->key_bits, h->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, b2, h->cnt, h->off, (int)cap + 1, h->stream);
+    size_t b3 = 0;
+    cub::DeviceSelect::Flagged(nullptr, b3, h->iota, h->cnt, h->perm, h->off, (int)cap, h->stream);
+    h->cub_tmp_bytes = std::max(std::max(b1, b2), b3) + 256;
+    CK(cudaMalloc(&h->cub_tmp, h->cub_tmp_bytes));
+    CK(cudaGetLastError());
+    h->cap = cap;
+    return AFV_OK;
+}
+
+struct StageTimer {
+    AfvHandle h;
+    int idx = -1;
+    StageTimer(AfvHandle h_, int stage) : h(h_) {
+        if (!h->profiling) return;
+        AfvContext::Span sp;
+        sp.stage = stage;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!h->event_pool.empty()) { e = h->event_pool.back(); h->event_pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        sp.a = get(); sp.b = get();
+        cudaEventRecord(sp.a, h->stream);
+        h->spans.push_back(sp);
+        idx = (int)h->spans.size() - 1;
+    }
+    ~StageTimer() {
+        if (idx >= 0) cudaEventRecord(h->spans[idx].b, h->stream);
+    }
+};
+
+void collect_spans(AfvHandle h) {
+    if (h->spans.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    for (auto &sp : h->spans) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, sp.a, sp.b);
+        h->stage_ms[sp.stage] += ms;
+        h->stage_launches[sp.stage] += 1;
+        h->event_pool.push_back(sp.a); h->event_pool.push_back(sp.b);
+    }
+    h->spans.clear();
+}
+
+RingView ring_view(AfvHandle h) { return RingView{h->rs, h->ro, h->ring_len, h->ovf_index, h->ovf_len, h->ovf_rs, h->ovf_ro}; }
+
+PhysDev phys_dev(const AfvParams &p) { return PhysDev{p.r, p.P0, p.KA, p.KP, p.Lambda, p.delta}; }
+
+int upload_grid_periodic(AfvHandle h) {
+    GridDesc g{};
+    const double cut = 2.0 * h->prm.r;
+    int nb = (int)std::floor(h->L / cut);
+    if (nb < 1) nb = 1;
+    while ((int64_t)nb * nb > h->nbins_cap) --nb;
+    g.x0 = 0.0; g.y0 = 0.0; g.inv_bx = g.inv_by = (double)nb / h->L; g.L = h->L; g.halfL = 0.5 * h->L;
+    g.nbx = g.nby = nb; g.periodic = 1; g.pad = 0;
+    CK(cudaMemcpyAsync(h->d_grid, &g, sizeof g, cudaMemcpyHostToDevice, h->stream));
+    return AFV_OK;
+}
+
+// bin + sort + reorder + bin starts
+int stage_sort(AfvHandle h) {
+    StageTimer t(h, 0);
+    const int n = (int)h->n;
+    const int c = h->cur, o = 1 - c;
+    if (h->L > 0.0) {
+        int rc = upload_grid_periodic(h);
+        if (rc) return rc;
+    } else {
+        int nb = std::min(nblk(n, 256), 1024);
+        k_bbox_partial<<<nb, 256, 0, h->stream>>>(h->x[c], h->y[c], n, h->bbox_part);
+        k_bbox_final<<<1, 32, 0, h->stream>>>(h->bbox_part, nb, h->prm.r, h->nbins_cap, h->d_grid);
+        h->launches += 2;
+    }
+    k_bin_keys<<<nblk(n, 256), 256, 0, h->stream>>>(h->x[c], h->y[c], n, h->d_grid, h->keys);
+    size_t tmp = h->cub_tmp_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->keys, h->keys_sorted, h->iota, h->perm, n, 0, h->key_bits, h->stream));
+    k_reorder<<<nblk(n, 256), 256, 0, h->stream>>>(h->perm, n, h->x[c], h->y[c], h->th[c], h->a0[c], h->gid[c], h->owned[c],
+                                                    h->x[o], h->y[o], h->th[o], h->a0[o], h->gid[o], h->owned[o]);
+    h->cur = o;
+    // the number of bins is a device-side quantity in the open case: launch for the capacity, threads beyond
+    // nbx*nby exit immediately
+    int64_t nb_launch = (h->L > 0.0) ? 0 : (int64_t)h->nbins_cap + 1;
+    if (h->L > 0.0) {
+        const double cut = 2.0 * h->prm.r;
+        int64_t nb1 = (int64_t)std::floor(h->L / cut);
+        if (nb1 < 1) nb1 = 1;
+        while (nb1 * nb1 > h->nbins_cap) --nb1;
+        nb_launch = nb1 * nb1 + 1;
+        h->h_flags[3] = (int)(nb1 * nb1);
+    }
+    k_bin_start<<<nblk(nb_launch, 256), 256, 0, h->stream>>>(h->keys_sorted, n, h->d_grid, h->bin_start);
+    h->launches += 4;  // keys, sort (counted once), reorder, bin_start
+    CK(cudaGetLastError());
+    return AFV_OK;
+}
+
+int stage_geometry(AfvHandle h) {
+    StageTimer t(h, 1);
+    const int n = (int)h->n;
+    const int c = h->cur;
+    GeomArgs a;
+    a.x = h->x[c]; a.y = h->y[c]; a.a0 = h->a0[c]; a.keys = h->keys_sorted; a.bin_start = h->bin_start; a.grid = h->d_grid;
+    a.n = n; a.ph = phys_dev(h->prm); a.rs = h->rs; a.ro = h->ro; a.ring_len = h->ring_len;
+    a.area = h->area; a.perim = h->perim; a.arcl = h->arcl; a.coord = h->coord; a.flags = h->flags;
+    a.ovf_cells = h->ovf_cells; a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
+    k_geometry<KPOLY, RS><<<nblk(n), TPB, 0, h->stream>>>(a);
+    // cells queued by the fast kernel (usually none): large-capacity path, reads the queue length on the device
+    k_geometry_slow<<<16, 64, 0, h->stream>>>(a);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return AFV_OK;
+}
+
+int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, double Dr, uint64_t seed, int64_t step,
+                const double *noise_row) {
+    StageTimer t(h, 2);
+    const int n = (int)h->n;
+    const int c = h->cur;
+    ForceArgs a;
+    a.rs = h->rs; a.ro = h->ro; a.ring_len = h->ring_len; a.owned = h->owned[c]; a.gid = h->gid[c]; a.n = n;
+    a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
+    a.ph = phys_dev(h->prm); a.fx = h->fx; a.fy = h->fy; a.flags = h->flags;
+    a.do_step = do_step ? 1 : 0; a.x = h->x[c]; a.y = h->y[c]; a.theta = h->th[c];
+    a.dt = dt; a.mu = mu; a.v0 = v0; a.noise_amp = std::sqrt(2.0 * Dr * dt); a.seed = seed; a.step = step;
+    a.noise = noise_row; a.L = h->L;
+    k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return AFV_OK;
+}
+
+int check_flags(AfvHandle h) {
+    int f[4];
+    CK(cudaMemcpyAsync(f, h->flags, sizeof f, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->h_flags[0] = f[0]; h->h_flags[1] = f[1]; h->h_flags[2] = f[2];
+    if (f[3] > 0) {
+        char buf[200];
+        snprintf(buf, sizeof buf, "%d cell(s) exceeded every capacity (slow path: ring %d, polygon %d, at most %d cells per build)",
+                 f[3], RS_SLOW, KPOLY_SLOW, OVF_MAX);
+        h->err = buf;
+        return AFV_ERR_CAPACITY;
+    }
+    return AFV_OK;
+}
+
+int require_built(AfvHandle h) {
+    if (!h->built) { h->err = "no geometry on the device: call afv_build first"; return AFV_ERR_STATE; }
+    return AFV_OK;
+}
+
+int get_unsorted(AfvHandle h, const double *src, double *out_host, int stride, int comp_count, const double *src2) {
+    // scatter to caller order into scratch, then D2H
+    const int n = (int)h->n;
+    if (!h->gid_is_perm) { h->err = "results in caller order are only defined for handles filled by afv_set_positions"; return AFV_ERR_STATE; }
+    int rc = ensure_buf(h, h->scratch_a, (size_t)n * stride * sizeof(double));
+    if (rc) return rc;
+    double *tmp = (double *)h->scratch_a.p;
+    k_unsort_f64<<<nblk(n, 256), 256, 0, h->stream>>>(src, h->gid[h->cur], n, tmp, stride, 0);
+    if (comp_count == 2) k_unsort_f64<<<nblk(n, 256), 256, 0, h->stream>>>(src2, h->gid[h->cur], n, tmp, stride, 1);
+    h->launches += comp_count;
+    CK(cudaMemcpyAsync(out_host, tmp, (size_t)n * stride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AFV_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" {
+
+const char *afv_build_info(void) {
+    static char buf[160];
+    snprintf(buf, sizeof buf, "afv_b200 sm_100a; ring_stride=%d; polygon_capacity=%d; cuda_runtime=%d", RS, KPOLY, CUDART_VERSION);
+    return buf;
+}
+
+const char *afv_last_error(AfvHandle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int afv_create(int device, const AfvParams *params, double box_L, void *stream, AfvHandle *out) {
+    if (!params || !out) { g_create_error = "null argument"; return AFV_ERR_ARG; }
+    if (!(params->r > 0.0)) { g_create_error = "r must be positive"; return AFV_ERR_ARG; }
+    if (box_L < 0.0 || (box_L > 0.0 && box_L < 4.0 * params->r)) { g_create_error = "periodic box side must be >= 4 r"; return AFV_ERR_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+        return AFV_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device ordinal out of range"; return AFV_ERR_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return AFV_ERR_CUDA; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major < 10) {
+        g_create_error = std::string("device '") + prop.name + "' is not sm_100-class; this library is built for sm_100a only";
+        return AFV_ERR_CUDA;
+    }
+    AfvHandle h = new AfvContext();
+    h->device = device; h->prm = *params; h->L = box_L;
+    if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
+    else {
+        e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete h; return AFV_ERR_CUDA; }
+        h->own_stream = true;
+    }
+    if (cudaMalloc((void **)&h->d_grid, sizeof(GridDesc)) != cudaSuccess || cudaMalloc((void **)&h->flags, 4 * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&h->bbox_part, 4 * 1024 * sizeof(double)) != cudaSuccess) {
+        g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
+    }
+    if (cudaMalloc((void **)&h->ovf_cells, OVF_MAX * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->ovf_len, OVF_MAX * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&h->ovf_rs, (size_t)OVF_MAX * RS_SLOW * sizeof(RingShared)) != cudaSuccess ||
+        cudaMalloc((void **)&h->ovf_ro, (size_t)OVF_MAX * RS_SLOW * sizeof(RingOwn)) != cudaSuccess) {
+        g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
+    }
+    cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream);
+    *out = h;
+    return AFV_OK;
+}
+
+void afv_destroy(AfvHandle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_all(h);
+    cudaFree(h->d_grid); cudaFree(h->flags); cudaFree(h->bbox_part);
+    cudaFree(h->ovf_cells); cudaFree(h->ovf_len); cudaFree(h->ovf_rs); cudaFree(h->ovf_ro);
+    for (DevBuf *b : {&h->scratch_a, &h->scratch_b, &h->noise_buf, &h->conn_buf, &h->ring_types, &h->ring_xy, &h->ring_off}) cudaFree(b->p);
+    for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : h->event_pool) cudaEventDestroy(e);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int afv_set_params(AfvHandle h, const AfvParams *p) {
+    CHECK_H(h);
+    if (!p || !(p->r > 0.0)) { h->err = "invalid params"; return AFV_ERR_ARG; }
+    if (h->L > 0.0 && h->L < 4.0 * p->r) { h->err = "periodic box side must be >= 4 r"; return AFV_ERR_ARG; }
+    h->prm = *p;
+    h->built = false;
+    return AFV_OK;
+}
+
+int64_t afv_num_cells(AfvHandle h) { return h ? h->n : 0; }
+int64_t afv_num_owned(AfvHandle h) { return h ? h->n_owned : 0; }
+
+int afv_set_positions(AfvHandle h, const double *xy_host, int64_t N) {
+    CHECK_H(h);
+    if (N < 0 || (N > 0 && !xy_host)) { h->err = "invalid positions"; return AFV_ERR_ARG; }
+    const bool same = (N == h->n) && h->gid_is_perm && h->n_owned == h->n && h->cap > 0;
+    int rc;
+    if (!same) {
+        if ((rc = reserve(h, N, 0))) return rc;
+    }
+    const int n = (int)N;
+    const int c = h->cur, o = 1 - c;
+    if ((rc = ensure_buf(h, h->scratch_a, (size_t)std::max<int64_t>(N, 1) * 2 * sizeof(double)))) return rc;
+    if (N > 0) CK(cudaMemcpyAsync(h->scratch_a.p, xy_host, (size_t)N * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (same && N > 0) {
+        // bring theta and A0 back to the caller's order, then reset the order
+        k_unsort_f64<<<nblk(n, 256), 256, 0, h->stream>>>(h->th[c], h->gid[c], n, h->th[o], 1, 0);
+        k_unsort_f64<<<nblk(n, 256), 256, 0, h->stream>>>(h->a0[c], h->gid[c], n, h->a0[o], 1, 0);
+        h->cur = o;
+        h->launches += 2;
+    } else if (N > 0) {
+        k_fill<<<nblk(n, 256), 256, 0, h->stream>>>(h->th[h->cur], n, 0.0);
+        k_fill<<<nblk(n, 256), 256, 0, h->stream>>>(h->a0[h->cur], n, h->prm.A0);
+        h->launches += 2;
+    }
+    if (N > 0) {
+        k_init_cells<<<nblk(n, 256), 256, 0, h->stream>>>((const double *)h->scratch_a.p, n, h->x[h->cur], h->y[h->cur], h->gid[h->cur], h->owned[h->cur]);
+        h->launches += 1;
+    }
+    h->n = N; h->n_owned = N; h->gid_is_perm = true; h->built = false;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));  // xy_host is borrowed for the call only
+    return AFV_OK;
+}
+
+static int set_per_cell(AfvHandle h, const double *host, int64_t N, double *const *field) {
+    if (N != h->n || !host) { h->err = "array length does not match the number of cells"; return AFV_ERR_ARG; }
+    if (!h->gid_is_perm) { h->err = "per-cell setters need a handle filled by afv_set_positions"; return AFV_ERR_STATE; }
+    if (N == 0) return AFV_OK;
+    int rc = ensure_buf(h, h->scratch_a, (size_t)N * sizeof(double));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->scratch_a.p, host, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_gather_by_gid<<<nblk(N, 256), 256, 0, h->stream>>>((const double *)h->scratch_a.p, h->gid[h->cur], (int)N, field[h->cur]);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return AFV_OK;
+}
+
+int afv_set_preferred_areas(AfvHandle h, const double *a0_host, int64_t N) {
+    CHECK_H(h);
+    h->built = false;
+    return set_per_cell(h, a0_host, N, h->a0);
+}
+
+int afv_set_theta(AfvHandle h, const double *theta_host, int64_t N) {
+    CHECK_H(h);
+    return set_per_cell(h, theta_host, N, h->th);
+}
+
+int afv_build(AfvHandle h, unsigned flags) {
+    CHECK_H(h);
+    h->n_conn = -1; h->n_ring = -1;
+    if (h->n == 0) { h->built = true; h->n_conn = 0; h->n_ring = 0; return AFV_OK; }
+    int rc;
+    CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
+    if ((rc = stage_sort(h))) return rc;
+    if ((rc = stage_geometry(h))) return rc;
+    if ((rc = stage_force(h, false, 0, 0, 0, 0, 0, 0, nullptr))) return rc;
+    if ((rc = check_flags(h))) return rc;
+    h->built = true;
+    const int n = (int)h->n;
+    const int c = h->cur;
+    if (flags & AFV_BUILD_CONNECT) {
+        StageTimer t(h, 3);
+        k_conn_count<<<nblk(n), TPB, 0, h->stream>>>(ring_view(h), h->gid[c], h->owned[c], n, h->cnt);
+        size_t tmp = h->cub_tmp_bytes;
+        CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp, tmp, h->cnt, h->off, n + 1, h->stream));
+        int total = 0;
+        CK(cudaMemcpyAsync(&total, h->off + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if ((rc = ensure_buf(h, h->conn_buf, (size_t)std::max(total, 1) * 2 * sizeof(int64_t)))) return rc;
+        k_conn_emit<<<nblk(n), TPB, 0, h->stream>>>(ring_view(h), h->gid[c], h->owned[c], n, h->off, (int64_t *)h->conn_buf.p);
+        h->n_conn = total;
+        h->launches += 3;
+    }
+    if (flags & AFV_BUILD_RINGS) {
+        if (!h->gid_is_perm) { h->err = "ring export needs a handle filled by afv_set_positions"; return AFV_ERR_STATE; }
+        StageTimer t(h, 3);
+        k_ring_len_by_gid<<<nblk(n, 256), 256, 0, h->stream>>>(ring_view(h), h->gid[c], n, h->cnt);
+        CK(cudaMemsetAsync(h->cnt + n, 0, sizeof(int), h->stream));
+        size_t tmp = h->cub_tmp_bytes;
+        CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp, tmp, h->cnt, h->off, n + 1, h->stream));
+        int total = 0;
+        CK(cudaMemcpyAsync(&total, h->off + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if ((rc = ensure_buf(h, h->ring_types, (size_t)std::max(total, 1)))) return rc;
+        if ((rc = ensure_buf(h, h->ring_xy, (size_t)std::max(total, 1) * 2 * sizeof(double)))) return rc;
+        if ((rc = ensure_buf(h, h->ring_off, (size_t)(n + 1) * sizeof(int)))) return rc;
+        CK(cudaMemcpyAsync(h->ring_off.p, h->off, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+        k_ring_emit<<<nblk(n), TPB, 0, h->stream>>>(ring_view(h), h->gid[c], h->x[c], h->y[c], n, (const int *)h->ring_off.p,
+                                                    (signed char *)h->ring_types.p, (double *)h->ring_xy.p);
+        h->n_ring = total;
+        h->launches += 3;
+    }
+    CK(cudaGetLastError());
+    return AFV_OK;
+}
+
+int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t seed, int64_t step0, int n_steps,
+             const double *noise_host) {
+    CHECK_H(h);
+    if (n_steps < 0 || Dr < 0.0 || !(dt >= 0.0)) { h->err = "invalid step arguments"; return AFV_ERR_ARG; }
+    if (h->n == 0 || n_steps == 0) return AFV_OK;
+    int rc;
+    const double *noise_dev = nullptr;
+    if (noise_host) {
+        if (!h->gid_is_perm) { h->err = "a recorded noise stream needs a handle filled by afv_set_positions"; return AFV_ERR_STATE; }
+        size_t bytes = (size_t)n_steps * (size_t)h->n * sizeof(double);
+        if ((rc = ensure_buf(h, h->noise_buf, bytes))) return rc;
+        CK(cudaMemcpyAsync(h->noise_buf.p, noise_host, bytes, cudaMemcpyHostToDevice, h->stream));
+        noise_dev = (const double *)h->noise_buf.p;
+    }
+    CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
+    for (int s = 0; s < n_steps; ++s) {
+        if ((rc = stage_sort(h))) return rc;
+        if ((rc = stage_geometry(h))) return rc;
+        if ((rc = stage_force(h, true, dt, mu, v0, Dr, seed, step0 + s, noise_dev ? noise_dev + (size_t)s * h->n : nullptr))) return rc;
+    }
+    if ((rc = check_flags(h))) return rc;   // also synchronises: noise_host is borrowed for the call only
+    h->built = true;
+    h->n_conn = -1; h->n_ring = -1;
+    return AFV_OK;
+}
+
+double afv_philox_normal(uint64_t seed, int64_t cell_id, int64_t step) { return philox_normal(seed, cell_id, step); }
+
+int afv_get_positions(AfvHandle h, double *out) {
+    CHECK_H(h);
+    if (h->n == 0) return AFV_OK;
+    return get_unsorted(h, h->x[h->cur], out, 2, 2, h->y[h->cur]);
+}
+int afv_get_theta(AfvHandle h, double *out) {
+    CHECK_H(h);
+    if (h->n == 0) return AFV_OK;
+    return get_unsorted(h, h->th[h->cur], out, 1, 1, nullptr);
+}
+int afv_get_forces(AfvHandle h, double *out) {
+    CHECK_H(h);
+    int rc = require_built(h); if (rc) return rc;
+    if (h->n == 0) return AFV_OK;
+    return get_unsorted(h, h->fx, out, 2, 2, h->fy);
+}
+int afv_get_areas(AfvHandle h, double *out) {
+    CHECK_H(h);
+    int rc = require_built(h); if (rc) return rc;
+    if (h->n == 0) return AFV_OK;
+    return get_unsorted(h, h->area, out, 1, 1, nullptr);
+}
+int afv_get_perimeters(AfvHandle h, double *out) {
+    CHECK_H(h);
+    int rc = require_built(h); if (rc) return rc;
+    if (h->n == 0) return AFV_OK;
+    return get_unsorted(h, h->perim, out, 1, 1, nullptr);
+}
+int afv_get_arclens(AfvHandle h, double *out) {
+    CHECK_H(h);
+    int rc = require_built(h); if (rc) return rc;
+    if (h->n == 0) return AFV_OK;
+    return get_unsorted(h, h->arcl, out, 1, 1, nullptr);
+}
+int afv_get_coord_nums(AfvHandle h, int64_t *out) {
+    CHECK_H(h);
+    int rc = require_built(h); if (rc) return rc;
+    if (h->n == 0) return AFV_OK;
+    if (!h->gid_is_perm) { h->err = "results in caller order are only defined for handles filled by afv_set_positions"; return AFV_ERR_STATE; }
+    const int n = (int)h->n;
+    if ((rc = ensure_buf(h, h->scratch_a, (size_t)n * sizeof(int64_t)))) return rc;
+    k_unsort_i32_to_i64<<<nblk(n, 256), 256, 0, h->stream>>>(h->coord, h->gid[h->cur], n, (int64_t *)h->scratch_a.p);
+    h->launches += 1;
+    CK(cudaMemcpyAsync(out, h->scratch_a.p, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AFV_OK;
+}
+
+int afv_get_num_connections(AfvHandle h, int64_t *K) {
+    CHECK_H(h);
+    if (h->n_conn < 0) { h->err = "no contact list: call afv_build with AFV_BUILD_CONNECT"; return AFV_ERR_STATE; }
+    *K = h->n_conn;
+    return AFV_OK;
+}
+int afv_get_connections(AfvHandle h, int64_t *pairs) {
+    CHECK_H(h);
+    if (h->n_conn < 0) { h->err = "no contact list: call afv_build with AFV_BUILD_CONNECT"; return AFV_ERR_STATE; }
+    if (h->n_conn > 0) {
+        CK(cudaMemcpyAsync(pairs, h->conn_buf.p, (size_t)h->n_conn * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return AFV_OK;
+}
+
+int afv_get_num_ring_entries(AfvHandle h, int64_t *T) {
+    CHECK_H(h);
+    if (h->n_ring < 0) { h->err = "no ring export: call afv_build with AFV_BUILD_RINGS"; return AFV_ERR_STATE; }
+    *T = h->n_ring;
+    return AFV_OK;
+}
+int afv_get_rings(AfvHandle h, int64_t *region_off, int8_t *edge_types, double *vertices_xy) {
+    CHECK_H(h);
+    if (h->n_ring < 0) { h->err = "no ring export: call afv_build with AFV_BUILD_RINGS"; return AFV_ERR_STATE; }
+    const int64_t n = h->n;
+    if (n == 0) { region_off[0] = 0; return AFV_OK; }
+    std::vector<int> off((size_t)n + 1);
+    CK(cudaMemcpyAsync(off.data(), h->ring_off.p, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h->n_ring > 0) {
+        CK(cudaMemcpyAsync(edge_types, h->ring_types.p, (size_t)h->n_ring, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(vertices_xy, h->ring_xy.p, (size_t)h->n_ring * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i <= n; ++i) region_off[i] = off[(size_t)i];
+    return AFV_OK;
+}
+
+int afv_get_diagnostics(AfvHandle h, int64_t out[4]) {
+    CHECK_H(h);
+    for (int i = 0; i < 4; ++i) out[i] = h->h_flags[i];
+    return AFV_OK;
+}
+
+int afv_set_profiling(AfvHandle h, int enabled) {
+    CHECK_H(h);
+    collect_spans(h);
+    h->profiling = enabled != 0;
+    return AFV_OK;
+}
+
+int afv_get_stage_times(AfvHandle h, double ms_out[4], int64_t launches_out[4], int reset) {
+    CHECK_H(h);
+    collect_spans(h);
+    for (int i = 0; i < 4; ++i) { ms_out[i] = h->stage_ms[i]; launches_out[i] = h->stage_launches[i]; }
+    if (reset) for (int i = 0; i < 4; ++i) { h->stage_ms[i] = 0; h->stage_launches[i] = 0; }
+    return AFV_OK;
+}
+
+int64_t afv_launch_count(AfvHandle h) { return h ? h->launches : 0; }
+
+void *afv_host_alloc(int64_t bytes) {
+    void *p = nullptr;
+    if (bytes <= 0) bytes = 1;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void afv_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int afv_measure_fp64_peak(AfvHandle h, double *tflops_out) {
+    CHECK_H(h);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    int rc = ensure_buf(h, h->scratch_b, (size_t)blocks * threads * sizeof(double));
+    if (rc) return rc;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a, h->stream);
+        k_dfma_peak<<<blocks, threads, 0, h->stream>>>((double *)h->scratch_b.p, iters);
+        cudaEventRecord(b, h->stream);
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        double fl = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    h->launches += 5;
+    *tflops_out = best;
+    return AFV_OK;
+}
+
+void *afv_device_ptr(AfvHandle h, int field) {
+    if (!h) return nullptr;
+    const int c = h->cur;
+    switch (field) {
+        case AFV_F_X: return h->x[c];
+        case AFV_F_Y: return h->y[c];
+        case AFV_F_THETA: return h->th[c];
+        case AFV_F_A0: return h->a0[c];
+        case AFV_F_GID: return h->gid[c];
+        case AFV_F_FX: return h->fx;
+        case AFV_F_FY: return h->fy;
+        case AFV_F_AREA: return h->area;
+        case AFV_F_PERIM: return h->perim;
+        case AFV_F_ARCLEN: return h->arcl;
+        case AFV_F_COORD: return h->coord;
+        case AFV_F_OWNED: return h->owned[c];
+        default: return nullptr;
+    }
+}
+
+void *afv_stream(AfvHandle h) { return h ? (void *)h->stream : nullptr; }
+
+int afv_synchronize(AfvHandle h) {
+    CHECK_H(h);
+    CK(cudaStreamSynchronize(h->stream));
+    return AFV_OK;
+}
+
+// ---- slab sharding primitives ----
+#include "afv_shard.inc"
+
+}  // extern "C"

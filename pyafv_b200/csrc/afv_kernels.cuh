@@ -1,0 +1,586 @@
+// The kernels of the AFV hot path (sm_100a): bin -> (radix sort) -> reorder -> geometry -> force(+step).
+#pragma once
+#include "afv_device.cuh"
+
+namespace afv {
+
+struct PhysDev {
+    double r, P0, KA, KP, Lambda, delta;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// K0: bounding box (open boundaries) -> grid description, entirely on the device
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_bbox_partial(const double *__restrict__ x, const double *__restrict__ y, int n, double *__restrict__ part) {
+    // part: [4 * gridDim.x] = xmin, xmax, ymin, ymax per block
+    __shared__ double sm[4][32];
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double a = x[i], b = y[i];
+        xmin = fmin(xmin, a); xmax = fmax(xmax, a); ymin = fmin(ymin, b); ymax = fmax(ymax, b);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sm[0][w] = xmin; sm[1][w] = xmax; sm[2][w] = ymin; sm[3][w] = ymax; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+        xmin = l < nw ? sm[0][l] : 1e300; xmax = l < nw ? sm[1][l] : -1e300;
+        ymin = l < nw ? sm[2][l] : 1e300; ymax = l < nw ? sm[3][l] : -1e300;
+        for (int o = 16; o > 0; o >>= 1) {
+            xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+            xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+            ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        }
+        if (l == 0) { part[4 * blockIdx.x] = xmin; part[4 * blockIdx.x + 1] = xmax; part[4 * blockIdx.x + 2] = ymin; part[4 * blockIdx.x + 3] = ymax; }
+    }
+}
+
+__global__ void k_bbox_final(const double *__restrict__ part, int nblocks, double r, int nbins_cap, GridDesc *__restrict__ g) {
+    // one warp
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    for (int i = threadIdx.x; i < nblocks; i += 32) {
+        xmin = fmin(xmin, part[4 * i]); xmax = fmax(xmax, part[4 * i + 1]);
+        ymin = fmin(ymin, part[4 * i + 2]); ymax = fmax(ymax, part[4 * i + 3]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if (threadIdx.x == 0) {
+        const double cut = 2.0 * r;
+        double sx = xmax - xmin, sy = ymax - ymin;
+        double fx = floor(sx / cut) + 1.0, fy = floor(sy / cut) + 1.0;
+        // keep nbx * nby <= nbins_cap by coarsening the larger direction
+        while (fx * fy > (double)nbins_cap) { if (fx >= fy) fx = ceil(fx * 0.5); else fy = ceil(fy * 0.5); }
+        int nbx = (int)fx, nby = (int)fy;
+        double bsx = fmax(cut, sx / (double)nbx), bsy = fmax(cut, sy / (double)nby);
+        g->x0 = xmin; g->y0 = ymin; g->inv_bx = 1.0 / bsx; g->inv_by = 1.0 / bsy;
+        g->L = 0.0; g->halfL = 0.0; g->nbx = nbx; g->nby = nby; g->periodic = 0; g->pad = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1a: bin hash.  key = by * nbx + bx  (row-major so that the 3 bins of a row are contiguous after the sort)
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_bin_keys(const double *__restrict__ x, const double *__restrict__ y, int n,
+                           const GridDesc *__restrict__ gp, unsigned *__restrict__ keys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GridDesc g = *gp;
+    int bx = (int)floor((x[i] - g.x0) * g.inv_bx), by = (int)floor((y[i] - g.y0) * g.inv_by);
+    bx = min(max(bx, 0), g.nbx - 1);
+    by = min(max(by, 0), g.nby - 1);
+    keys[i] = (unsigned)(by * g.nbx + bx);
+}
+
+// K1b: gather the SoA state into sorted order
+__global__ void k_reorder(const int *__restrict__ perm, int n, const double *__restrict__ x0, const double *__restrict__ y0,
+                          const double *__restrict__ t0, const double *__restrict__ a0, const int64_t *__restrict__ g0,
+                          const unsigned char *__restrict__ o0, double *__restrict__ x1, double *__restrict__ y1,
+                          double *__restrict__ t1, double *__restrict__ a1, int64_t *__restrict__ g1,
+                          unsigned char *__restrict__ o1) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int p = perm[s];
+    x1[s] = x0[p]; y1[s] = y0[p]; t1[s] = t0[p]; a1[s] = a0[p]; g1[s] = g0[p]; o1[s] = o0[p];
+}
+
+// K1c: first sorted slot of every bin (lower bound), bin_start[nbins] = n
+__global__ void k_bin_start(const unsigned *__restrict__ keys_sorted, int n, const GridDesc *__restrict__ gp,
+                            int *__restrict__ bin_start) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int nb = gp->nbx * gp->nby;
+    if (b > nb) return;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (keys_sorted[mid] < (unsigned)b) lo = mid + 1; else hi = mid;
+    }
+    bin_start[b] = lo;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2: geometry.  One thread per cell (sorted slot).  Clip the bounding square by the bisectors of all
+// neighbours within 2r, walk the polygon clockwise to emit the ring exactly as the reference defines it
+// (finite_voronoi.py:363-459), then area / perimeter / arc length (cell_geom.pyx:432-475) and the per-vertex
+// energy gradients of THIS cell (cell_geom.pyx:478-539), written as fixed-stride ring records.
+// ------------------------------------------------------------------------------------------------------
+struct GeomArgs {
+    const double *x, *y, *a0;
+    const unsigned *keys;      // sorted
+    const int *bin_start;
+    const GridDesc *grid;
+    int n;
+    PhysDev ph;
+    RingShared *rs;
+    RingOwn *ro;
+    unsigned char *ring_len;
+    double *area, *perim, *arcl;
+    int *coord;
+    int *flags;                // [0] cells sent to the slow path, [1] lookup misses, [2] max ring length, [3] hard overflows
+    // slow path (cells whose polygon / ring exceeds the fast-path capacity)
+    int *ovf_cells;            // [OVF_MAX] sorted slots queued by the fast kernel
+    int *ovf_index;            // [n] slot -> pool index, valid where ring_len == RING_IN_POOL
+    int *ovf_len;              // [OVF_MAX] ring length of pooled rings
+    RingShared *ovf_rs;        // [OVF_MAX * RS_SLOW]
+    RingOwn *ovf_ro;
+};
+
+// Geometry of one cell.  SLOW = false: fast path, capacity (K, R) = (KPOLY, RS); on overflow the cell is queued.
+// SLOW = true: large capacity; rings longer than RS go to the overflow pool at index `pool_idx`.
+template <int K, int R, bool SLOW>
+__device__ __forceinline__ void geom_cell(const GeomArgs &a, const int s, const int pool_idx) {
+    const double r = a.ph.r, r2 = r * r, cut2 = 4.0 * r2;
+    const double xi = a.x[s], yi = a.y[s];
+    const GridDesc g = *a.grid;
+    const unsigned key = a.keys[s];
+    const int by = (int)(key / (unsigned)g.nbx), bx = (int)(key - (unsigned)by * (unsigned)g.nbx);
+
+    // bounding square of half side B = 2r as four virtual bisectors (virtual neighbours at distance 4r)
+    double vx[K], vy[K], px[K], py[K];
+    int lab[K];
+    const double B = 2.0 * r;
+    vx[0] = -B; vy[0] = -B; px[0] = 0.0;      py[0] = -2.0 * B; lab[0] = -2;
+    vx[1] = B;  vy[1] = -B; px[1] = 2.0 * B;  py[1] = 0.0;      lab[1] = -2;
+    vx[2] = B;  vy[2] = B;  px[2] = 0.0;      py[2] = 2.0 * B;  lab[2] = -2;
+    vx[3] = -B; vy[3] = B;  px[3] = -2.0 * B; py[3] = 0.0;      lab[3] = -2;
+    int m = 4;
+    bool ok = true;
+
+    const int nrow = (g.periodic && g.nby < 3) ? g.nby : 3;
+    const int ncol = (g.periodic && g.nbx < 3) ? g.nbx : 3;
+    for (int ir = 0; ir < nrow; ++ir) {
+        int row = (nrow == 3) ? by + ir - 1 : ir;
+        if (g.periodic) { if (row < 0) row += g.nby; else if (row >= g.nby) row -= g.nby; }
+        else if (row < 0 || row >= g.nby) continue;
+        for (int ic = 0; ic < ncol; ++ic) {
+            int col = (ncol == 3) ? bx + ic - 1 : ic;
+            if (g.periodic) { if (col < 0) col += g.nbx; else if (col >= g.nbx) col -= g.nbx; }
+            else if (col < 0 || col >= g.nbx) continue;
+            const int b = row * g.nbx + col;
+            const int c0 = a.bin_start[b], c1 = a.bin_start[b + 1];
+            for (int c = c0; c < c1; ++c) {
+                if (c == s) continue;
+                double dx = a.x[c] - xi, dy = a.y[c] - yi;
+                if (g.periodic) { dx = min_image(dx, g.L, g.halfL); dy = min_image(dy, g.L, g.halfL); }
+                const double d2 = dx * dx + dy * dy;
+                if (d2 >= cut2) continue;
+                ok = ok && clip_polygon<K>(vx, vy, px, py, lab, m, dx, dy, 0.5 * d2, c);
+            }
+        }
+    }
+
+    // ---- ring, clockwise: edge k of the ccw polygon is walked from vertex k+1 to vertex k ----
+    double hx[R], hy[R], qx[R], qy[R];
+    int typ[R], nbr[R];
+    int E = 0;
+    for (int kk = 0; kk < m; ++kk) {
+        const int k = m - 1 - kk;
+        const int j = lab[k];
+        if (j < 0) continue;                       // side of the bounding square (the reference's ray-ray pair)
+        const int k1 = (k + 1 == m) ? 0 : k + 1;
+        const double V1x = vx[k1], V1y = vy[k1], V2x = vx[k], V2y = vy[k];
+        const double ex = px[k], ey = py[k];
+        if (E + 2 > R) { ok = false; break; }      // an edge emits at most 2 entries
+        if (sqrt(V1x * V1x + V1y * V1y) <= r) {    // inner start vertex: d1 <= r  (finite_voronoi.py:375-377)
+            hx[E] = V1x; hy[E] = V1y; qx[E] = ex; qy[E] = ey; typ[E] = 1; nbr[E] = j; ++E;
+        }
+        const double Cx = 0.5 * ex, Cy = 0.5 * ey;
+        const double d2c = Cx * Cx + Cy * Cy;
+        if (sqrt(d2c) < r) {                        // bisector crosses the disk (finite_voronoi.py:395-407)
+            const double dVx = V2x - V1x, dVy = V2y - V1y;
+            const double segL = sqrt(dVx * dVx + dVy * dVy);
+            const double den = segL > 0.0 ? segL : 1.0;
+            const double t1 = (V1x * dVx + V1y * dVy) / den, t2 = t1 + den;
+            const double tr = sqrt(r2 - d2c);
+            const double ux = dVx / den, uy = dVy / den;
+            if (-tr < t2 && -tr > t1) {             // entry point: straight edge starts on the circle
+                hx[E] = Cx - tr * ux; hy[E] = Cy - tr * uy; qx[E] = ex; qy[E] = ey; typ[E] = 1; nbr[E] = j; ++E;
+            }
+            if (tr < t2 && tr > t1) {               // exit point: an arc starts here
+                hx[E] = Cx + tr * ux; hy[E] = Cy + tr * uy; qx[E] = ex; qy[E] = ey; typ[E] = 0; nbr[E] = ARC; ++E;
+            }
+        }
+    }
+
+    if (!ok) {
+        if (!SLOW) {  // queue the cell for the large-capacity kernel
+            const int idx = atomicAdd(&a.flags[0], 1);
+            if (idx < OVF_MAX) a.ovf_cells[idx] = s; else atomicAdd(&a.flags[3], 1);
+            a.ring_len[s] = 0;
+            return;
+        }
+        atomicAdd(&a.flags[3], 1);  // exceeded even the slow-path capacity: the host reports AFV_ERR_CAPACITY
+        E = 0;
+    }
+
+    // ---- measures (cell_geom.pyx:402-475) ----
+    const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
+    if (E < 2) {
+        a.area[s] = PI * r2; a.perim[s] = TWO_PI * r; a.arcl[s] = TWO_PI * r; a.coord[s] = 0;
+        a.ring_len[s] = 0;
+        return;
+    }
+    double ux_[R], uy_[R];   // unit vector (v1 - v2)/|v1 - v2| of straight edge e, 0 for arcs
+    double A = 0.0, P = 0.0, Larc = 0.0;
+    int z = 0;
+    for (int e = 0; e < E; ++e) {
+        const int e2 = (e + 1 == E) ? 0 : e + 1;
+        const double v1x = hx[e], v1y = hy[e], v2x = hx[e2], v2y = hy[e2];
+        if (typ[e] == 1) {
+            const double sx = v1x - v2x, sy = v1y - v2y;
+            const double l = sqrt(sx * sx + sy * sy);
+            P += l;
+            A += -0.5 * (v1x * v2y - v1y * v2x);
+            const double il = l > 0.0 ? 1.0 / l : 0.0;
+            ux_[e] = sx * il; uy_[e] = sy * il;
+            ++z;
+        } else {
+            double ang = atan2(v2x * v1y - v2y * v1x, v1x * v2x + v1y * v2y);  // angle(v1) - angle(v2)
+            if (ang < 0.0) ang += TWO_PI;
+            Larc += r * ang;
+            A += 0.5 * r2 * ang;
+            ux_[e] = 0.0; uy_[e] = 0.0;
+        }
+    }
+    P += Larc;
+    a.area[s] = A; a.perim[s] = P; a.arcl[s] = Larc; a.coord[s] = z;
+    RingShared *rs = a.rs + (size_t)s * RS;
+    RingOwn *ro = a.ro + (size_t)s * RS;
+    if (SLOW && E > RS) {
+        a.ring_len[s] = RING_IN_POOL; a.ovf_index[s] = pool_idx; a.ovf_len[pool_idx] = E;
+        rs = a.ovf_rs + (size_t)pool_idx * RS_SLOW; ro = a.ovf_ro + (size_t)pool_idx * RS_SLOW;
+    } else {
+        a.ring_len[s] = (unsigned char)E;
+    }
+    if (E > 12 || SLOW) atomicMax(&a.flags[2], E);
+
+    // ---- per-vertex gradients of this cell (cell_geom.pyx:478-539) ----
+    const double cA = 2.0 * a.ph.KA * (A - a.a0[s]);
+    const double cP = 2.0 * a.ph.KP * (P - a.ph.P0);
+    const double cL = cP + a.ph.Lambda;
+    for (int e = 0; e < E; ++e) {
+        const int e2 = (e + 1 == E) ? 0 : e + 1, e0 = (e == 0) ? E - 1 : e - 1;
+        // dA/dv1 = 0.5 (perp(v0) - perp(v2)), perp(u) = (uy, -ux);  dP/dv1 = u(e) - u(e-1)
+        const double gx = cA * 0.5 * (hy[e0] - hy[e2]) + cP * (ux_[e] - ux_[e0]);
+        const double gy = cA * 0.5 * (hx[e2] - hx[e0]) + cP * (uy_[e] - uy_[e0]);
+        double w = 0.0;
+        if (typ[e] == 0)        // an arc starts here: da = +0.5 r^2 (1 - cos D), dl = +r
+            w = cA * 0.5 * (r2 - (hx[e] * hx[e2] + hy[e] * hy[e2])) + cL * r;
+        else if (typ[e0] == 0)  // an arc ends here
+            w = -(cA * 0.5 * (r2 - (hx[e0] * hx[e] + hy[e0] * hy[e])) + cL * r);
+        RingShared o; o.nbr = nbr[e]; o.type = typ[e]; o.gx = gx; o.gy = gy; o.w = w;
+        rs[e] = o;
+        RingOwn q; q.hx = hx[e]; q.hy = hy[e]; q.px = qx[e]; q.py = qy[e];
+        ro[e] = q;
+    }
+}
+
+template <int K, int R>
+__global__ void __launch_bounds__(128) k_geometry(GeomArgs a) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n) return;
+    geom_cell<K, R, false>(a, s, 0);
+}
+
+// slow path: the (few) queued cells, one thread each, large local arrays
+__global__ void __launch_bounds__(64) k_geometry_slow(GeomArgs a) {
+    const int cnt = min(a.flags[0], OVF_MAX);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x)
+        geom_cell<KPOLY_SLOW, RS_SLOW, true>(a, a.ovf_cells[idx], idx);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K3: force gather (+ fused active-Langevin update).  One thread per cell walks its own ring; for every
+// contact edge it finds the edge back to itself in the neighbour's ring (<= RS keys) and reads the
+// neighbour's two records at the ends of the shared edge.  No atomics; summation order is the ring order.
+// ------------------------------------------------------------------------------------------------------
+struct ForceArgs {
+    const RingShared *rs;
+    const RingOwn *ro;
+    const unsigned char *ring_len;
+    const int *ovf_index, *ovf_len;
+    const RingShared *ovf_rs;
+    const RingOwn *ovf_ro;
+    const unsigned char *owned;
+    const int64_t *gid;
+    int n;
+    PhysDev ph;
+    double *fx, *fy;
+    int *flags;
+    // step (do_step != 0)
+    int do_step;
+    double *x, *y, *theta;
+    double dt, mu, v0, noise_amp;  // noise_amp = sqrt(2 Dr dt)
+    uint64_t seed;
+    int64_t step;
+    const double *noise;           // nullptr -> Philox; else row of this step, indexed by gid
+    double L;                      // periodic wrap (0 = none)
+};
+
+struct NbrRec { double gx, gy, w; };
+
+__device__ __forceinline__ bool lookup_edge(const ForceArgs &a, int j, int self, NbrRec &at_start, NbrRec &at_end) {
+    // edge (j -> self) in j's ring runs from slot t to slot t+1; seen from `self` the same edge runs the other
+    // way, so j's slot t is the END of self's edge and j's slot t+1 its START.
+    int Ej = a.ring_len[j];
+    const RingShared *rj = a.rs + (size_t)j * RS;
+    if (Ej == RING_IN_POOL) { const int pi = a.ovf_index[j]; Ej = a.ovf_len[pi]; rj = a.ovf_rs + (size_t)pi * RS_SLOW; }
+    for (int t = 0; t < Ej; ++t) {
+        const int2 kt = *reinterpret_cast<const int2 *>(&rj[t]);
+        if (kt.x == self && kt.y == 1) {
+            const int t1 = (t + 1 == Ej) ? 0 : t + 1;
+            at_end.gx = rj[t].gx; at_end.gy = rj[t].gy; at_end.w = rj[t].w;
+            at_start.gx = rj[t1].gx; at_start.gy = rj[t1].gy; at_start.w = rj[t1].w;
+            return true;
+        }
+    }
+    at_start.gx = at_start.gy = at_start.w = 0.0;
+    at_end.gx = at_end.gy = at_end.w = 0.0;
+    return false;
+}
+
+__global__ void __launch_bounds__(128) k_force(ForceArgs a) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n) return;
+    if (!a.owned[s]) { a.fx[s] = 0.0; a.fy[s] = 0.0; return; }
+    int E = a.ring_len[s];
+    const double r = a.ph.r, r2 = r * r;
+    double dEx = 0.0, dEy = 0.0;
+    if (E >= 2) {
+        const RingShared *rs = a.rs + (size_t)s * RS;
+        const RingOwn *ro = a.ro + (size_t)s * RS;
+        if (E == RING_IN_POOL) {
+            const int pi = a.ovf_index[s];
+            E = a.ovf_len[pi]; rs = a.ovf_rs + (size_t)pi * RS_SLOW; ro = a.ovf_ro + (size_t)pi * RS_SLOW;
+        }
+        int misses = 0;
+        // contribution of the last edge's neighbour to vertex 0
+        RingShared prev = rs[E - 1];
+        RingOwn prev_o = ro[E - 1];
+        NbrRec pend = {0.0, 0.0, 0.0}, tmp;
+        if (prev.type == 1) misses += !lookup_edge(a, prev.nbr, s, tmp, pend);
+        for (int e = 0; e < E; ++e) {
+            const RingShared cur = rs[e];
+            const RingOwn own = ro[e];
+            NbrRec cs = {0.0, 0.0, 0.0}, ce = {0.0, 0.0, 0.0};
+            if (cur.type == 1) misses += !lookup_edge(a, cur.nbr, s, cs, ce);
+            const double Gx = cur.gx + pend.gx + cs.gx, Gy = cur.gy + pend.gy + cs.gy;
+            const double hx = own.hx, hy = own.hy;
+            if (prev.type == 1 && cur.type == 1) {
+                // inner vertex = circumcentre(0, pa, pb): dh = eps (h . dr_i) / (pa . eps), eps = perp(pb - pa)
+                const double pax = prev_o.px, pay = prev_o.py, pbx = own.px, pby = own.py;
+                const double epx = -(pby - pay), epy = pbx - pax;
+                const double coef = (Gx * epx + Gy * epy) / (pax * epx + pay * epy);
+                dEx += coef * hx; dEy += coef * hy;
+            } else if (prev.type != cur.type) {
+                // outer vertex on the bisector with j (finite_voronoi.py:653-746)
+                const bool entry = (cur.type == 1);
+                const double pjx = entry ? own.px : prev_o.px, pjy = entry ? own.py : prev_o.py;
+                const double Wj = entry ? cs.w : pend.w, Wi = cur.w;
+                const double rho2 = pjx * pjx + pjy * pjy, rho = sqrt(rho2);
+                const double root = sqrt(fmax(4.0 * r2 - rho2, 0.0));
+                const double cr = pjx * hy - pjy * hx;
+                const double sg = (cr > 0.0) ? 1.0 : ((cr < 0.0) ? -1.0 : 0.0);
+                const double k1 = 2.0 * r2 / (fmax(root, a.ph.delta) * rho2 * rho);
+                const double k2 = root / (2.0 * rho);
+                // T_x = dx_terms, T_y = dy_terms of the reference with r_IJ = -p_j
+                const double Txx = -k1 * pjx * pjy,       Txy = k1 * pjx * pjx - k2;
+                const double Tyx = -k1 * pjy * pjy + k2,  Tyy = k1 * pjx * pjy;
+                // dh/dx_i = (1/2 + s Txx, s Txy), dh/dy_i = (s Tyx, 1/2 + s Tyy); dh/dr_j = e - dh/dr_i
+                const double hxi_x = 0.5 + sg * Txx, hxi_y = sg * Txy, hyi_x = sg * Tyx, hyi_y = 0.5 + sg * Tyy;
+                const double hxj_x = 0.5 - sg * Txx, hxj_y = -sg * Txy, hyj_x = -sg * Tyx, hyj_y = 0.5 - sg * Tyy;
+                dEx += Gx * hxi_x + Gy * hxi_y;
+                dEy += Gx * hyi_x + Gy * hyi_y;
+                // arc angles: theta_i of h about i, theta_j of h about j
+                const double ujx = hx - pjx, ujy = hy - pjy;
+                const double iui = 1.0 / (hx * hx + hy * hy), iuj = 1.0 / (ujx * ujx + ujy * ujy);
+                const double upix = -hy * iui, upiy = hx * iui, upjx = -ujy * iuj, upjy = ujx * iuj;
+                const double dti_x = -(hxj_x * upix + hxj_y * upiy), dti_y = -(hyj_x * upix + hyj_y * upiy);
+                const double dtj_x = hxi_x * upjx + hxi_y * upjy, dtj_y = hyi_x * upjx + hyi_y * upjy;
+                dEx += Wi * dti_x + Wj * dtj_x;
+                dEy += Wi * dti_y + Wj * dtj_y;
+            }
+            pend = ce; prev = cur; prev_o = own;
+        }
+        if (misses) atomicAdd(&a.flags[1], misses);
+    }
+    const double Fx = -dEx, Fy = -dEy;
+    a.fx[s] = Fx; a.fy[s] = Fy;
+    if (a.do_step) {
+        const double th = a.theta[s];
+        double sn, cs_;
+        sincos(th, &sn, &cs_);
+        double xn = a.x[s] + (a.mu * Fx + a.v0 * cs_) * a.dt;
+        double yn = a.y[s] + (a.mu * Fy + a.v0 * sn) * a.dt;
+        if (a.L > 0.0) {
+            xn -= a.L * floor(xn / a.L); yn -= a.L * floor(yn / a.L);
+            if (xn >= a.L) xn = 0.0;
+            if (yn >= a.L) yn = 0.0;
+        }
+        double xi_ = 0.0;
+        if (a.noise_amp != 0.0) {
+            const int64_t id = a.gid[s];
+            xi_ = a.noise ? a.noise[id] : philox_normal(a.seed, id, a.step);
+        }
+        a.x[s] = xn; a.y[s] = yn; a.theta[s] = th + a.noise_amp * xi_;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// small utility kernels
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_iota(int *p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
+
+__global__ void k_init_cells(const double *__restrict__ xy, int n, double *__restrict__ x, double *__restrict__ y,
+                             int64_t *__restrict__ gid, unsigned char *__restrict__ owned) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[i] = xy[2 * i]; y[i] = xy[2 * i + 1]; gid[i] = i; owned[i] = 1;
+}
+
+__global__ void k_fill(double *p, int n, double v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+// out[gid[s]] = src[s]   (back to the caller's order)
+__global__ void k_unsort_f64(const double *__restrict__ src, const int64_t *__restrict__ gid, int n, double *__restrict__ out,
+                             int stride, int comp) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) out[gid[s] * stride + comp] = src[s];
+}
+__global__ void k_unsort_i32_to_i64(const int *__restrict__ src, const int64_t *__restrict__ gid, int n, int64_t *__restrict__ out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) out[gid[s]] = (int64_t)src[s];
+}
+// dst[s] = src[gid[s]]   (caller's order -> current sorted order)
+__global__ void k_gather_by_gid(const double *__restrict__ src, const int64_t *__restrict__ gid, int n, double *__restrict__ dst) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) dst[s] = src[gid[s]];
+}
+
+// read-only view of all rings (regular fixed-stride storage + overflow pool)
+struct RingView {
+    const RingShared *rs;
+    const RingOwn *ro;
+    const unsigned char *ring_len;
+    const int *ovf_index, *ovf_len;
+    const RingShared *ovf_rs;
+    const RingOwn *ovf_ro;
+    __device__ __forceinline__ int get(int s, const RingShared *&prs, const RingOwn *&pro) const {
+        int E = ring_len[s];
+        prs = rs + (size_t)s * RS; pro = ro + (size_t)s * RS;
+        if (E == RING_IN_POOL) { const int pi = ovf_index[s]; E = ovf_len[pi]; prs = ovf_rs + (size_t)pi * RS_SLOW; pro = ovf_ro + (size_t)pi * RS_SLOW; }
+        return E;
+    }
+};
+
+// connections: count and emit pairs (gid_i < gid_j) from the rings
+__global__ void k_conn_count(RingView rv, const int64_t *__restrict__ gid, const unsigned char *__restrict__ owned, int n, int *__restrict__ cnt) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int c = 0;
+    if (owned[s]) {
+        const RingShared *rs; const RingOwn *ro;
+        const int E = rv.get(s, rs, ro);
+        const int64_t gi = gid[s];
+        for (int e = 0; e < E; ++e) {
+            const int2 q = *reinterpret_cast<const int2 *>(&rs[e]);
+            if (q.y == 1 && gi < gid[q.x]) ++c;
+        }
+    }
+    cnt[s] = c;
+}
+__global__ void k_conn_emit(RingView rv, const int64_t *__restrict__ gid, const unsigned char *__restrict__ owned, int n,
+                            const int *__restrict__ off, int64_t *__restrict__ pairs) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n || !owned[s]) return;
+    const RingShared *rs; const RingOwn *ro;
+    const int E = rv.get(s, rs, ro);
+    const int64_t gi = gid[s];
+    int o = off[s];
+    for (int e = 0; e < E; ++e) {
+        const int2 q = *reinterpret_cast<const int2 *>(&rs[e]);
+        if (q.y == 1) {
+            const int64_t gj = gid[q.x];
+            if (gi < gj) { pairs[2 * (size_t)o] = gi; pairs[2 * (size_t)o + 1] = gj; ++o; }
+        }
+    }
+}
+
+// ring export: lengths in the caller's order, then entries
+__global__ void k_ring_len_by_gid(RingView rv, const int64_t *__restrict__ gid, int n, int *__restrict__ len_out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const RingShared *rs; const RingOwn *ro;
+    len_out[gid[s]] = rv.get(s, rs, ro);
+}
+__global__ void k_ring_emit(RingView rv, const int64_t *__restrict__ gid, const double *__restrict__ x, const double *__restrict__ y, int n,
+                            const int *__restrict__ off_by_gid, signed char *__restrict__ types, double *__restrict__ vxy) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const RingShared *rs; const RingOwn *ro;
+    const int E = rv.get(s, rs, ro);
+    const int o = off_by_gid[gid[s]];
+    const double xi = x[s], yi = y[s];
+    for (int e = 0; e < E; ++e) {
+        types[o + e] = (signed char)rs[e].type;
+        const RingOwn q = ro[e];
+        vxy[2 * (size_t)(o + e)] = xi + q.hx; vxy[2 * (size_t)(o + e) + 1] = yi + q.hy;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// slab sharding helpers.  Rows are (n,5) float64: x, y, theta, A0, gid
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_unpack_rows(const double *__restrict__ rows, int n, int offset, int n_owned_in_rows, double *__restrict__ x,
+                              double *__restrict__ y, double *__restrict__ th, double *__restrict__ a0, int64_t *__restrict__ gid,
+                              unsigned char *__restrict__ owned) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *q = rows + 5 * (size_t)i;
+    const int d = offset + i;
+    x[d] = q[0]; y[d] = q[1]; th[d] = q[2]; a0[d] = q[3]; gid[d] = (int64_t)q[4];
+    owned[d] = (i < n_owned_in_rows) ? 1 : 0;
+}
+__global__ void k_pack_rows(const int *__restrict__ idx, int m, double x_shift, const double *__restrict__ x, const double *__restrict__ y,
+                            const double *__restrict__ th, const double *__restrict__ a0, const int64_t *__restrict__ gid,
+                            double *__restrict__ rows) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int s = idx[i];
+    double *q = rows + 5 * (size_t)i;
+    q[0] = x[s] + x_shift; q[1] = y[s]; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
+}
+// flag = owned && x in [lo,hi)   (invert != 0: the complement, i.e. the cells to keep)
+__global__ void k_flag_slab(const double *__restrict__ x, const unsigned char *__restrict__ owned, int n, double lo, double hi, int invert,
+                            int *__restrict__ flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int sel = (owned[i] && x[i] >= lo && x[i] < hi) ? 1 : 0;
+    flag[i] = invert ? 1 - sel : sel;
+}
+__global__ void k_flag_owned(const unsigned char *__restrict__ owned, int n, int *__restrict__ flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = owned[i] ? 1 : 0;
+}
+
+// DFMA throughput micro-benchmark: 8 independent chains per thread
+__global__ void k_dfma_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace afv
