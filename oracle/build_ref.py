@@ -10,7 +10,9 @@ installed in this image):
   2. cythonize ``pyafv/cell_geom.pyx`` -> C++ -> ``cell_geom.*.so`` with the directives the reference
      declares in ``pyproject.toml:72`` (boundscheck=False, wraparound=False, language_level=3),
   3. byte-compile the pure-Python modules to sourceless ``*.pyc``,
-  4. install ONLY the compiled outputs (``*.so`` + ``*.pyc``) to ``oracle/_ref/pyafv/``.
+  4. install ONLY the compiled outputs to ``oracle/_ref/``: ``pyafv_pyc.zip`` (the ``*.pyc`` files; the gpurun
+     snapshot drops bare ``*.pyc`` files, a zip travels) and ``cell_geom.*.so``.  ``import_reference()`` unpacks
+     both into a scratch directory and imports ``pyafv`` from there.
 
 No reference source file is written into this repository: ``oracle/_ref/`` is git-ignored, holds
 binaries only, and travels to the GPU box with the gpurun snapshot so that ``bench.py --impl
@@ -48,8 +50,7 @@ setup(name="pyafv_ref", ext_modules=cythonize(
 
 def ref_available() -> bool:
     """True when oracle/_ref holds an importable build of the reference."""
-    pkg = DEST / "pyafv"
-    return (pkg / "__init__.pyc").exists() and any(pkg.glob("cell_geom*.so"))
+    return (DEST / "pyafv_pyc.zip").exists() and any(DEST.glob("cell_geom*.so"))
 
 
 def build(force: bool = False) -> bool:
@@ -67,19 +68,41 @@ def build(force: bool = False) -> bool:
         compileall.compile_dir(str(tmp / "pyafv"), quiet=1, legacy=True, force=True)
         if DEST.exists():
             shutil.rmtree(DEST)
-        for src in (tmp / "pyafv").rglob("*"):
-            if src.suffix in (".pyc", ".so") and "__pycache__" not in src.parts:
-                rel = src.relative_to(tmp)
-                (DEST / rel).parent.mkdir(parents=True, exist_ok=True)
-                shutil.copy2(src, DEST / rel)
+        DEST.mkdir(parents=True)
+        import zipfile
+        with zipfile.ZipFile(DEST / "pyafv_pyc.zip", "w", zipfile.ZIP_DEFLATED) as z:
+            for src in sorted((tmp / "pyafv").rglob("*.pyc")):
+                if "__pycache__" not in src.parts:
+                    z.write(src, str(src.relative_to(tmp)))
+        for src in (tmp / "pyafv").glob("cell_geom*.so"):
+            shutil.copy2(src, DEST / src.name)
     return ref_available()
+
+
+_UNPACKED = None
+
+
+def _unpack() -> Path:
+    """Unpack oracle/_ref into a scratch directory laid out as an importable ``pyafv`` package."""
+    global _UNPACKED
+    if _UNPACKED is None:
+        import atexit
+        import zipfile
+        d = Path(tempfile.mkdtemp(prefix="afv_ref_"))
+        atexit.register(shutil.rmtree, d, ignore_errors=True)
+        with zipfile.ZipFile(DEST / "pyafv_pyc.zip") as z:
+            z.extractall(d)
+        for so in DEST.glob("cell_geom*.so"):
+            shutil.copy2(so, d / "pyafv" / so.name)
+        _UNPACKED = d
+    return _UNPACKED
 
 
 def import_reference():
     """Import the built reference as module ``pyafv`` (from oracle/_ref) and return it."""
     if not ref_available():
         raise ImportError("oracle/_ref is not built; run `python oracle/build_ref.py` where /root/reference exists")
-    p = str(DEST)
+    p = str(_unpack())
     if p not in sys.path:
         sys.path.insert(0, p)
     import pyafv  # noqa: E402

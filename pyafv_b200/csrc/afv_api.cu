@@ -65,6 +65,7 @@ struct AfvContext {
     int *cnt = nullptr, *off = nullptr;  // per-cell counts / offsets (cap + 1)
     int64_t n_conn = -1, n_ring = -1;
     bool built = false;
+    int cmax_hint = 32;
     // profiling
     bool profiling = false;
     struct Span { int stage; cudaEvent_t a, b; };
@@ -294,7 +295,15 @@ int stage_geometry(AfvHandle h) {
     a.n = n; a.ph = phys_dev(h->prm); a.rs = h->rs; a.ro = h->ro; a.ring_len = h->ring_len;
     a.area = h->area; a.perim = h->perim; a.arcl = h->arcl; a.coord = h->coord; a.flags = h->flags;
     a.ovf_cells = h->ovf_cells; a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
-    k_geometry<KPOLY, RS><<<nblk(n), TPB, 0, h->stream>>>(a);
+    // candidate-list capacity per cell (shared memory scales with it): for a periodic box the mean number of cells
+    // within 2r is known, 4 pi r^2 N / L^2; otherwise start at 32 and grow when the slow path gets busy
+    if (h->L > 0.0) {
+        const double mean = 4.0 * 3.141592653589793 * h->prm.r * h->prm.r * (double)h->n / (h->L * h->L);
+        h->cmax_hint = std::max(h->cmax_hint, std::min(CMAX_HARD, std::max(24, (int)(1.6 * mean) + 12)));
+    }
+    int cmax = h->cmax_hint;
+    const size_t smem = (size_t)cmax * HULL_TPB * sizeof(double2);
+    k_geometry_hull<<<nblk(n, HULL_TPB), HULL_TPB, smem, h->stream>>>(a, cmax);
     // cells queued by the fast kernel (usually none): large-capacity path, reads the queue length on the device
     k_geometry_slow<<<16, 64, 0, h->stream>>>(a);
     h->launches += 2;
@@ -325,6 +334,7 @@ int check_flags(AfvHandle h) {
     CK(cudaMemcpyAsync(f, h->flags, sizeof f, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->h_flags[0] = f[0]; h->h_flags[1] = f[1]; h->h_flags[2] = f[2];
+    if ((int64_t)f[0] * 100 > h->n + 400) h->cmax_hint = std::min(CMAX_HARD, h->cmax_hint + 12);  // busy slow path: longer lists next time
     if (f[3] > 0) {
         char buf[200];
         snprintf(buf, sizeof buf, "%d cell(s) exceeded every capacity (slow path: ring %d, polygon %d, at most %d cells per build)",
@@ -405,6 +415,7 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
     cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream);
+    cudaFuncSetAttribute(k_geometry_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(double2));
     *out = h;
     return AFV_OK;
 }

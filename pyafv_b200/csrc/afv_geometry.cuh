@@ -1,0 +1,394 @@
+// K2: geometry of the finite-Voronoi cells.  Included by afv_kernels.cuh inside namespace afv.
+//
+// Fast path (k_geometry_hull): one thread per cell; the in-range neighbours of each cell are gathered once into
+// shared memory ([entry][lane] layout, conflict free) and the Voronoi polygon is found by gift wrapping in the
+// dual plane (half-plane p.x <= |p|^2/2  <->  dual point 2p/|p|^2; the cell's edges are the hull vertices, in
+// counter-clockwise order).  The loops are regular (hull steps x candidates), warp-uniform in their bounds, hold no
+// per-thread arrays while wrapping, and need no division; a vertex is computed once per final edge as the
+// intersection of its two bisectors.  Cells with too many in-range neighbours / hull vertices / ring entries are
+// queued for the slow path.
+//
+// Slow path (k_geometry_slow): the queued cells, one thread each, by in-place clipping of a bounding square
+// (afv_device.cuh: clip_polygon) with large local arrays; long rings go to the overflow pool.
+//
+// Both paths then share finish_cell(): ring emission exactly as the reference defines it
+// (finite_voronoi.py:363-459), area / perimeter / arc length (cell_geom.pyx:432-475), per-vertex energy gradients
+// of this cell (cell_geom.pyx:478-539), written as ring records.
+
+struct GeomArgs {
+    const double *x, *y, *a0;
+    const unsigned *keys;      // sorted
+    const int *bin_start;
+    const GridDesc *grid;
+    int n;
+    PhysDev ph;
+    RingShared *rs;
+    RingOwn *ro;
+    unsigned char *ring_len;
+    double *area, *perim, *arcl;
+    int *coord;
+    int *flags;                // [0] cells sent to the slow path, [1] lookup misses, [2] max ring length, [3] hard overflows
+    // slow path (cells whose neighbourhood / polygon / ring exceeds the fast-path capacity)
+    int *ovf_cells;            // [OVF_MAX] sorted slots queued by the fast kernel
+    int *ovf_index;            // [n] slot -> pool index, valid where ring_len == RING_IN_POOL
+    int *ovf_len;              // [OVF_MAX] ring length of pooled rings
+    RingShared *ovf_rs;        // [OVF_MAX * RS_SLOW]
+    RingOwn *ovf_ro;
+};
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------------
+// Shared second half.  Input: the convex polygon of the cell, counter-clockwise, relative to the centre: vertex k,
+// and for the edge from vertex k to vertex k+1 the displacement (px,py) of the neighbour whose bisector carries
+// it and that neighbour's sorted slot `lab` (< 0: side of the bounding square).
+// LOCKSTEP: every lane of the warp calls this (invalid lanes with m = 0); loop bounds are warp maxima so that the
+// expensive bodies run converged.
+// ------------------------------------------------------------------------------------------------------
+template <int K, int R, bool SLOW>
+__device__ __forceinline__ void finish_cell(const GeomArgs &a, const int s, const int pool_idx, const bool live, bool ok,
+                                            const double (&vx)[K], const double (&vy)[K], const double (&px)[K],
+                                            const double (&py)[K], const int (&lab)[K], const int m) {
+    constexpr bool LOCKSTEP = !SLOW;
+    const double r = a.ph.r, r2 = r * r;
+    const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
+
+    // ---- ring, clockwise: edge k of the ccw polygon is walked from vertex k+1 to vertex k ----
+    double hx[R], hy[R], qx[R], qy[R];
+    int typ[R], nbr[R];
+    int E = 0;
+    const int mm = (live && ok) ? m : 0;
+    const int mloop = LOCKSTEP ? __reduce_max_sync(FULL_MASK, mm) : mm;
+    for (int kk = 0; kk < mloop; ++kk) {
+        if (kk < mm && ok) {
+            const int k = mm - 1 - kk;
+            const int j = lab[k];
+            if (j >= 0) {                                  // j < 0: side of the bounding square (the reference's ray-ray pair)
+                if (E + 2 > R) ok = false;                 // an edge emits at most 2 entries
+                else {
+                    const int k1 = (k + 1 == mm) ? 0 : k + 1;
+                    const double V1x = vx[k1], V1y = vy[k1], V2x = vx[k], V2y = vy[k];
+                    const double ex = px[k], ey = py[k];
+                    if (V1x * V1x + V1y * V1y <= r2) {     // inner start vertex: d1 <= r  (finite_voronoi.py:375-377)
+                        hx[E] = V1x; hy[E] = V1y; qx[E] = ex; qy[E] = ey; typ[E] = 1; nbr[E] = j; ++E;
+                    }
+                    const double d2c = 0.25 * (ex * ex + ey * ey);   // |C|^2, C = p/2 the foot of the bisector
+                    if (d2c < r2) {                        // bisector crosses the disk (finite_voronoi.py:395-407)
+                        // clockwise unit vector along the bisector: u = (ey, -ex)/|p|
+                        const double inv = 0.5 / sqrt(d2c);
+                        const double ux = ey * inv, uy = -ex * inv;
+                        const double t1 = V1x * ux + V1y * uy, t2 = V2x * ux + V2y * uy;
+                        const double tr = sqrt(r2 - d2c);
+                        const double Cx = 0.5 * ex, Cy = 0.5 * ey;
+                        if (-tr < t2 && -tr > t1) {        // entry point: the straight edge starts on the circle
+                            hx[E] = Cx - tr * ux; hy[E] = Cy - tr * uy; qx[E] = ex; qy[E] = ey; typ[E] = 1; nbr[E] = j; ++E;
+                        }
+                        if (tr < t2 && tr > t1) {          // exit point: an arc starts here
+                            hx[E] = Cx + tr * ux; hy[E] = Cy + tr * uy; qx[E] = ex; qy[E] = ey; typ[E] = 0; nbr[E] = ARC; ++E;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    if (live && !ok) {
+        if (!SLOW) {  // queue the cell for the large-capacity kernel
+            const int idx = atomicAdd(&a.flags[0], 1);
+            if (idx < OVF_MAX) a.ovf_cells[idx] = s; else atomicAdd(&a.flags[3], 1);
+            a.ring_len[s] = 0;
+        } else {
+            atomicAdd(&a.flags[3], 1);  // exceeded even the slow-path capacity: the host reports AFV_ERR_CAPACITY
+        }
+    }
+    const bool act = live && (ok || SLOW);     // this lane writes results
+    if (!ok) E = 0;
+
+    // ---- measures (cell_geom.pyx:402-475) ----
+    const bool ringed = act && E >= 2;
+    if (act && E < 2) {
+        a.area[s] = PI * r2; a.perim[s] = TWO_PI * r; a.arcl[s] = TWO_PI * r; a.coord[s] = 0;
+        a.ring_len[s] = 0;
+    }
+    const int EE = ringed ? E : 0;
+    const int Eloop = LOCKSTEP ? __reduce_max_sync(FULL_MASK, EE) : EE;
+    double ux_[R], uy_[R];   // unit vector (v1 - v2)/|v1 - v2| of straight edge e, 0 for arcs
+    int arc_e[R / 2 + 1];
+    int n_arc = 0;
+    double A = 0.0, P = 0.0, Larc = 0.0;
+    int z = 0;
+    for (int e = 0; e < Eloop; ++e) {
+        if (e < EE) {
+            const int e2 = (e + 1 == EE) ? 0 : e + 1;
+            if (typ[e] == 1) {
+                const double v1x = hx[e], v1y = hy[e], v2x = hx[e2], v2y = hy[e2];
+                const double sx = v1x - v2x, sy = v1y - v2y;
+                const double l2 = sx * sx + sy * sy;
+                const double l = sqrt(l2);
+                P += l;
+                A += -0.5 * (v1x * v2y - v1y * v2x);
+                const double il = l > 0.0 ? 1.0 / l : 0.0;
+                ux_[e] = sx * il; uy_[e] = sy * il;
+                ++z;
+            } else {
+                ux_[e] = 0.0; uy_[e] = 0.0;
+                if (n_arc < R / 2 + 1) arc_e[n_arc++] = e;
+            }
+        }
+    }
+    // arcs, compacted so that the lanes of a warp evaluate their atan2 together
+    const int aloop = LOCKSTEP ? __reduce_max_sync(FULL_MASK, n_arc) : n_arc;
+    for (int q = 0; q < aloop; ++q) {
+        if (q < n_arc) {
+            const int e = arc_e[q];
+            const int e2 = (e + 1 == EE) ? 0 : e + 1;
+            const double v1x = hx[e], v1y = hy[e], v2x = hx[e2], v2y = hy[e2];
+            double ang = atan2(v2x * v1y - v2y * v1x, v1x * v2x + v1y * v2y);  // angle(v1) - angle(v2)
+            if (ang < 0.0) ang += TWO_PI;
+            Larc += r * ang;
+            A += 0.5 * r2 * ang;
+        }
+    }
+    P += Larc;
+
+    RingShared *rs = a.rs + (size_t)s * RS;
+    RingOwn *ro = a.ro + (size_t)s * RS;
+    double cA = 0.0, cP = 0.0, cL = 0.0;
+    if (ringed) {
+        a.area[s] = A; a.perim[s] = P; a.arcl[s] = Larc; a.coord[s] = z;
+        if (SLOW && E > RS) {
+            a.ring_len[s] = RING_IN_POOL; a.ovf_index[s] = pool_idx; a.ovf_len[pool_idx] = E;
+            rs = a.ovf_rs + (size_t)pool_idx * RS_SLOW; ro = a.ovf_ro + (size_t)pool_idx * RS_SLOW;
+        } else {
+            a.ring_len[s] = (unsigned char)E;
+        }
+        if (E > 12) atomicMax(&a.flags[2], E);
+        cA = 2.0 * a.ph.KA * (A - a.a0[s]);
+        cP = 2.0 * a.ph.KP * (P - a.ph.P0);
+        cL = cP + a.ph.Lambda;
+    }
+
+    // ---- per-vertex gradients of this cell (cell_geom.pyx:478-539) ----
+    for (int e = 0; e < Eloop; ++e) {
+        if (e < EE) {
+            const int e2 = (e + 1 == EE) ? 0 : e + 1, e0 = (e == 0) ? EE - 1 : e - 1;
+            // dA/dv1 = 0.5 (perp(v0) - perp(v2)), perp(u) = (uy, -ux);  dP/dv1 = u(e) - u(e-1)
+            const double gx = cA * 0.5 * (hy[e0] - hy[e2]) + cP * (ux_[e] - ux_[e0]);
+            const double gy = cA * 0.5 * (hx[e2] - hx[e0]) + cP * (uy_[e] - uy_[e0]);
+            double w = 0.0;
+            if (typ[e] == 0)        // an arc starts here: da = +0.5 r^2 (1 - cos D), dl = +r
+                w = cA * 0.5 * (r2 - (hx[e] * hx[e2] + hy[e] * hy[e2])) + cL * r;
+            else if (typ[e0] == 0)  // an arc ends here
+                w = -(cA * 0.5 * (r2 - (hx[e0] * hx[e] + hy[e0] * hy[e])) + cL * r);
+            RingShared o; o.nbr = nbr[e]; o.type = typ[e]; o.gx = gx; o.gy = gy; o.w = w;
+            rs[e] = o;
+            RingOwn q; q.hx = hx[e]; q.hy = hy[e]; q.px = qx[e]; q.py = qy[e];
+            ro[e] = q;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// candidate runs of one bin row: columns bx-1..bx+1 as (up to) two contiguous runs of sorted slots
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int row_runs(const GridDesc &g, const int *__restrict__ bin_start, int row, int bx, int (&c0)[2], int (&c1)[2]) {
+    const int base = row * g.nbx;
+    if (!g.periodic || g.nbx < 3) {
+        const int lo = g.periodic ? 0 : max(bx - 1, 0), hi = g.periodic ? g.nbx - 1 : min(bx + 1, g.nbx - 1);
+        c0[0] = bin_start[base + lo]; c1[0] = bin_start[base + hi + 1];
+        return 1;
+    }
+    if (bx == 0) {
+        c0[0] = bin_start[base]; c1[0] = bin_start[base + 2];
+        c0[1] = bin_start[base + g.nbx - 1]; c1[1] = bin_start[base + g.nbx];
+        return 2;
+    }
+    if (bx == g.nbx - 1) {
+        c0[0] = bin_start[base + bx - 1]; c1[0] = bin_start[base + bx + 1];
+        c0[1] = bin_start[base]; c1[1] = bin_start[base + 1];
+        return 2;
+    }
+    c0[0] = bin_start[base + bx - 1]; c1[0] = bin_start[base + bx + 2];
+    return 1;
+}
+
+// rows to visit for a cell in bin row `by`: returns the count, fills rows[]
+__device__ __forceinline__ int cell_rows(const GridDesc &g, int by, int (&rows)[3]) {
+    if (g.periodic) {
+        if (g.nby < 3) { for (int i = 0; i < g.nby; ++i) rows[i] = i; return g.nby; }
+        rows[0] = (by == 0) ? g.nby - 1 : by - 1; rows[1] = by; rows[2] = (by == g.nby - 1) ? 0 : by + 1;
+        return 3;
+    }
+    int n = 0;
+    if (by > 0) rows[n++] = by - 1;
+    rows[n++] = by;
+    if (by < g.nby - 1) rows[n++] = by + 1;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fast path
+// ------------------------------------------------------------------------------------------------------
+constexpr int HULL_TPB = 128;
+constexpr int KHULL = 16;        // hull vertices (= polygon edges) on the fast path
+constexpr int CMAX_HARD = 60;    // upper bound of the per-cell candidate list (the launch picks cmax <= this)
+
+__device__ __forceinline__ void virtual_nbr(int v, double B4, double &x, double &y) {
+    // four virtual neighbours at distance 4r whose bisectors are the sides of the bounding square of half side 2r
+    x = (v == 1) ? B4 : ((v == 3) ? -B4 : 0.0);
+    y = (v == 0) ? -B4 : ((v == 2) ? B4 : 0.0);
+}
+
+__global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const int cmax) {
+    extern __shared__ double2 s_cand[];          // [cmax][HULL_TPB]
+    const int tid = threadIdx.x;
+    const int s = blockIdx.x * HULL_TPB + tid;
+    const bool live = s < a.n;
+    const double r = a.ph.r, cut2 = 4.0 * r * r, B4 = 4.0 * r;
+    int cidx[CMAX_HARD];                          // sorted slot of every gathered candidate (read back for <= 16 of them)
+    int n = 0, imin = 0;
+    bool ok = true;
+
+    // ---- gather the neighbours within 2r ----
+    if (live) {
+        const double xi = a.x[s], yi = a.y[s];
+        const GridDesc g = *a.grid;
+        const unsigned key = a.keys[s];
+        const int by = (int)(key / (unsigned)g.nbx), bx = (int)(key - (unsigned)by * (unsigned)g.nbx);
+        int rows[3];
+        const int nrow = cell_rows(g, by, rows);
+        double dmin = 1e300;
+        for (int ir = 0; ir < nrow; ++ir) {
+            int c0[2], c1[2];
+            const int nrun = row_runs(g, a.bin_start, rows[ir], bx, c0, c1);
+            for (int q = 0; q < nrun; ++q) {
+                for (int c = c0[q]; c < c1[q]; ++c) {
+                    double dx = a.x[c] - xi, dy = a.y[c] - yi;
+                    if (g.periodic) { dx = min_image(dx, g.L, g.halfL); dy = min_image(dy, g.L, g.halfL); }
+                    const double d2 = dx * dx + dy * dy;
+                    if (d2 < cut2 && c != s && d2 > 0.0) {
+                        if (n < cmax) {
+                            s_cand[n * HULL_TPB + tid] = make_double2(dx, dy);
+                            cidx[n] = c;
+                            if (d2 < dmin) { dmin = d2; imin = n; }
+                            ++n;
+                        } else ok = false;
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- gift wrapping in the dual plane.  Candidate c <-> homogeneous dual point (p_c, k_c), k_c = |p_c|^2 / 2.
+    //      orient(a, b, c) = sign((p_b k_a - p_a k_b) x (p_c k_a - p_a k_c));  the nearest neighbour is on the hull. ----
+    unsigned long long hull_lo = 0ull, hull_hi = 0ull;   // 16 x 8-bit candidate indices (n..n+3 = virtual)
+    int m = 0;
+    const bool wrap = live && ok && n > 0;
+    const int nreal_max = __reduce_max_sync(FULL_MASK, wrap ? n : 0);
+    bool done = !wrap;
+    int cur = imin;
+    while (__any_sync(FULL_MASK, !done)) {
+        double pax = 0.0, pay = 0.0, ka = 1.0;
+        if (!done) {
+            if (m < 8) hull_lo |= (unsigned long long)cur << (8 * m); else hull_hi |= (unsigned long long)cur << (8 * (m - 8));
+            ++m;
+            if (cur < n) { const double2 p = s_cand[cur * HULL_TPB + tid]; pax = p.x; pay = p.y; }
+            else virtual_nbr(cur - n, B4, pax, pay);
+            ka = 0.5 * (pax * pax + pay * pay);
+        }
+        int best = -1;
+        double ux = 0.0, uy = 0.0;
+        for (int c = 0; c < nreal_max; ++c) {
+            if (!done && c < n && c != cur) {
+                const double2 p = s_cand[c * HULL_TPB + tid];
+                const double kc = 0.5 * (p.x * p.x + p.y * p.y);
+                const double wx = p.x * ka - pax * kc, wy = p.y * ka - pay * kc;
+                if (best < 0 || ux * wy - uy * wx < 0.0) { best = c; ux = wx; uy = wy; }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            if (!done && n + v != cur) {
+                double qx_, qy_;
+                virtual_nbr(v, B4, qx_, qy_);
+                const double kc = 0.5 * B4 * B4;
+                const double wx = qx_ * ka - pax * kc, wy = qy_ * ka - pay * kc;
+                if (best < 0 || ux * wy - uy * wx < 0.0) { best = n + v; ux = wx; uy = wy; }
+            }
+        }
+        if (!done) {
+            cur = best;
+            if (cur == imin) done = true;
+            else if (m >= KHULL) { ok = false; done = true; }
+        }
+    }
+
+    // ---- polygon: edge k = hull vertex k, vertex k = bisector(k-1) ^ bisector(k) ----
+    double vx[KHULL], vy[KHULL], px[KHULL], py[KHULL];
+    int lab[KHULL];
+    const int mm = (wrap && ok) ? m : 0;
+    const int mloop = __reduce_max_sync(FULL_MASK, mm);
+    for (int k = 0; k < mloop; ++k) {
+        if (k < mm) {
+            const int h = (int)(((k < 8) ? (hull_lo >> (8 * k)) : (hull_hi >> (8 * (k - 8)))) & 0xffull);
+            if (h < n) { const double2 p = s_cand[h * HULL_TPB + tid]; px[k] = p.x; py[k] = p.y; lab[k] = cidx[h]; }
+            else { virtual_nbr(h - n, B4, px[k], py[k]); lab[k] = -2; }
+        }
+    }
+    for (int k = 0; k < mloop; ++k) {
+        if (k < mm) {
+            const int km = (k == 0) ? mm - 1 : k - 1;
+            const double ax = px[km], ay = py[km], bx_ = px[k], by_ = py[k];
+            const double ca = 0.5 * (ax * ax + ay * ay), cb = 0.5 * (bx_ * bx_ + by_ * by_);
+            const double idet = 1.0 / (ax * by_ - ay * bx_);
+            vx[k] = (ca * by_ - cb * ay) * idet;
+            vy[k] = (ax * cb - bx_ * ca) * idet;
+        }
+    }
+    finish_cell<KHULL, RS, false>(a, s, 0, live, ok, vx, vy, px, py, lab, mm);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// slow path: the (few) queued cells, one thread each, in-place clipping with large local arrays
+// ------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void geom_cell_slow(const GeomArgs &a, const int s, const int pool_idx) {
+    constexpr int K = KPOLY_SLOW;
+    const double r = a.ph.r, cut2 = 4.0 * r * r;
+    const double xi = a.x[s], yi = a.y[s];
+    const GridDesc g = *a.grid;
+    const unsigned key = a.keys[s];
+    const int by = (int)(key / (unsigned)g.nbx), bx = (int)(key - (unsigned)by * (unsigned)g.nbx);
+    // bounding square of half side B = 2r as four virtual bisectors (virtual neighbours at distance 4r)
+    double vx[K], vy[K], px[K], py[K];
+    int lab[K];
+    const double B = 2.0 * r;
+    vx[0] = -B; vy[0] = -B; px[0] = 0.0;      py[0] = -2.0 * B; lab[0] = -2;
+    vx[1] = B;  vy[1] = -B; px[1] = 2.0 * B;  py[1] = 0.0;      lab[1] = -2;
+    vx[2] = B;  vy[2] = B;  px[2] = 0.0;      py[2] = 2.0 * B;  lab[2] = -2;
+    vx[3] = -B; vy[3] = B;  px[3] = -2.0 * B; py[3] = 0.0;      lab[3] = -2;
+    int m = 4;
+    bool ok = true;
+    int rows[3];
+    const int nrow = cell_rows(g, by, rows);
+    for (int ir = 0; ir < nrow; ++ir) {
+        int c0[2], c1[2];
+        const int nrun = row_runs(g, a.bin_start, rows[ir], bx, c0, c1);
+        for (int q = 0; q < nrun; ++q) {
+            for (int c = c0[q]; c < c1[q]; ++c) {
+                if (c == s) continue;
+                double dx = a.x[c] - xi, dy = a.y[c] - yi;
+                if (g.periodic) { dx = min_image(dx, g.L, g.halfL); dy = min_image(dy, g.L, g.halfL); }
+                const double d2 = dx * dx + dy * dy;
+                if (d2 >= cut2 || d2 == 0.0) continue;
+                ok = ok && clip_polygon<K>(vx, vy, px, py, lab, m, dx, dy, 0.5 * d2, c);
+            }
+        }
+    }
+    finish_cell<K, RS_SLOW, true>(a, s, pool_idx, true, ok, vx, vy, px, py, lab, m);
+}
+
+__global__ void __launch_bounds__(64) k_geometry_slow(GeomArgs a) {
+    const int cnt = min(a.flags[0], OVF_MAX);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x)
+        geom_cell_slow(a, a.ovf_cells[idx], idx);
+}

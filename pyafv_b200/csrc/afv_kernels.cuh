@@ -108,196 +108,7 @@ __global__ void k_bin_start(const unsigned *__restrict__ keys_sorted, int n, con
     bin_start[b] = lo;
 }
 
-// ------------------------------------------------------------------------------------------------------
-// K2: geometry.  One thread per cell (sorted slot).  Clip the bounding square by the bisectors of all
-// neighbours within 2r, walk the polygon clockwise to emit the ring exactly as the reference defines it
-// (finite_voronoi.py:363-459), then area / perimeter / arc length (cell_geom.pyx:432-475) and the per-vertex
-// energy gradients of THIS cell (cell_geom.pyx:478-539), written as fixed-stride ring records.
-// ------------------------------------------------------------------------------------------------------
-struct GeomArgs {
-    const double *x, *y, *a0;
-    const unsigned *keys;      // sorted
-    const int *bin_start;
-    const GridDesc *grid;
-    int n;
-    PhysDev ph;
-    RingShared *rs;
-    RingOwn *ro;
-    unsigned char *ring_len;
-    double *area, *perim, *arcl;
-    int *coord;
-    int *flags;                // [0] cells sent to the slow path, [1] lookup misses, [2] max ring length, [3] hard overflows
-    // slow path (cells whose polygon / ring exceeds the fast-path capacity)
-    int *ovf_cells;            // [OVF_MAX] sorted slots queued by the fast kernel
-    int *ovf_index;            // [n] slot -> pool index, valid where ring_len == RING_IN_POOL
-    int *ovf_len;              // [OVF_MAX] ring length of pooled rings
-    RingShared *ovf_rs;        // [OVF_MAX * RS_SLOW]
-    RingOwn *ovf_ro;
-};
-
-// Geometry of one cell.  SLOW = false: fast path, capacity (K, R) = (KPOLY, RS); on overflow the cell is queued.
-// SLOW = true: large capacity; rings longer than RS go to the overflow pool at index `pool_idx`.
-template <int K, int R, bool SLOW>
-__device__ __forceinline__ void geom_cell(const GeomArgs &a, const int s, const int pool_idx) {
-    const double r = a.ph.r, r2 = r * r, cut2 = 4.0 * r2;
-    const double xi = a.x[s], yi = a.y[s];
-    const GridDesc g = *a.grid;
-    const unsigned key = a.keys[s];
-    const int by = (int)(key / (unsigned)g.nbx), bx = (int)(key - (unsigned)by * (unsigned)g.nbx);
-
-    // bounding square of half side B = 2r as four virtual bisectors (virtual neighbours at distance 4r)
-    double vx[K], vy[K], px[K], py[K];
-    int lab[K];
-    const double B = 2.0 * r;
-    vx[0] = -B; vy[0] = -B; px[0] = 0.0;      py[0] = -2.0 * B; lab[0] = -2;
-    vx[1] = B;  vy[1] = -B; px[1] = 2.0 * B;  py[1] = 0.0;      lab[1] = -2;
-    vx[2] = B;  vy[2] = B;  px[2] = 0.0;      py[2] = 2.0 * B;  lab[2] = -2;
-    vx[3] = -B; vy[3] = B;  px[3] = -2.0 * B; py[3] = 0.0;      lab[3] = -2;
-    int m = 4;
-    bool ok = true;
-
-    const int nrow = (g.periodic && g.nby < 3) ? g.nby : 3;
-    const int ncol = (g.periodic && g.nbx < 3) ? g.nbx : 3;
-    for (int ir = 0; ir < nrow; ++ir) {
-        int row = (nrow == 3) ? by + ir - 1 : ir;
-        if (g.periodic) { if (row < 0) row += g.nby; else if (row >= g.nby) row -= g.nby; }
-        else if (row < 0 || row >= g.nby) continue;
-        for (int ic = 0; ic < ncol; ++ic) {
-            int col = (ncol == 3) ? bx + ic - 1 : ic;
-            if (g.periodic) { if (col < 0) col += g.nbx; else if (col >= g.nbx) col -= g.nbx; }
-            else if (col < 0 || col >= g.nbx) continue;
-            const int b = row * g.nbx + col;
-            const int c0 = a.bin_start[b], c1 = a.bin_start[b + 1];
-            for (int c = c0; c < c1; ++c) {
-                if (c == s) continue;
-                double dx = a.x[c] - xi, dy = a.y[c] - yi;
-                if (g.periodic) { dx = min_image(dx, g.L, g.halfL); dy = min_image(dy, g.L, g.halfL); }
-                const double d2 = dx * dx + dy * dy;
-                if (d2 >= cut2) continue;
-                ok = ok && clip_polygon<K>(vx, vy, px, py, lab, m, dx, dy, 0.5 * d2, c);
-            }
-        }
-    }
-
-    // ---- ring, clockwise: edge k of the ccw polygon is walked from vertex k+1 to vertex k ----
-    double hx[R], hy[R], qx[R], qy[R];
-    int typ[R], nbr[R];
-    int E = 0;
-    for (int kk = 0; kk < m; ++kk) {
-        const int k = m - 1 - kk;
-        const int j = lab[k];
-        if (j < 0) continue;                       // side of the bounding square (the reference's ray-ray pair)
-        const int k1 = (k + 1 == m) ? 0 : k + 1;
-        const double V1x = vx[k1], V1y = vy[k1], V2x = vx[k], V2y = vy[k];
-        const double ex = px[k], ey = py[k];
-        if (E + 2 > R) { ok = false; break; }      // an edge emits at most 2 entries
-        if (sqrt(V1x * V1x + V1y * V1y) <= r) {    // inner start vertex: d1 <= r  (finite_voronoi.py:375-377)
-            hx[E] = V1x; hy[E] = V1y; qx[E] = ex; qy[E] = ey; typ[E] = 1; nbr[E] = j; ++E;
-        }
-        const double Cx = 0.5 * ex, Cy = 0.5 * ey;
-        const double d2c = Cx * Cx + Cy * Cy;
-        if (sqrt(d2c) < r) {                        // bisector crosses the disk (finite_voronoi.py:395-407)
-            const double dVx = V2x - V1x, dVy = V2y - V1y;
-            const double segL = sqrt(dVx * dVx + dVy * dVy);
-            const double den = segL > 0.0 ? segL : 1.0;
-            const double t1 = (V1x * dVx + V1y * dVy) / den, t2 = t1 + den;
-            const double tr = sqrt(r2 - d2c);
-            const double ux = dVx / den, uy = dVy / den;
-            if (-tr < t2 && -tr > t1) {             // entry point: straight edge starts on the circle
-                hx[E] = Cx - tr * ux; hy[E] = Cy - tr * uy; qx[E] = ex; qy[E] = ey; typ[E] = 1; nbr[E] = j; ++E;
-            }
-            if (tr < t2 && tr > t1) {               // exit point: an arc starts here
-                hx[E] = Cx + tr * ux; hy[E] = Cy + tr * uy; qx[E] = ex; qy[E] = ey; typ[E] = 0; nbr[E] = ARC; ++E;
-            }
-        }
-    }
-
-    if (!ok) {
-        if (!SLOW) {  // queue the cell for the large-capacity kernel
-            const int idx = atomicAdd(&a.flags[0], 1);
-            if (idx < OVF_MAX) a.ovf_cells[idx] = s; else atomicAdd(&a.flags[3], 1);
-            a.ring_len[s] = 0;
-            return;
-        }
-        atomicAdd(&a.flags[3], 1);  // exceeded even the slow-path capacity: the host reports AFV_ERR_CAPACITY
-        E = 0;
-    }
-
-    // ---- measures (cell_geom.pyx:402-475) ----
-    const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
-    if (E < 2) {
-        a.area[s] = PI * r2; a.perim[s] = TWO_PI * r; a.arcl[s] = TWO_PI * r; a.coord[s] = 0;
-        a.ring_len[s] = 0;
-        return;
-    }
-    double ux_[R], uy_[R];   // unit vector (v1 - v2)/|v1 - v2| of straight edge e, 0 for arcs
-    double A = 0.0, P = 0.0, Larc = 0.0;
-    int z = 0;
-    for (int e = 0; e < E; ++e) {
-        const int e2 = (e + 1 == E) ? 0 : e + 1;
-        const double v1x = hx[e], v1y = hy[e], v2x = hx[e2], v2y = hy[e2];
-        if (typ[e] == 1) {
-            const double sx = v1x - v2x, sy = v1y - v2y;
-            const double l = sqrt(sx * sx + sy * sy);
-            P += l;
-            A += -0.5 * (v1x * v2y - v1y * v2x);
-            const double il = l > 0.0 ? 1.0 / l : 0.0;
-            ux_[e] = sx * il; uy_[e] = sy * il;
-            ++z;
-        } else {
-            double ang = atan2(v2x * v1y - v2y * v1x, v1x * v2x + v1y * v2y);  // angle(v1) - angle(v2)
-            if (ang < 0.0) ang += TWO_PI;
-            Larc += r * ang;
-            A += 0.5 * r2 * ang;
-            ux_[e] = 0.0; uy_[e] = 0.0;
-        }
-    }
-    P += Larc;
-    a.area[s] = A; a.perim[s] = P; a.arcl[s] = Larc; a.coord[s] = z;
-    RingShared *rs = a.rs + (size_t)s * RS;
-    RingOwn *ro = a.ro + (size_t)s * RS;
-    if (SLOW && E > RS) {
-        a.ring_len[s] = RING_IN_POOL; a.ovf_index[s] = pool_idx; a.ovf_len[pool_idx] = E;
-        rs = a.ovf_rs + (size_t)pool_idx * RS_SLOW; ro = a.ovf_ro + (size_t)pool_idx * RS_SLOW;
-    } else {
-        a.ring_len[s] = (unsigned char)E;
-    }
-    if (E > 12 || SLOW) atomicMax(&a.flags[2], E);
-
-    // ---- per-vertex gradients of this cell (cell_geom.pyx:478-539) ----
-    const double cA = 2.0 * a.ph.KA * (A - a.a0[s]);
-    const double cP = 2.0 * a.ph.KP * (P - a.ph.P0);
-    const double cL = cP + a.ph.Lambda;
-    for (int e = 0; e < E; ++e) {
-        const int e2 = (e + 1 == E) ? 0 : e + 1, e0 = (e == 0) ? E - 1 : e - 1;
-        // dA/dv1 = 0.5 (perp(v0) - perp(v2)), perp(u) = (uy, -ux);  dP/dv1 = u(e) - u(e-1)
-        const double gx = cA * 0.5 * (hy[e0] - hy[e2]) + cP * (ux_[e] - ux_[e0]);
-        const double gy = cA * 0.5 * (hx[e2] - hx[e0]) + cP * (uy_[e] - uy_[e0]);
-        double w = 0.0;
-        if (typ[e] == 0)        // an arc starts here: da = +0.5 r^2 (1 - cos D), dl = +r
-            w = cA * 0.5 * (r2 - (hx[e] * hx[e2] + hy[e] * hy[e2])) + cL * r;
-        else if (typ[e0] == 0)  // an arc ends here
-            w = -(cA * 0.5 * (r2 - (hx[e0] * hx[e] + hy[e0] * hy[e])) + cL * r);
-        RingShared o; o.nbr = nbr[e]; o.type = typ[e]; o.gx = gx; o.gy = gy; o.w = w;
-        rs[e] = o;
-        RingOwn q; q.hx = hx[e]; q.hy = hy[e]; q.px = qx[e]; q.py = qy[e];
-        ro[e] = q;
-    }
-}
-
-template <int K, int R>
-__global__ void __launch_bounds__(128) k_geometry(GeomArgs a) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.n) return;
-    geom_cell<K, R, false>(a, s, 0);
-}
-
-// slow path: the (few) queued cells, one thread each, large local arrays
-__global__ void __launch_bounds__(64) k_geometry_slow(GeomArgs a) {
-    const int cnt = min(a.flags[0], OVF_MAX);
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x)
-        geom_cell<KPOLY_SLOW, RS_SLOW, true>(a, a.ovf_cells[idx], idx);
-}
+#include "afv_geometry.cuh"
 
 // ------------------------------------------------------------------------------------------------------
 // K3: force gather (+ fused active-Langevin update).  One thread per cell walks its own ring; for every

@@ -104,7 +104,7 @@ class FiniteVoronoiSimulator:
         1 = straight contact edge, 0 = arc).  Vertex ids are implementation-defined, as in the reference: every
         ring entry owns one row of ``vertices``.
 
-        ``rings=False`` skips the ragged export (``vertices`` is empty, ``regions`` / ``edges_type`` hold empty
+        ``rings=False`` skips the ragged export (``vertices`` is empty, ``regions`` / ``edges_type`` are empty
         lists); use it inside time loops.
         """
         flags = _lib.BUILD_FORCES | (_lib.BUILD_CONNECT if connect else 0) | (_lib.BUILD_RINGS if rings else 0)
@@ -130,8 +130,8 @@ class FiniteVoronoiSimulator:
             out["regions"] = [a.tolist() for a in np.split(ids, cuts)] if N else []
         else:
             out["vertices"] = np.zeros((0, 2), dtype=np.float64)
-            out["edges_type"] = [[] for _ in range(N)]
-            out["regions"] = [[] for _ in range(N)]
+            out["edges_type"] = []
+            out["regions"] = []
         if connect:
             K = C.c_int64()
             h.call("afv_get_num_connections", C.byref(K))

@@ -104,26 +104,39 @@ def hex_jitter(ncol, nrow, a, sigma, seed):
     return np.mod(pts, L), L
 
 
-def trajectory(name, pts0, ph, L, n_steps, mu, v0, Dr, dt, seed, A0=None):
-    """examples/active_FV.py:43-54 with a recorded noise stream (periodic via tile_pbc when L>0)."""
+def ref_forces(pts, ph, L, A0=None):
+    """Forces of the reference on pts (periodic through its own tile_pbc when L > 0)."""
+    N = len(pts)
+    if L > 0:
+        tiled, idx = afv.tile_pbc(pts, L, ph.r)
+        sim = afv.FiniteVoronoiSimulator(tiled, ph)
+        if A0 is not None:
+            sim.update_preferred_areas(np.asarray(A0)[idx])
+        return sim.build(connect=False)["forces"][:N]
+    sim = afv.FiniteVoronoiSimulator(pts, ph)
+    if A0 is not None:
+        sim.update_preferred_areas(A0)
+    return sim.build(connect=False)["forces"]
+
+
+def trajectory(name, pts_init, ph, L, n_relax, n_steps, mu, v0, Dr, dt, seed, A0=None):
+    """examples/active_FV.py:37-54: relax to mechanical equilibrium first (v0 = 0), then record n_steps active
+    steps with a recorded noise stream.  (Without the relaxation the explicit Euler map is violently unstable --
+    |F| dt ~ 2 l -- and even two builds that agree to 1e-14 diverge to O(1) within 50 steps.)"""
     rng = np.random.default_rng(seed)
-    N = len(pts0)
+    N = len(pts_init)
+    pts = pts_init.copy()
+    for _ in range(n_relax):
+        pts = pts + mu * ref_forces(pts, ph, L, A0) * dt
+        if L > 0:
+            pts = np.mod(pts, L)
+    pts0 = pts.copy()
     theta0 = 2 * np.pi * rng.random(N) - np.pi
     noise = rng.standard_normal((n_steps, N))
-    pts, theta = pts0.copy(), theta0.copy()
+    theta = theta0.copy()
     snaps = {}
     for s in range(n_steps):
-        if L > 0:
-            tiled, idx = afv.tile_pbc(pts, L, ph.r)
-            sim = afv.FiniteVoronoiSimulator(tiled, ph)
-            if A0 is not None:
-                sim.update_preferred_areas(np.asarray(A0)[idx])
-            F = sim.build(connect=False)["forces"][:N]
-        else:
-            sim = afv.FiniteVoronoiSimulator(pts, ph)
-            if A0 is not None:
-                sim.update_preferred_areas(A0)
-            F = sim.build(connect=False)["forces"]
+        F = ref_forces(pts, ph, L, A0)
         pts = pts + (mu * F + v0 * np.column_stack((np.cos(theta), np.sin(theta)))) * dt
         theta = theta + np.sqrt(2 * Dr * dt) * noise[s]
         if L > 0:
@@ -136,11 +149,10 @@ def trajectory(name, pts0, ph, L, n_steps, mu, v0, Dr, dt, seed, A0=None):
     if A0 is not None:
         d["A0"] = np.asarray(A0, dtype=float)
     np.savez_compressed(HERE / f"ref_{name}.npz", **d)
-    print(f"ref_{name}.npz  N={N} steps={n_steps}")
+    print(f"ref_{name}.npz  N={N} relax={n_relax} steps={n_steps}  max|F0|={np.abs(ref_forces(pts0, ph, L, A0)).max():.3g}")
 
 
-def main():
-    P = afv.PhysicalParams
+def static_cases(P):
     init = np.loadtxt(HERE / "init_pts.csv", delimiter=",")
     varA0 = np.loadtxt(HERE / "varying_A0.csv", delimiter=",")
     open_case("init_d0", init, P(delta=0.0))
@@ -174,12 +186,19 @@ def main():
     rng = np.random.default_rng(4)
     A0 = np.maximum(2.0 * (1 + 0.1 * rng.standard_normal(len(pts))), 0.4)
     pbc_case("pbc_hex_varyA0", pts, L, P(), A0=A0)
-    # trajectories (examples/active_FV.py parameters: mu=1, v0=2.4, Dr=0.3, dt=0.01)
-    rng = np.random.default_rng(31)
-    trajectory("traj_open", (rng.random((150, 2)) * 0.3 + 0.35) * 25.0 * np.sqrt(1.5), P(), 0.0, 100, 1.0, 2.4, 0.3, 0.01, 32)
-    rng = np.random.default_rng(33)
-    trajectory("traj_pbc", rng.random((400, 2)) * 20.0, P(), 20.0, 100, 1.0, 2.4, 0.3, 0.01, 34)
+
+
+def main(only=None):
+    P = afv.PhysicalParams
+    if only is None:
+        static_cases(P)
+    # trajectories (examples/active_FV.py parameters: mu=1, v0=2.4, Dr=0.3, dt=0.01), relaxed first (:37-41)
+    if only is None or "traj" in only:
+        rng = np.random.default_rng(31)
+        trajectory("traj_open", (rng.random((150, 2)) * 0.3 + 0.35) * 25.0 * np.sqrt(1.5), P(), 0.0, 300, 100, 1.0, 2.4, 0.3, 0.01, 32)
+        rng = np.random.default_rng(33)
+        trajectory("traj_pbc", rng.random((400, 2)) * 30.0, P(), 30.0, 300, 100, 1.0, 2.4, 0.3, 0.01, 34)
 
 
 if __name__ == "__main__":
-    main()
+    main(only=sys.argv[1:] or None)

@@ -194,12 +194,13 @@ def test_many_neighbour_cell_uses_overflow_pool(n_ring, radius):
     sim = afv.FiniteVoronoiSimulator(pts, afv.PhysicalParams())
     d = sim.build()
     o = oracle_build(pts, rings=True)
-    assert o["ring_off"][1] - o["ring_off"][0] == n_ring
+    n_expect = int(o["ring_off"][1] - o["ring_off"][0])
+    assert n_expect > 16   # more than the fixed ring stride of the fast path
     for k in ("areas", "perimeters", "arclens", "forces"):
         _close(d[k], o[k], k)
-    assert np.array_equal(d["coord_nums"], o["coord_nums"]) and d["coord_nums"][0] == n_ring
+    assert np.array_equal(d["coord_nums"], o["coord_nums"]) and d["coord_nums"][0] == n_expect
     assert np.array_equal(d["connections"], o["connections"])
-    assert len(d["regions"][0]) == n_ring
+    assert len(d["regions"][0]) == n_expect
     diag = sim.diagnostics()
-    assert diag["slow_path_cells"] >= 1 and diag["lookup_misses"] == 0 and diag["max_ring_len"] == n_ring
+    assert diag["slow_path_cells"] >= 1 and diag["lookup_misses"] == 0 and diag["max_ring_len"] == n_expect
     sim.close()
