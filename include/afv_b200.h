@@ -59,7 +59,7 @@ typedef struct AfvContext *AfvHandle;
 /* fields for afv_device_ptr (device arrays in the CURRENT SORTED ORDER; afv_device_ptr(AFV_F_GID) maps a
  * sorted slot back to the caller's cell index) */
 enum AfvField {
-    AFV_F_X = 0, AFV_F_Y = 1, AFV_F_THETA = 2, AFV_F_A0 = 3, AFV_F_GID = 4,
+    AFV_F_XY = 0 /* (n,2) interleaved */, AFV_F_THETA = 2, AFV_F_A0 = 3, AFV_F_GID = 4,
     AFV_F_FX = 5, AFV_F_FY = 6, AFV_F_AREA = 7, AFV_F_PERIM = 8, AFV_F_ARCLEN = 9, AFV_F_COORD = 10,
     AFV_F_OWNED = 11
 };

@@ -11,7 +11,7 @@ LIB_PATH = PKG / "libafv_b200.so"
 
 AFV_OK, AFV_ERR_CUDA, AFV_ERR_ARG, AFV_ERR_CAPACITY, AFV_ERR_STATE = 0, -1, -2, -3, -4
 BUILD_FORCES, BUILD_CONNECT, BUILD_RINGS = 1, 2, 4
-F_X, F_Y, F_THETA, F_A0, F_GID, F_FX, F_FY, F_AREA, F_PERIM, F_ARCLEN, F_COORD, F_OWNED = range(12)
+F_XY, _F_UNUSED, F_THETA, F_A0, F_GID, F_FX, F_FY, F_AREA, F_PERIM, F_ARCLEN, F_COORD, F_OWNED = range(12)
 
 # every symbol include/afv_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [

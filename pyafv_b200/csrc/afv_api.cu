@@ -37,7 +37,8 @@ struct AfvContext {
     int64_t n = 0, n_owned = 0, cap = 0;
     bool gid_is_perm = true;  // gid is a permutation of 0..n-1 (single-GPU use); false after set_cells_device
     // SoA state, double-buffered for the reorder
-    double *x[2] = {nullptr, nullptr}, *y[2] = {nullptr, nullptr}, *th[2] = {nullptr, nullptr}, *a0[2] = {nullptr, nullptr};
+    double2 *xy[2] = {nullptr, nullptr};
+    double *th[2] = {nullptr, nullptr}, *a0[2] = {nullptr, nullptr};
     int64_t *gid[2] = {nullptr, nullptr};
     unsigned char *owned[2] = {nullptr, nullptr};
     int cur = 0;
@@ -115,8 +116,8 @@ int ensure_buf(AfvHandle h, DevBuf &b, size_t bytes) {
 
 void free_all(AfvHandle h) {
     for (int k = 0; k < 2; ++k) {
-        cudaFree(h->x[k]); cudaFree(h->y[k]); cudaFree(h->th[k]); cudaFree(h->a0[k]); cudaFree(h->gid[k]); cudaFree(h->owned[k]);
-        h->x[k] = h->y[k] = h->th[k] = h->a0[k] = nullptr; h->gid[k] = nullptr; h->owned[k] = nullptr;
+        cudaFree(h->xy[k]); cudaFree(h->th[k]); cudaFree(h->a0[k]); cudaFree(h->gid[k]); cudaFree(h->owned[k]);
+        h->xy[k] = nullptr; h->th[k] = h->a0[k] = nullptr; h->gid[k] = nullptr; h->owned[k] = nullptr;
     }
     cudaFree(h->keys); cudaFree(h->keys_sorted); cudaFree(h->iota); cudaFree(h->perm); cudaFree(h->bin_start);
     cudaFree(h->cub_tmp); cudaFree(h->fx); cudaFree(h->fy); cudaFree(h->area); cudaFree(h->perim); cudaFree(h->arcl);
@@ -135,31 +136,30 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     int64_t cap = std::max<int64_t>(want + want / 8, 1024);
     cap = std::min<int64_t>(cap, ((int64_t)1 << 31) - 1);
     // keep old state
-    double *ox = h->x[h->cur], *oy = h->y[h->cur], *ot = h->th[h->cur], *oa = h->a0[h->cur];
+    double2 *oxy = h->xy[h->cur];
+    double *ot = h->th[h->cur], *oa = h->a0[h->cur];
     int64_t *og = h->gid[h->cur];
     unsigned char *oo = h->owned[h->cur];
-    h->x[h->cur] = h->y[h->cur] = h->th[h->cur] = h->a0[h->cur] = nullptr; h->gid[h->cur] = nullptr; h->owned[h->cur] = nullptr;
+    h->xy[h->cur] = nullptr; h->th[h->cur] = h->a0[h->cur] = nullptr; h->gid[h->cur] = nullptr; h->owned[h->cur] = nullptr;
     free_all(h);
     int rc = AFV_OK;
     for (int k = 0; k < 2 && rc == AFV_OK; ++k) {
-        if ((rc = dev_alloc(h, &h->x[k], cap))) break;
-        if ((rc = dev_alloc(h, &h->y[k], cap))) break;
+        if ((rc = dev_alloc(h, &h->xy[k], cap))) break;
         if ((rc = dev_alloc(h, &h->th[k], cap))) break;
         if ((rc = dev_alloc(h, &h->a0[k], cap))) break;
         if ((rc = dev_alloc(h, &h->gid[k], cap))) break;
         if ((rc = dev_alloc(h, &h->owned[k], cap))) break;
     }
-    if (rc == AFV_OK && keep > 0 && ox) {
+    if (rc == AFV_OK && keep > 0 && oxy) {
         h->cur = 0;
-        cudaMemcpyAsync(h->x[0], ox, keep * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
-        cudaMemcpyAsync(h->y[0], oy, keep * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->xy[0], oxy, keep * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream);
         cudaMemcpyAsync(h->th[0], ot, keep * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
         cudaMemcpyAsync(h->a0[0], oa, keep * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
         cudaMemcpyAsync(h->gid[0], og, keep * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream);
         cudaMemcpyAsync(h->owned[0], oo, keep, cudaMemcpyDeviceToDevice, h->stream);
         cudaStreamSynchronize(h->stream);
     }
-    cudaFree(ox); cudaFree(oy); cudaFree(ot); cudaFree(oa); cudaFree(og); cudaFree(oo);
+    cudaFree(oxy); cudaFree(ot); cudaFree(oa); cudaFree(og); cudaFree(oo);
     if (rc) return rc;
     // bins: up to 2 per cell, power of two so that the sort width is fixed
     int bits = 6;
@@ -259,15 +259,15 @@ int stage_sort(AfvHandle h) {
         if (rc) return rc;
     } else {
         int nb = std::min(nblk(n, 256), 1024);
-        k_bbox_partial<<<nb, 256, 0, h->stream>>>(h->x[c], h->y[c], n, h->bbox_part);
+        k_bbox_partial<<<nb, 256, 0, h->stream>>>(h->xy[c], n, h->bbox_part);
         k_bbox_final<<<1, 32, 0, h->stream>>>(h->bbox_part, nb, h->prm.r, h->nbins_cap, h->d_grid);
         h->launches += 2;
     }
-    k_bin_keys<<<nblk(n, 256), 256, 0, h->stream>>>(h->x[c], h->y[c], n, h->d_grid, h->keys);
+    k_bin_keys<<<nblk(n, 256), 256, 0, h->stream>>>(h->xy[c], n, h->d_grid, h->keys);
     size_t tmp = h->cub_tmp_bytes;
     CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->keys, h->keys_sorted, h->iota, h->perm, n, 0, h->key_bits, h->stream));
-    k_reorder<<<nblk(n, 256), 256, 0, h->stream>>>(h->perm, n, h->x[c], h->y[c], h->th[c], h->a0[c], h->gid[c], h->owned[c],
-                                                    h->x[o], h->y[o], h->th[o], h->a0[o], h->gid[o], h->owned[o]);
+    k_reorder<<<nblk(n, 256), 256, 0, h->stream>>>(h->perm, n, h->xy[c], h->th[c], h->a0[c], h->gid[c], h->owned[c],
+                                                    h->xy[o], h->th[o], h->a0[o], h->gid[o], h->owned[o]);
     h->cur = o;
     // the number of bins is a device-side quantity in the open case: launch for the capacity, threads beyond
     // nbx*nby exit immediately
@@ -291,7 +291,7 @@ int stage_geometry(AfvHandle h) {
     const int n = (int)h->n;
     const int c = h->cur;
     GeomArgs a;
-    a.x = h->x[c]; a.y = h->y[c]; a.a0 = h->a0[c]; a.keys = h->keys_sorted; a.bin_start = h->bin_start; a.grid = h->d_grid;
+    a.xy = h->xy[c]; a.a0 = h->a0[c]; a.keys = h->keys_sorted; a.bin_start = h->bin_start; a.grid = h->d_grid;
     a.n = n; a.ph = phys_dev(h->prm); a.rs = h->rs; a.ro = h->ro; a.ring_len = h->ring_len;
     a.area = h->area; a.perim = h->perim; a.arcl = h->arcl; a.coord = h->coord; a.flags = h->flags;
     a.ovf_cells = h->ovf_cells; a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
@@ -299,10 +299,10 @@ int stage_geometry(AfvHandle h) {
     // within 2r is known, 4 pi r^2 N / L^2; otherwise start at 32 and grow when the slow path gets busy
     if (h->L > 0.0) {
         const double mean = 4.0 * 3.141592653589793 * h->prm.r * h->prm.r * (double)h->n / (h->L * h->L);
-        h->cmax_hint = std::max(h->cmax_hint, std::min(CMAX_HARD, std::max(24, (int)(1.6 * mean) + 12)));
+        h->cmax_hint = std::max(h->cmax_hint, std::min(CMAX_HARD, std::max(24, (int)(1.8 * mean) + 12)));
     }
     int cmax = h->cmax_hint;
-    const size_t smem = (size_t)cmax * HULL_TPB * sizeof(double2);
+    const size_t smem = (size_t)cmax * HULL_TPB * sizeof(int);
     k_geometry_hull<<<nblk(n, HULL_TPB), HULL_TPB, smem, h->stream>>>(a, cmax);
     // cells queued by the fast kernel (usually none): large-capacity path, reads the queue length on the device
     k_geometry_slow<<<16, 64, 0, h->stream>>>(a);
@@ -320,7 +320,7 @@ int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, doub
     a.rs = h->rs; a.ro = h->ro; a.ring_len = h->ring_len; a.owned = h->owned[c]; a.gid = h->gid[c]; a.n = n;
     a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
     a.ph = phys_dev(h->prm); a.fx = h->fx; a.fy = h->fy; a.flags = h->flags;
-    a.do_step = do_step ? 1 : 0; a.x = h->x[c]; a.y = h->y[c]; a.theta = h->th[c];
+    a.do_step = do_step ? 1 : 0; a.xy = h->xy[c]; a.theta = h->th[c];
     a.dt = dt; a.mu = mu; a.v0 = v0; a.noise_amp = std::sqrt(2.0 * Dr * dt); a.seed = seed; a.step = step;
     a.noise = noise_row; a.L = h->L;
     k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
@@ -415,7 +415,7 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
     cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream);
-    cudaFuncSetAttribute(k_geometry_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(double2));
+    cudaFuncSetAttribute(k_geometry_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(int));
     *out = h;
     return AFV_OK;
 }
@@ -456,8 +456,6 @@ int afv_set_positions(AfvHandle h, const double *xy_host, int64_t N) {
     }
     const int n = (int)N;
     const int c = h->cur, o = 1 - c;
-    if ((rc = ensure_buf(h, h->scratch_a, (size_t)std::max<int64_t>(N, 1) * 2 * sizeof(double)))) return rc;
-    if (N > 0) CK(cudaMemcpyAsync(h->scratch_a.p, xy_host, (size_t)N * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if (same && N > 0) {
         // bring theta and A0 back to the caller's order, then reset the order
         k_unsort_f64<<<nblk(n, 256), 256, 0, h->stream>>>(h->th[c], h->gid[c], n, h->th[o], 1, 0);
@@ -470,7 +468,9 @@ int afv_set_positions(AfvHandle h, const double *xy_host, int64_t N) {
         h->launches += 2;
     }
     if (N > 0) {
-        k_init_cells<<<nblk(n, 256), 256, 0, h->stream>>>((const double *)h->scratch_a.p, n, h->x[h->cur], h->y[h->cur], h->gid[h->cur], h->owned[h->cur]);
+        // the caller's (N,2) row-major array is exactly the device layout
+        CK(cudaMemcpyAsync(h->xy[h->cur], xy_host, (size_t)N * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+        k_init_cells<<<nblk(n, 256), 256, 0, h->stream>>>(n, h->gid[h->cur], h->owned[h->cur]);
         h->launches += 1;
     }
     h->n = N; h->n_owned = N; h->gid_is_perm = true; h->built = false;
@@ -544,7 +544,7 @@ int afv_build(AfvHandle h, unsigned flags) {
         if ((rc = ensure_buf(h, h->ring_xy, (size_t)std::max(total, 1) * 2 * sizeof(double)))) return rc;
         if ((rc = ensure_buf(h, h->ring_off, (size_t)(n + 1) * sizeof(int)))) return rc;
         CK(cudaMemcpyAsync(h->ring_off.p, h->off, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
-        k_ring_emit<<<nblk(n), TPB, 0, h->stream>>>(ring_view(h), h->gid[c], h->x[c], h->y[c], n, (const int *)h->ring_off.p,
+        k_ring_emit<<<nblk(n), TPB, 0, h->stream>>>(ring_view(h), h->gid[c], h->xy[c], n, (const int *)h->ring_off.p,
                                                     (signed char *)h->ring_types.p, (double *)h->ring_xy.p);
         h->n_ring = total;
         h->launches += 3;
@@ -584,7 +584,15 @@ double afv_philox_normal(uint64_t seed, int64_t cell_id, int64_t step) { return 
 int afv_get_positions(AfvHandle h, double *out) {
     CHECK_H(h);
     if (h->n == 0) return AFV_OK;
-    return get_unsorted(h, h->x[h->cur], out, 2, 2, h->y[h->cur]);
+    if (!h->gid_is_perm) { h->err = "results in caller order are only defined for handles filled by afv_set_positions"; return AFV_ERR_STATE; }
+    const int n = (int)h->n;
+    int rc = ensure_buf(h, h->scratch_a, (size_t)n * sizeof(double2));
+    if (rc) return rc;
+    k_unsort_xy<<<nblk(n, 256), 256, 0, h->stream>>>(h->xy[h->cur], h->gid[h->cur], n, (double2 *)h->scratch_a.p);
+    h->launches += 1;
+    CK(cudaMemcpyAsync(out, h->scratch_a.p, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AFV_OK;
 }
 int afv_get_theta(AfvHandle h, double *out) {
     CHECK_H(h);
@@ -728,8 +736,7 @@ void *afv_device_ptr(AfvHandle h, int field) {
     if (!h) return nullptr;
     const int c = h->cur;
     switch (field) {
-        case AFV_F_X: return h->x[c];
-        case AFV_F_Y: return h->y[c];
+        case AFV_F_XY: return h->xy[c];
         case AFV_F_THETA: return h->th[c];
         case AFV_F_A0: return h->a0[c];
         case AFV_F_GID: return h->gid[c];

@@ -16,7 +16,8 @@
 // of this cell (cell_geom.pyx:478-539), written as ring records.
 
 struct GeomArgs {
-    const double *x, *y, *a0;
+    const double2 *xy;
+    const double *a0;
     const unsigned *keys;      // sorted
     const int *bin_start;
     const GridDesc *grid;
@@ -231,7 +232,7 @@ __device__ __forceinline__ int cell_rows(const GridDesc &g, int by, int (&rows)[
 // ------------------------------------------------------------------------------------------------------
 constexpr int HULL_TPB = 128;
 constexpr int KHULL = 16;        // hull vertices (= polygon edges) on the fast path
-constexpr int CMAX_HARD = 60;    // upper bound of the per-cell candidate list (the launch picks cmax <= this)
+constexpr int CMAX_HARD = 64;    // upper bound of the per-cell candidate list (the launch picks cmax <= this)
 
 __device__ __forceinline__ void virtual_nbr(int v, double B4, double &x, double &y) {
     // four virtual neighbours at distance 4r whose bisectors are the sides of the bounding square of half side 2r
@@ -240,21 +241,24 @@ __device__ __forceinline__ void virtual_nbr(int v, double B4, double &x, double 
 }
 
 __global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const int cmax) {
-    extern __shared__ double2 s_cand[];          // [cmax][HULL_TPB]
+    extern __shared__ int s_idx[];               // [cmax][HULL_TPB]: sorted slots of the in-range neighbours of each lane's cell
     const int tid = threadIdx.x;
     const int s = blockIdx.x * HULL_TPB + tid;
     const bool live = s < a.n;
     const double r = a.ph.r, cut2 = 4.0 * r * r, B4 = 4.0 * r;
-    int cidx[CMAX_HARD];                          // sorted slot of every gathered candidate (read back for <= 16 of them)
+    const GridDesc g = *a.grid;
     int n = 0, imin = 0;
     bool ok = true;
+    double xi = 0.0, yi = 0.0;
+    bool wrapcell = false;                        // only cells in the outermost bins can see a periodic image
 
     // ---- gather the neighbours within 2r ----
     if (live) {
-        const double xi = a.x[s], yi = a.y[s];
-        const GridDesc g = *a.grid;
+        const double2 pi_ = a.xy[s];
+        xi = pi_.x; yi = pi_.y;
         const unsigned key = a.keys[s];
         const int by = (int)(key / (unsigned)g.nbx), bx = (int)(key - (unsigned)by * (unsigned)g.nbx);
+        wrapcell = g.periodic && (bx == 0 || by == 0 || bx == g.nbx - 1 || by == g.nby - 1 || g.nbx < 3 || g.nby < 3);
         int rows[3];
         const int nrow = cell_rows(g, by, rows);
         double dmin = 1e300;
@@ -262,14 +266,15 @@ __global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const in
             int c0[2], c1[2];
             const int nrun = row_runs(g, a.bin_start, rows[ir], bx, c0, c1);
             for (int q = 0; q < nrun; ++q) {
+#pragma unroll 4
                 for (int c = c0[q]; c < c1[q]; ++c) {
-                    double dx = a.x[c] - xi, dy = a.y[c] - yi;
-                    if (g.periodic) { dx = min_image(dx, g.L, g.halfL); dy = min_image(dy, g.L, g.halfL); }
+                    const double2 pc = a.xy[c];
+                    double dx = pc.x - xi, dy = pc.y - yi;
+                    if (wrapcell) { dx = min_image(dx, g.L, g.halfL); dy = min_image(dy, g.L, g.halfL); }
                     const double d2 = dx * dx + dy * dy;
                     if (d2 < cut2 && c != s && d2 > 0.0) {
                         if (n < cmax) {
-                            s_cand[n * HULL_TPB + tid] = make_double2(dx, dy);
-                            cidx[n] = c;
+                            s_idx[n * HULL_TPB + tid] = c;
                             if (d2 < dmin) { dmin = d2; imin = n; }
                             ++n;
                         } else ok = false;
@@ -278,13 +283,22 @@ __global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const in
             }
         }
     }
+    // displacement of list entry c (c >= n: virtual neighbour c - n)
+    auto disp = [&](int c, double &dx, double &dy) {
+        if (c < n) {
+            const double2 pc = a.xy[s_idx[c * HULL_TPB + tid]];
+            dx = pc.x - xi; dy = pc.y - yi;
+            if (wrapcell) { dx = min_image(dx, g.L, g.halfL); dy = min_image(dy, g.L, g.halfL); }
+        } else virtual_nbr(c - n, B4, dx, dy);
+    };
 
     // ---- gift wrapping in the dual plane.  Candidate c <-> homogeneous dual point (p_c, k_c), k_c = |p_c|^2 / 2.
-    //      orient(a, b, c) = sign((p_b k_a - p_a k_b) x (p_c k_a - p_a k_c));  the nearest neighbour is on the hull. ----
-    unsigned long long hull_lo = 0ull, hull_hi = 0ull;   // 16 x 8-bit candidate indices (n..n+3 = virtual)
+    //      orient(a, b, c) = sign((p_b k_a - p_a k_b) x (p_c k_a - p_a k_c));  the nearest neighbour is on the hull.
+    //      Two independent running-best chains (even / odd list entries) halve the dependent latency. ----
+    unsigned long long hull_lo = 0ull, hull_hi = 0ull;   // 16 x 8-bit list indices (n..n+3 = virtual)
     int m = 0;
     const bool wrap = live && ok && n > 0;
-    const int nreal_max = __reduce_max_sync(FULL_MASK, wrap ? n : 0);
+    const int npair_max = (__reduce_max_sync(FULL_MASK, wrap ? n : 0) + 1) >> 1;
     bool done = !wrap;
     int cur = imin;
     while (__any_sync(FULL_MASK, !done)) {
@@ -292,51 +306,62 @@ __global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const in
         if (!done) {
             if (m < 8) hull_lo |= (unsigned long long)cur << (8 * m); else hull_hi |= (unsigned long long)cur << (8 * (m - 8));
             ++m;
-            if (cur < n) { const double2 p = s_cand[cur * HULL_TPB + tid]; pax = p.x; pay = p.y; }
-            else virtual_nbr(cur - n, B4, pax, pay);
+            disp(cur, pax, pay);
             ka = 0.5 * (pax * pax + pay * pay);
         }
-        int best = -1;
-        double ux = 0.0, uy = 0.0;
-        for (int c = 0; c < nreal_max; ++c) {
-            if (!done && c < n && c != cur) {
-                const double2 p = s_cand[c * HULL_TPB + tid];
-                const double kc = 0.5 * (p.x * p.x + p.y * p.y);
-                const double wx = p.x * ka - pax * kc, wy = p.y * ka - pay * kc;
-                if (best < 0 || ux * wy - uy * wx < 0.0) { best = c; ux = wx; uy = wy; }
+        int best0 = -1, best1 = -1;
+        double u0x = 0.0, u0y = 0.0, u1x = 0.0, u1y = 0.0;
+        for (int cp = 0; cp < npair_max; ++cp) {
+            const int ca = 2 * cp, cb = 2 * cp + 1;
+            if (!done && ca < n && ca != cur) {
+                double qx_, qy_; disp(ca, qx_, qy_);
+                const double kc = 0.5 * (qx_ * qx_ + qy_ * qy_);
+                const double wx = qx_ * ka - pax * kc, wy = qy_ * ka - pay * kc;
+                if (best0 < 0 || u0x * wy - u0y * wx < 0.0) { best0 = ca; u0x = wx; u0y = wy; }
+            }
+            if (!done && cb < n && cb != cur) {
+                double qx_, qy_; disp(cb, qx_, qy_);
+                const double kc = 0.5 * (qx_ * qx_ + qy_ * qy_);
+                const double wx = qx_ * ka - pax * kc, wy = qy_ * ka - pay * kc;
+                if (best1 < 0 || u1x * wy - u1y * wx < 0.0) { best1 = cb; u1x = wx; u1y = wy; }
             }
         }
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < 4; ++v) {     // the four virtual neighbours, two per chain
             if (!done && n + v != cur) {
                 double qx_, qy_;
                 virtual_nbr(v, B4, qx_, qy_);
                 const double kc = 0.5 * B4 * B4;
                 const double wx = qx_ * ka - pax * kc, wy = qy_ * ka - pay * kc;
-                if (best < 0 || ux * wy - uy * wx < 0.0) { best = n + v; ux = wx; uy = wy; }
+                if (v & 1) { if (best1 < 0 || u1x * wy - u1y * wx < 0.0) { best1 = n + v; u1x = wx; u1y = wy; } }
+                else       { if (best0 < 0 || u0x * wy - u0y * wx < 0.0) { best0 = n + v; u0x = wx; u0y = wy; } }
             }
         }
         if (!done) {
+            // merge the chains: the overall next hull vertex is the one with every other point on its left
+            int best = best0;
+            if (best0 < 0 || (best1 >= 0 && u0x * u1y - u0y * u1x < 0.0)) best = best1;
             cur = best;
             if (cur == imin) done = true;
             else if (m >= KHULL) { ok = false; done = true; }
         }
     }
 
-    // ---- polygon: edge k = hull vertex k, vertex k = bisector(k-1) ^ bisector(k) ----
-    double vx[KHULL], vy[KHULL], px[KHULL], py[KHULL];
+    // ---- polygon edges (counter-clockwise): edge k = hull vertex k.  Local copies of the <= 16 edges. ----
+    double px[KHULL], py[KHULL];
     int lab[KHULL];
     const int mm = (wrap && ok) ? m : 0;
     const int mloop = __reduce_max_sync(FULL_MASK, mm);
     for (int k = 0; k < mloop; ++k) {
         if (k < mm) {
             const int h = (int)(((k < 8) ? (hull_lo >> (8 * k)) : (hull_hi >> (8 * (k - 8)))) & 0xffull);
-            if (h < n) { const double2 p = s_cand[h * HULL_TPB + tid]; px[k] = p.x; py[k] = p.y; lab[k] = cidx[h]; }
-            else { virtual_nbr(h - n, B4, px[k], py[k]); lab[k] = -2; }
+            disp(h, px[k], py[k]);
+            lab[k] = (h < n) ? s_idx[h * HULL_TPB + tid] : -2;
         }
     }
+    double vx[KHULL], vy[KHULL];
     for (int k = 0; k < mloop; ++k) {
-        if (k < mm) {
+        if (k < mm) {   // vertex k = bisector(k-1) ^ bisector(k)
             const int km = (k == 0) ? mm - 1 : k - 1;
             const double ax = px[km], ay = py[km], bx_ = px[k], by_ = py[k];
             const double ca = 0.5 * (ax * ax + ay * ay), cb = 0.5 * (bx_ * bx_ + by_ * by_);
@@ -354,7 +379,7 @@ __global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const in
 __device__ __noinline__ void geom_cell_slow(const GeomArgs &a, const int s, const int pool_idx) {
     constexpr int K = KPOLY_SLOW;
     const double r = a.ph.r, cut2 = 4.0 * r * r;
-    const double xi = a.x[s], yi = a.y[s];
+    const double xi = a.xy[s].x, yi = a.xy[s].y;
     const GridDesc g = *a.grid;
     const unsigned key = a.keys[s];
     const int by = (int)(key / (unsigned)g.nbx), bx = (int)(key - (unsigned)by * (unsigned)g.nbx);
@@ -376,7 +401,8 @@ __device__ __noinline__ void geom_cell_slow(const GeomArgs &a, const int s, cons
         for (int q = 0; q < nrun; ++q) {
             for (int c = c0[q]; c < c1[q]; ++c) {
                 if (c == s) continue;
-                double dx = a.x[c] - xi, dy = a.y[c] - yi;
+                const double2 pc = a.xy[c];
+                double dx = pc.x - xi, dy = pc.y - yi;
                 if (g.periodic) { dx = min_image(dx, g.L, g.halfL); dy = min_image(dy, g.L, g.halfL); }
                 const double d2 = dx * dx + dy * dy;
                 if (d2 >= cut2 || d2 == 0.0) continue;

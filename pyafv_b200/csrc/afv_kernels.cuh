@@ -11,12 +11,13 @@ struct PhysDev {
 // ------------------------------------------------------------------------------------------------------
 // K0: bounding box (open boundaries) -> grid description, entirely on the device
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_bbox_partial(const double *__restrict__ x, const double *__restrict__ y, int n, double *__restrict__ part) {
+__global__ void k_bbox_partial(const double2 *__restrict__ xy, int n, double *__restrict__ part) {
     // part: [4 * gridDim.x] = xmin, xmax, ymin, ymax per block
     __shared__ double sm[4][32];
     double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double a = x[i], b = y[i];
+        const double2 q = xy[i];
+        const double a = q.x, b = q.y;
         xmin = fmin(xmin, a); xmax = fmax(xmax, a); ymin = fmin(ymin, b); ymax = fmax(ymax, b);
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -71,27 +72,27 @@ __global__ void k_bbox_final(const double *__restrict__ part, int nblocks, doubl
 // ------------------------------------------------------------------------------------------------------
 // K1a: bin hash.  key = by * nbx + bx  (row-major so that the 3 bins of a row are contiguous after the sort)
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_bin_keys(const double *__restrict__ x, const double *__restrict__ y, int n,
-                           const GridDesc *__restrict__ gp, unsigned *__restrict__ keys) {
+__global__ void k_bin_keys(const double2 *__restrict__ xy, int n, const GridDesc *__restrict__ gp, unsigned *__restrict__ keys) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const GridDesc g = *gp;
-    int bx = (int)floor((x[i] - g.x0) * g.inv_bx), by = (int)floor((y[i] - g.y0) * g.inv_by);
+    const double2 q = xy[i];
+    int bx = (int)floor((q.x - g.x0) * g.inv_bx), by = (int)floor((q.y - g.y0) * g.inv_by);
     bx = min(max(bx, 0), g.nbx - 1);
     by = min(max(by, 0), g.nby - 1);
     keys[i] = (unsigned)(by * g.nbx + bx);
 }
 
 // K1b: gather the SoA state into sorted order
-__global__ void k_reorder(const int *__restrict__ perm, int n, const double *__restrict__ x0, const double *__restrict__ y0,
+__global__ void k_reorder(const int *__restrict__ perm, int n, const double2 *__restrict__ xy0,
                           const double *__restrict__ t0, const double *__restrict__ a0, const int64_t *__restrict__ g0,
-                          const unsigned char *__restrict__ o0, double *__restrict__ x1, double *__restrict__ y1,
+                          const unsigned char *__restrict__ o0, double2 *__restrict__ xy1,
                           double *__restrict__ t1, double *__restrict__ a1, int64_t *__restrict__ g1,
                           unsigned char *__restrict__ o1) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     int p = perm[s];
-    x1[s] = x0[p]; y1[s] = y0[p]; t1[s] = t0[p]; a1[s] = a0[p]; g1[s] = g0[p]; o1[s] = o0[p];
+    xy1[s] = xy0[p]; t1[s] = t0[p]; a1[s] = a0[p]; g1[s] = g0[p]; o1[s] = o0[p];
 }
 
 // K1c: first sorted slot of every bin (lower bound), bin_start[nbins] = n
@@ -130,7 +131,8 @@ struct ForceArgs {
     int *flags;
     // step (do_step != 0)
     int do_step;
-    double *x, *y, *theta;
+    double2 *xy;
+    double *theta;
     double dt, mu, v0, noise_amp;  // noise_amp = sqrt(2 Dr dt)
     uint64_t seed;
     int64_t step;
@@ -231,8 +233,9 @@ __global__ void __launch_bounds__(128) k_force(ForceArgs a) {
         const double th = a.theta[s];
         double sn, cs_;
         sincos(th, &sn, &cs_);
-        double xn = a.x[s] + (a.mu * Fx + a.v0 * cs_) * a.dt;
-        double yn = a.y[s] + (a.mu * Fy + a.v0 * sn) * a.dt;
+        const double2 pos = a.xy[s];
+        double xn = pos.x + (a.mu * Fx + a.v0 * cs_) * a.dt;
+        double yn = pos.y + (a.mu * Fy + a.v0 * sn) * a.dt;
         if (a.L > 0.0) {
             xn -= a.L * floor(xn / a.L); yn -= a.L * floor(yn / a.L);
             if (xn >= a.L) xn = 0.0;
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(128) k_force(ForceArgs a) {
             const int64_t id = a.gid[s];
             xi_ = a.noise ? a.noise[id] : philox_normal(a.seed, id, a.step);
         }
-        a.x[s] = xn; a.y[s] = yn; a.theta[s] = th + a.noise_amp * xi_;
+        a.xy[s] = make_double2(xn, yn); a.theta[s] = th + a.noise_amp * xi_;
     }
 }
 
@@ -252,11 +255,14 @@ __global__ void __launch_bounds__(128) k_force(ForceArgs a) {
 // ------------------------------------------------------------------------------------------------------
 __global__ void k_iota(int *p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
 
-__global__ void k_init_cells(const double *__restrict__ xy, int n, double *__restrict__ x, double *__restrict__ y,
-                             int64_t *__restrict__ gid, unsigned char *__restrict__ owned) {
+__global__ void k_init_cells(int n, int64_t *__restrict__ gid, unsigned char *__restrict__ owned) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    x[i] = xy[2 * i]; y[i] = xy[2 * i + 1]; gid[i] = i; owned[i] = 1;
+    gid[i] = i; owned[i] = 1;
+}
+__global__ void k_unsort_xy(const double2 *__restrict__ src, const int64_t *__restrict__ gid, int n, double2 *__restrict__ out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) out[gid[s]] = src[s];
 }
 
 __global__ void k_fill(double *p, int n, double v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
@@ -333,14 +339,14 @@ __global__ void k_ring_len_by_gid(RingView rv, const int64_t *__restrict__ gid, 
     const RingShared *rs; const RingOwn *ro;
     len_out[gid[s]] = rv.get(s, rs, ro);
 }
-__global__ void k_ring_emit(RingView rv, const int64_t *__restrict__ gid, const double *__restrict__ x, const double *__restrict__ y, int n,
+__global__ void k_ring_emit(RingView rv, const int64_t *__restrict__ gid, const double2 *__restrict__ xy, int n,
                             const int *__restrict__ off_by_gid, signed char *__restrict__ types, double *__restrict__ vxy) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const RingShared *rs; const RingOwn *ro;
     const int E = rv.get(s, rs, ro);
     const int o = off_by_gid[gid[s]];
-    const double xi = x[s], yi = y[s];
+    const double xi = xy[s].x, yi = xy[s].y;
     for (int e = 0; e < E; ++e) {
         types[o + e] = (signed char)rs[e].type;
         const RingOwn q = ro[e];
@@ -351,31 +357,32 @@ __global__ void k_ring_emit(RingView rv, const int64_t *__restrict__ gid, const 
 // ------------------------------------------------------------------------------------------------------
 // slab sharding helpers.  Rows are (n,5) float64: x, y, theta, A0, gid
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_unpack_rows(const double *__restrict__ rows, int n, int offset, int n_owned_in_rows, double *__restrict__ x,
-                              double *__restrict__ y, double *__restrict__ th, double *__restrict__ a0, int64_t *__restrict__ gid,
+__global__ void k_unpack_rows(const double *__restrict__ rows, int n, int offset, int n_owned_in_rows, double2 *__restrict__ xy,
+                              double *__restrict__ th, double *__restrict__ a0, int64_t *__restrict__ gid,
                               unsigned char *__restrict__ owned) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double *q = rows + 5 * (size_t)i;
     const int d = offset + i;
-    x[d] = q[0]; y[d] = q[1]; th[d] = q[2]; a0[d] = q[3]; gid[d] = (int64_t)q[4];
+    xy[d] = make_double2(q[0], q[1]); th[d] = q[2]; a0[d] = q[3]; gid[d] = (int64_t)q[4];
     owned[d] = (i < n_owned_in_rows) ? 1 : 0;
 }
-__global__ void k_pack_rows(const int *__restrict__ idx, int m, double x_shift, const double *__restrict__ x, const double *__restrict__ y,
+__global__ void k_pack_rows(const int *__restrict__ idx, int m, double x_shift, const double2 *__restrict__ xy,
                             const double *__restrict__ th, const double *__restrict__ a0, const int64_t *__restrict__ gid,
                             double *__restrict__ rows) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const int s = idx[i];
     double *q = rows + 5 * (size_t)i;
-    q[0] = x[s] + x_shift; q[1] = y[s]; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
+    q[0] = xy[s].x + x_shift; q[1] = xy[s].y; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
 }
 // flag = owned && x in [lo,hi)   (invert != 0: the complement, i.e. the cells to keep)
-__global__ void k_flag_slab(const double *__restrict__ x, const unsigned char *__restrict__ owned, int n, double lo, double hi, int invert,
+__global__ void k_flag_slab(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, double lo, double hi, int invert,
                             int *__restrict__ flag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int sel = (owned[i] && x[i] >= lo && x[i] < hi) ? 1 : 0;
+    const double xv = xy[i].x;
+    const int sel = (owned[i] && xv >= lo && xv < hi) ? 1 : 0;
     flag[i] = invert ? 1 - sel : sel;
 }
 __global__ void k_flag_owned(const unsigned char *__restrict__ owned, int n, int *__restrict__ flag) {
