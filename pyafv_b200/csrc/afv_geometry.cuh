@@ -347,30 +347,164 @@ __global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const in
         }
     }
 
-    // ---- polygon edges (counter-clockwise): edge k = hull vertex k.  Local copies of the <= 16 edges. ----
-    double px[KHULL], py[KHULL];
-    int lab[KHULL];
+    // ---- ring, streamed.  The polygon edges are the hull vertices h_0..h_{m-1} (counter-clockwise); the ring is
+    //      clockwise, so edge k is walked from vertex k+1 to vertex k for k = m-1 .. 0 (finite_voronoi.py:363-459).
+    //      Ring records are written as they are produced; their gx/gy slots double as scratch (1/length of a
+    //      straight edge, or the (cross, dot) of an arc's end points) until the last pass overwrites them, so the
+    //      kernel keeps no per-thread arrays at all. ----
+    const double r2 = r * r;
+    const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
+    RingShared *const rs = a.rs + (size_t)s * RS;
+    RingOwn *const ro = a.ro + (size_t)s * RS;
     const int mm = (wrap && ok) ? m : 0;
     const int mloop = __reduce_max_sync(FULL_MASK, mm);
-    for (int k = 0; k < mloop; ++k) {
-        if (k < mm) {
-            const int h = (int)(((k < 8) ? (hull_lo >> (8 * k)) : (hull_hi >> (8 * (k - 8)))) & 0xffull);
-            disp(h, px[k], py[k]);
-            lab[k] = (h < n) ? s_idx[h * HULL_TPB + tid] : -2;
+    auto hull_at = [&](int k) { return (int)(((k < 8) ? (hull_lo >> (8 * k)) : (hull_hi >> (8 * (k - 8)))) & 0xffull); };
+    auto isect = [](double ax, double ay, double bx_, double by_, double &x, double &y) {
+        const double ca = 0.5 * (ax * ax + ay * ay), cb = 0.5 * (bx_ * bx_ + by_ * by_);
+        const double idet = 1.0 / (ax * by_ - ay * bx_);
+        x = (ca * by_ - cb * ay) * idet;
+        y = (ax * cb - bx_ * ca) * idet;
+    };
+    int E = 0, z = 0;
+    unsigned arcmask = 0u;                       // bit e set: ring entry e starts an arc
+    double A = 0.0, P = 0.0;
+    double x0 = 0.0, y0 = 0.0;                   // first ring entry
+    double xp = 0.0, yp = 0.0;                   // previous ring entry (its record is written when the next one arrives)
+    int nbr_p = ARC;
+    // connect the previous entry to (x, y): measure the edge, then write the previous entry's shared record
+    auto close_prev = [&](double x, double y) {
+        RingShared o; o.nbr = nbr_p; o.type = (nbr_p != ARC) ? 1 : 0; o.w = 0.0;
+        if (nbr_p != ARC) {
+            const double sx = xp - x, sy = yp - y;
+            const double l = sqrt(sx * sx + sy * sy);
+            P += l;
+            A += -0.5 * (xp * y - yp * x);
+            o.gx = l > 0.0 ? 1.0 / l : 0.0; o.gy = 0.0;
+            ++z;
+        } else {
+            o.gx = x * yp - y * xp;              // v2 x v1
+            o.gy = xp * x + yp * y;              // v1 . v2
+        }
+        rs[E - 1] = o;
+    };
+    auto emit = [&](double x, double y, double ex, double ey, int nb) {
+        if (E >= RS) { ok = false; return; }
+        if (E > 0) close_prev(x, y); else { x0 = x; y0 = y; }
+        RingOwn q; q.hx = x; q.hy = y; q.px = ex; q.py = ey;
+        ro[E] = q;
+        if (nb == ARC) arcmask |= 1u << E;
+        xp = x; yp = y; nbr_p = nb; ++E;
+    };
+    {
+        double pcx = 0.0, pcy = 0.0, pnx = 0.0, pny = 0.0, V1x = 0.0, V1y = 0.0;
+        int hc = 0;
+        if (mm > 0) {
+            hc = hull_at(mm - 1);
+            disp(hc, pcx, pcy);
+            disp(hull_at(0), pnx, pny);
+            isect(pcx, pcy, pnx, pny, V1x, V1y);           // vertex m = vertex 0 = edge(m-1) ^ edge(0)
+        }
+        for (int kk = 0; kk < mloop; ++kk) {
+            if (kk < mm) {
+                const int k = mm - 1 - kk;
+                const int hp = hull_at(k == 0 ? mm - 1 : k - 1);
+                double ppx, ppy, V2x, V2y;
+                disp(hp, ppx, ppy);
+                isect(ppx, ppy, pcx, pcy, V2x, V2y);       // vertex k = edge(k-1) ^ edge(k)
+                if (hc < n && ok) {                        // a real neighbour (virtual edges emit nothing)
+                    const int j = s_idx[hc * HULL_TPB + tid];
+                    if (V1x * V1x + V1y * V1y <= r2) emit(V1x, V1y, pcx, pcy, j);      // inner start vertex, d1 <= r
+                    const double d2c = 0.25 * (pcx * pcx + pcy * pcy);               // |C|^2, C = p/2
+                    if (d2c < r2) {                        // the bisector crosses the disk
+                        const double inv = 0.5 / sqrt(d2c);
+                        const double ux = pcy * inv, uy = -pcx * inv;                  // clockwise unit vector along the edge
+                        const double t1 = V1x * ux + V1y * uy, t2 = V2x * ux + V2y * uy;
+                        const double tr = sqrt(r2 - d2c);
+                        if (-tr < t2 && -tr > t1) emit(0.5 * pcx - tr * ux, 0.5 * pcy - tr * uy, pcx, pcy, j);   // entry point
+                        if (tr < t2 && tr > t1) emit(0.5 * pcx + tr * ux, 0.5 * pcy + tr * uy, pcx, pcy, ARC);  // exit point
+                    }
+                }
+                pcx = ppx; pcy = ppy; hc = hp; V1x = V2x; V1y = V2y;
+            }
         }
     }
-    double vx[KHULL], vy[KHULL];
-    for (int k = 0; k < mloop; ++k) {
-        if (k < mm) {   // vertex k = bisector(k-1) ^ bisector(k)
-            const int km = (k == 0) ? mm - 1 : k - 1;
-            const double ax = px[km], ay = py[km], bx_ = px[k], by_ = py[k];
-            const double ca = 0.5 * (ax * ax + ay * ay), cb = 0.5 * (bx_ * bx_ + by_ * by_);
-            const double idet = 1.0 / (ax * by_ - ay * bx_);
-            vx[k] = (ca * by_ - cb * ay) * idet;
-            vy[k] = (ax * cb - bx_ * ca) * idet;
+    const bool ringed = live && ok && E >= 2;
+    if (ringed) close_prev(x0, y0);              // closing edge: last entry -> first entry
+
+    if (live && !ok) {                           // queue the cell for the large-capacity kernel
+        const int idx = atomicAdd(&a.flags[0], 1);
+        if (idx < OVF_MAX) a.ovf_cells[idx] = s; else atomicAdd(&a.flags[3], 1);
+        a.ring_len[s] = 0;
+    }
+    if (live && ok && E < 2) {                   // isolated cell (cell_geom.pyx:402-406)
+        a.area[s] = PI * r2; a.perim[s] = TWO_PI * r; a.arcl[s] = TWO_PI * r; a.coord[s] = 0;
+        a.ring_len[s] = 0;
+    }
+
+    // ---- arcs: the lanes of a warp evaluate their q-th arc together (cell_geom.pyx:454-469) ----
+    double Larc = 0.0;
+    {
+        unsigned rem = ringed ? arcmask : 0u;
+        const int aloop = __reduce_max_sync(FULL_MASK, __popc(rem));
+        for (int q = 0; q < aloop; ++q) {
+            if (rem) {
+                const int e = __ffs(rem) - 1;
+                rem &= rem - 1;
+                double ang = atan2(rs[e].gx, rs[e].gy);   // angle(v1) - angle(v2)
+                if (ang < 0.0) ang += TWO_PI;
+                Larc += r * ang;
+                A += 0.5 * r2 * ang;
+            }
         }
     }
-    finish_cell<KHULL, RS, false>(a, s, 0, live, ok, vx, vy, px, py, lab, mm);
+    P += Larc;
+    double cA = 0.0, cP = 0.0, cL = 0.0;
+    if (ringed) {
+        a.area[s] = A; a.perim[s] = P; a.arcl[s] = Larc; a.coord[s] = z;
+        a.ring_len[s] = (unsigned char)E;
+        if (E > 12) atomicMax(&a.flags[2], E);
+        cA = 2.0 * a.ph.KA * (A - a.a0[s]);
+        cP = 2.0 * a.ph.KP * (P - a.ph.P0);
+        cL = cP + a.ph.Lambda;
+    }
+
+    // ---- per-vertex gradients of this cell (cell_geom.pyx:478-539), streamed over the ring records ----
+    {
+        const int EE = ringed ? E : 0;
+        const int Eloop = __reduce_max_sync(FULL_MASK, EE);
+        double hpx = 0.0, hpy = 0.0, hcx = 0.0, hcy = 0.0, ilp = 0.0, ilc = 0.0;
+        if (EE > 0) {
+            const double2 a0_ = *reinterpret_cast<const double2 *>(&ro[EE - 1]);
+            const double2 a1_ = *reinterpret_cast<const double2 *>(&ro[0]);
+            hpx = a0_.x; hpy = a0_.y; hcx = a1_.x; hcy = a1_.y;
+            ilp = ((arcmask >> (EE - 1)) & 1u) ? 0.0 : rs[EE - 1].gx;
+            ilc = (arcmask & 1u) ? 0.0 : rs[0].gx;
+        }
+        for (int e = 0; e < Eloop; ++e) {
+            if (e < EE) {
+                const int e2 = (e + 1 == EE) ? 0 : e + 1, e0 = (e == 0) ? EE - 1 : e - 1;
+                const double2 nx_ = *reinterpret_cast<const double2 *>(&ro[e2]);
+                const double hnx = nx_.x, hny = nx_.y;
+                const bool arc_c = (arcmask >> e) & 1u, arc_p = (arcmask >> e0) & 1u;
+                // next edge's 1/length must be read before this entry's record is overwritten when e2 == e (never: EE >= 2)
+                const double iln = ((arcmask >> e2) & 1u) ? 0.0 : rs[e2].gx;
+                // u(e) = (v1 - v2)/|v1 - v2| for straight edges, 0 for arcs;  dP/dv1 = u(e) - u(e-1);  dA/dv1 = 0.5 (perp(v0) - perp(v2))
+                const double uex = (hcx - hnx) * ilc, uey = (hcy - hny) * ilc;
+                const double upx = (hpx - hcx) * ilp, upy = (hpy - hcy) * ilp;
+                const double gx = cA * 0.5 * (hpy - hny) + cP * (uex - upx);
+                const double gy = cA * 0.5 * (hnx - hpx) + cP * (uey - upy);
+                double w = 0.0;
+                if (arc_c)       // an arc starts here: da = +0.5 r^2 (1 - cos D), dl = +r
+                    w = cA * 0.5 * (r2 - (hcx * hnx + hcy * hny)) + cL * r;
+                else if (arc_p)  // an arc ends here
+                    w = -(cA * 0.5 * (r2 - (hpx * hcx + hpy * hcy)) + cL * r);
+                double *dst = reinterpret_cast<double *>(&rs[e]);
+                // entry 0's scratch is still needed by the last entry (as "next"): keep it in a register
+                dst[1] = gx; dst[2] = gy; dst[3] = w;
+                hpx = hcx; hpy = hcy; hcx = hnx; hcy = hny; ilp = ilc; ilc = iln;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
