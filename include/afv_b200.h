@@ -134,6 +134,10 @@ int afv_measure_fp64_peak(AfvHandle h, double *tflops_out);
 void *afv_device_ptr(AfvHandle h, int field);
 void *afv_stream(AfvHandle h);
 int afv_synchronize(AfvHandle h);
+/* Turn a periodic handle (box_L > 0) into one x-slab of that box: the bin grid covers x in [grid_x0, grid_x1)
+ * without wrap (the caller supplies halo cells with x already shifted by +-L where the slab touches the box
+ * face), y stays periodic, and afv_step no longer wraps x (cells leaving the slab are migrated by the caller). */
+int afv_set_slab(AfvHandle h, double grid_x0, double grid_x1);
 /* Replace the device state by (x, y, theta, A0, gid) rows given in DEVICE memory: n_owned owned cells followed
  * by n_halo halo cells (halo cells take part in the geometry but receive no force / update).  rows: (n,5)
  * float64 row-major with gid stored as a float64-exact integer. */
@@ -147,6 +151,9 @@ int afv_drop_halo(AfvHandle h);
 /* append rows (device memory) as owned (is_halo = 0) or halo (is_halo = 1) cells */
 int afv_append_cells(AfvHandle h, const double *rows_dev, int64_t n, int is_halo);
 int64_t afv_num_owned(AfvHandle h);
+/* after afv_build: rows (count,11) of the OWNED cells in device memory:
+ * x, y, theta, A0, gid, fx, fy, area, perimeter, arclen, coord_num */
+int afv_pack_owned(AfvHandle h, double *rows_dev_out, int64_t capacity, int64_t *count);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,8 @@ struct AfvContext {
     bool own_stream = false;
     AfvParams prm{};
     double L = 0.0;
+    bool slab = false;          // x-slab of a periodic box: grid open in x over [slab_x0, slab_x1), periodic in y
+    double slab_x0 = 0.0, slab_x1 = 0.0;
     int64_t n = 0, n_owned = 0, cap = 0;
     bool gid_is_perm = true;  // gid is a permutation of 0..n-1 (single-GPU use); false after set_cells_device
     // SoA state, double-buffered for the reorder
@@ -237,14 +239,22 @@ RingView ring_view(AfvHandle h) { return RingView{h->rs, h->ro, h->ring_len, h->
 
 PhysDev phys_dev(const AfvParams &p) { return PhysDev{p.r, p.P0, p.KA, p.KP, p.Lambda, p.delta}; }
 
+// grid of a periodic box (or of an x-slab of it): returns the bin counts
+void periodic_grid(AfvHandle h, GridDesc &g) {
+    const double cut = 2.0 * h->prm.r;
+    int nby = std::max(1, (int)std::floor(h->L / cut));
+    const double wx = h->slab ? (h->slab_x1 - h->slab_x0) : h->L;
+    int nbx = std::max(1, (int)std::floor(wx / cut));
+    while ((int64_t)nbx * nby > h->nbins_cap) { if (nbx >= nby) --nbx; else --nby; }
+    g.x0 = h->slab ? h->slab_x0 : 0.0; g.y0 = 0.0;
+    g.inv_bx = (double)nbx / wx; g.inv_by = (double)nby / h->L;
+    g.Lx = h->L; g.halfLx = 0.5 * h->L; g.Ly = h->L; g.halfLy = 0.5 * h->L;
+    g.nbx = nbx; g.nby = nby; g.perx = h->slab ? 0 : 1; g.pery = 1;
+}
+
 int upload_grid_periodic(AfvHandle h) {
     GridDesc g{};
-    const double cut = 2.0 * h->prm.r;
-    int nb = (int)std::floor(h->L / cut);
-    if (nb < 1) nb = 1;
-    while ((int64_t)nb * nb > h->nbins_cap) --nb;
-    g.x0 = 0.0; g.y0 = 0.0; g.inv_bx = g.inv_by = (double)nb / h->L; g.L = h->L; g.halfL = 0.5 * h->L;
-    g.nbx = g.nby = nb; g.periodic = 1; g.pad = 0;
+    periodic_grid(h, g);
     CK(cudaMemcpyAsync(h->d_grid, &g, sizeof g, cudaMemcpyHostToDevice, h->stream));
     return AFV_OK;
 }
@@ -273,12 +283,10 @@ int stage_sort(AfvHandle h) {
     // nbx*nby exit immediately
     int64_t nb_launch = (h->L > 0.0) ? 0 : (int64_t)h->nbins_cap + 1;
     if (h->L > 0.0) {
-        const double cut = 2.0 * h->prm.r;
-        int64_t nb1 = (int64_t)std::floor(h->L / cut);
-        if (nb1 < 1) nb1 = 1;
-        while (nb1 * nb1 > h->nbins_cap) --nb1;
-        nb_launch = nb1 * nb1 + 1;
-        h->h_flags[3] = (int)(nb1 * nb1);
+        GridDesc g{};
+        periodic_grid(h, g);
+        nb_launch = (int64_t)g.nbx * g.nby + 1;
+        h->h_flags[3] = g.nbx * g.nby;
     }
     k_bin_start<<<nblk(nb_launch, 256), 256, 0, h->stream>>>(h->keys_sorted, n, h->d_grid, h->bin_start);
     h->launches += 4;  // keys, sort (counted once), reorder, bin_start
@@ -298,7 +306,8 @@ int stage_geometry(AfvHandle h) {
     // candidate-list capacity per cell (shared memory scales with it): for a periodic box the mean number of cells
     // within 2r is known, 4 pi r^2 N / L^2; otherwise start at 32 and grow when the slow path gets busy
     if (h->L > 0.0) {
-        const double mean = 4.0 * 3.141592653589793 * h->prm.r * h->prm.r * (double)h->n / (h->L * h->L);
+        const double area = h->L * (h->slab ? (h->slab_x1 - h->slab_x0) : h->L);
+        const double mean = 4.0 * 3.141592653589793 * h->prm.r * h->prm.r * (double)h->n / area;
         h->cmax_hint = std::max(h->cmax_hint, std::min(CMAX_HARD, std::max(24, (int)(1.8 * mean) + 12)));
     }
     int cmax = h->cmax_hint;
@@ -322,7 +331,7 @@ int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, doub
     a.ph = phys_dev(h->prm); a.fx = h->fx; a.fy = h->fy; a.flags = h->flags;
     a.do_step = do_step ? 1 : 0; a.xy = h->xy[c]; a.theta = h->th[c];
     a.dt = dt; a.mu = mu; a.v0 = v0; a.noise_amp = std::sqrt(2.0 * Dr * dt); a.seed = seed; a.step = step;
-    a.noise = noise_row; a.L = h->L;
+    a.noise = noise_row; a.Lx = h->slab ? 0.0 : h->L; a.Ly = h->L;
     k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
     h->launches += 1;
     CK(cudaGetLastError());

@@ -18,10 +18,10 @@ constexpr int RING_IN_POOL = 255; // ring_len sentinel: the ring lives in the ov
 struct GridDesc {
     double x0, y0;        // origin of bin (0,0)
     double inv_bx, inv_by; // 1 / bin side
-    double L, halfL;      // periodic box side (0 = open)
+    double Lx, halfLx;    // periodic period in x (used when perx)
+    double Ly, halfLy;    // periodic period in y (used when pery)
     int nbx, nby;
-    int periodic;
-    int pad;
+    int perx, pery;       // periodic wrap of the bin grid / minimum image per direction
 };
 
 // Shared part of a ring entry: what OTHER cells read during the force gather.  32 B = one DRAM sector.

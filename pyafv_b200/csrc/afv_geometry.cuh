@@ -194,8 +194,8 @@ __device__ __forceinline__ void finish_cell(const GeomArgs &a, const int s, cons
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int row_runs(const GridDesc &g, const int *__restrict__ bin_start, int row, int bx, int (&c0)[2], int (&c1)[2]) {
     const int base = row * g.nbx;
-    if (!g.periodic || g.nbx < 3) {
-        const int lo = g.periodic ? 0 : max(bx - 1, 0), hi = g.periodic ? g.nbx - 1 : min(bx + 1, g.nbx - 1);
+    if (!g.perx || g.nbx < 3) {
+        const int lo = g.perx ? 0 : max(bx - 1, 0), hi = g.perx ? g.nbx - 1 : min(bx + 1, g.nbx - 1);
         c0[0] = bin_start[base + lo]; c1[0] = bin_start[base + hi + 1];
         return 1;
     }
@@ -215,7 +215,7 @@ __device__ __forceinline__ int row_runs(const GridDesc &g, const int *__restrict
 
 // rows to visit for a cell in bin row `by`: returns the count, fills rows[]
 __device__ __forceinline__ int cell_rows(const GridDesc &g, int by, int (&rows)[3]) {
-    if (g.periodic) {
+    if (g.pery) {
         if (g.nby < 3) { for (int i = 0; i < g.nby; ++i) rows[i] = i; return g.nby; }
         rows[0] = (by == 0) ? g.nby - 1 : by - 1; rows[1] = by; rows[2] = (by == g.nby - 1) ? 0 : by + 1;
         return 3;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const in
     int n = 0, imin = 0;
     bool ok = true;
     double xi = 0.0, yi = 0.0;
-    bool wrapcell = false;                        // only cells in the outermost bins can see a periodic image
+    bool wrapx = false, wrapy = false;            // only cells in the outermost bins can see a periodic image
 
     // ---- gather the neighbours within 2r ----
     if (live) {
@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const in
         xi = pi_.x; yi = pi_.y;
         const unsigned key = a.keys[s];
         const int by = (int)(key / (unsigned)g.nbx), bx = (int)(key - (unsigned)by * (unsigned)g.nbx);
-        wrapcell = g.periodic && (bx == 0 || by == 0 || bx == g.nbx - 1 || by == g.nby - 1 || g.nbx < 3 || g.nby < 3);
+        wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);
+        wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
         int rows[3];
         const int nrow = cell_rows(g, by, rows);
         double dmin = 1e300;
@@ -270,7 +271,8 @@ __global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const in
                 for (int c = c0[q]; c < c1[q]; ++c) {
                     const double2 pc = a.xy[c];
                     double dx = pc.x - xi, dy = pc.y - yi;
-                    if (wrapcell) { dx = min_image(dx, g.L, g.halfL); dy = min_image(dy, g.L, g.halfL); }
+                    if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
+                    if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
                     const double d2 = dx * dx + dy * dy;
                     if (d2 < cut2 && c != s && d2 > 0.0) {
                         if (n < cmax) {
@@ -288,7 +290,8 @@ __global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const in
         if (c < n) {
             const double2 pc = a.xy[s_idx[c * HULL_TPB + tid]];
             dx = pc.x - xi; dy = pc.y - yi;
-            if (wrapcell) { dx = min_image(dx, g.L, g.halfL); dy = min_image(dy, g.L, g.halfL); }
+            if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
+            if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
         } else virtual_nbr(c - n, B4, dx, dy);
     };
 
@@ -537,7 +540,8 @@ __device__ __noinline__ void geom_cell_slow(const GeomArgs &a, const int s, cons
                 if (c == s) continue;
                 const double2 pc = a.xy[c];
                 double dx = pc.x - xi, dy = pc.y - yi;
-                if (g.periodic) { dx = min_image(dx, g.L, g.halfL); dy = min_image(dy, g.L, g.halfL); }
+                if (g.perx) dx = min_image(dx, g.Lx, g.halfLx);
+                if (g.pery) dy = min_image(dy, g.Ly, g.halfLy);
                 const double d2 = dx * dx + dy * dy;
                 if (d2 >= cut2 || d2 == 0.0) continue;
                 ok = ok && clip_polygon<K>(vx, vy, px, py, lab, m, dx, dy, 0.5 * d2, c);

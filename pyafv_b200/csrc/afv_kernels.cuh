@@ -65,7 +65,7 @@ __global__ void k_bbox_final(const double *__restrict__ part, int nblocks, doubl
         int nbx = (int)fx, nby = (int)fy;
         double bsx = fmax(cut, sx / (double)nbx), bsy = fmax(cut, sy / (double)nby);
         g->x0 = xmin; g->y0 = ymin; g->inv_bx = 1.0 / bsx; g->inv_by = 1.0 / bsy;
-        g->L = 0.0; g->halfL = 0.0; g->nbx = nbx; g->nby = nby; g->periodic = 0; g->pad = 0;
+        g->Lx = g->Ly = 0.0; g->halfLx = g->halfLy = 0.0; g->nbx = nbx; g->nby = nby; g->perx = 0; g->pery = 0;
     }
 }
 
@@ -137,7 +137,7 @@ struct ForceArgs {
     uint64_t seed;
     int64_t step;
     const double *noise;           // nullptr -> Philox; else row of this step, indexed by gid
-    double L;                      // periodic wrap (0 = none)
+    double Lx, Ly;                 // periodic wrap of the updated positions per direction (0 = none)
 };
 
 struct NbrRec { double gx, gy, w; };
@@ -236,11 +236,8 @@ __global__ void __launch_bounds__(128) k_force(ForceArgs a) {
         const double2 pos = a.xy[s];
         double xn = pos.x + (a.mu * Fx + a.v0 * cs_) * a.dt;
         double yn = pos.y + (a.mu * Fy + a.v0 * sn) * a.dt;
-        if (a.L > 0.0) {
-            xn -= a.L * floor(xn / a.L); yn -= a.L * floor(yn / a.L);
-            if (xn >= a.L) xn = 0.0;
-            if (yn >= a.L) yn = 0.0;
-        }
+        if (a.Lx > 0.0) { xn -= a.Lx * floor(xn / a.Lx); if (xn >= a.Lx) xn = 0.0; }
+        if (a.Ly > 0.0) { yn -= a.Ly * floor(yn / a.Ly); if (yn >= a.Ly) yn = 0.0; }
         double xi_ = 0.0;
         if (a.noise_amp != 0.0) {
             const int64_t id = a.gid[s];
@@ -375,6 +372,18 @@ __global__ void k_pack_rows(const int *__restrict__ idx, int m, double x_shift, 
     const int s = idx[i];
     double *q = rows + 5 * (size_t)i;
     q[0] = xy[s].x + x_shift; q[1] = xy[s].y; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
+}
+// rows (m,11): x, y, theta, A0, gid, fx, fy, area, perimeter, arclen, coord_num of the selected slots
+__global__ void k_pack_results(const int *__restrict__ idx, int m, const double2 *__restrict__ xy, const double *__restrict__ th,
+                               const double *__restrict__ a0, const int64_t *__restrict__ gid, const double *__restrict__ fx,
+                               const double *__restrict__ fy, const double *__restrict__ area, const double *__restrict__ perim,
+                               const double *__restrict__ arcl, const int *__restrict__ coord, double *__restrict__ rows) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int s = idx[i];
+    double *q = rows + 11 * (size_t)i;
+    q[0] = xy[s].x; q[1] = xy[s].y; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
+    q[5] = fx[s]; q[6] = fy[s]; q[7] = area[s]; q[8] = perim[s]; q[9] = arcl[s]; q[10] = (double)coord[s];
 }
 // flag = owned && x in [lo,hi)   (invert != 0: the complement, i.e. the cells to keep)
 __global__ void k_flag_slab(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, double lo, double hi, int invert,

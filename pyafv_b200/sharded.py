@@ -1,0 +1,350 @@
+"""Slab sharding of one periodic box across the GPUs of a node: one process (rank) per GPU.
+
+Replaces the reference's multiprocessing domain decomposition (``pyafv/parallel_voronoi.py:125-338`` decompose,
+``:351-418`` per-domain build, ``:590-633`` merge): instead of re-decomposing all points on a parent process and
+pickling them to workers every step, every rank keeps its x-slab resident on its GPU and exchanges, per step,
+
+1. a halo: the owned cells within ``halo_width`` (default 4.01 l, the reference's default at
+   ``parallel_voronoi.py:485`` -- forces need a 4 l dependence range, ``_connectutil.py:19``) of each slab face go
+   to the neighbouring rank, shifted by +-L across the periodic box face;
+2. migrants: cells that crossed a face during the update change owner.
+
+Both are point-to-point messages with the two ring neighbours (NCCL send/recv under ``torch.distributed``); there
+is no collective on the data path.  The exchange logic is written against two small interfaces so that it can be
+exercised without GPUs: a *cell store* (``GpuCellStore`` over the C-ABI handle; the tests use a numpy one) and a
+*communicator* (``TorchDistComm``; ``LoopbackComm`` runs all ranks inside one process).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+ROW = 5        # x, y, theta, A0, gid
+RES_ROW = 11   # + fx, fy, area, perimeter, arclen, coord_num
+
+
+# ------------------------------------------------------------------------------------------------------
+# cell stores
+# ------------------------------------------------------------------------------------------------------
+class GpuCellStore:
+    """The cells of one rank, resident on one GPU behind an ``AfvHandle``."""
+
+    def __init__(self, handle, device: torch.device):
+        self.h = handle
+        self.device = device
+        self._buf = {}
+
+    def _rows(self, key: str, n: int, width: int = ROW) -> torch.Tensor:
+        t = self._buf.get(key)
+        if t is None or t.shape[0] < n or t.shape[1] != width:
+            t = torch.empty((max(int(n * 1.25) + 64, 256), width), dtype=torch.float64, device=self.device)
+            self._buf[key] = t
+        return t
+
+    @property
+    def n_owned(self) -> int:
+        return int(self.h.lib.afv_num_owned(self.h._h))
+
+    @property
+    def n(self) -> int:
+        return self.h.n
+
+    def set_cells(self, rows: torch.Tensor, n_owned: int) -> None:
+        rows = rows.contiguous()
+        self.h.call("afv_set_cells_device", rows.data_ptr(), int(n_owned), int(rows.shape[0] - n_owned))
+
+    def extract(self, x_lo: float, x_hi: float, x_shift: float, keep: bool, key: str) -> torch.Tensor:
+        cap = max(self.n_owned, 1)
+        buf = self._rows(key, cap)
+        cnt = C.c_int64()
+        self.h.call("afv_extract_slab", float(x_lo), float(x_hi), float(x_shift), 1 if keep else 0, buf.data_ptr(),
+                    int(buf.shape[0]), C.byref(cnt))
+        return buf[: cnt.value]
+
+    def append(self, rows: torch.Tensor, is_halo: bool) -> None:
+        if rows.shape[0]:
+            rows = rows.contiguous()
+            self.h.call("afv_append_cells", rows.data_ptr(), int(rows.shape[0]), 1 if is_halo else 0)
+
+    def drop_halo(self) -> None:
+        self.h.call("afv_drop_halo")
+
+    def results(self) -> torch.Tensor:
+        buf = self._rows("res", max(self.n_owned, 1), RES_ROW)
+        cnt = C.c_int64()
+        self.h.call("afv_pack_owned", buf.data_ptr(), int(buf.shape[0]), C.byref(cnt))
+        return buf[: cnt.value]
+
+
+# ------------------------------------------------------------------------------------------------------
+# communicators: exchange one buffer with each ring neighbour
+# ------------------------------------------------------------------------------------------------------
+class TorchDistComm:
+    """Ring neighbours over ``torch.distributed`` (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, rank: int, world: int):
+        self.rank, self.world = rank, world
+        self.left, self.right = (rank - 1) % world, (rank + 1) % world
+
+    def exchange(self, to_left: torch.Tensor, to_right: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """Send ``to_left`` / ``to_right`` (k,W) to the two neighbours; return what they sent us."""
+        import torch.distributed as dist
+        dev, width = to_left.device, to_left.shape[1]
+        cnt_out = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=dev)
+        cnt_in = torch.zeros(2, dtype=torch.int64, device=dev)   # [from_left, from_right]
+        # a message to the left arrives as the right neighbour's "from right" ... on 2 ranks both neighbours
+        # coincide, so the two directions are separated by tags / order within one batch
+        ops = [dist.P2POp(dist.isend, cnt_out[0:1], self.left, tag=1), dist.P2POp(dist.isend, cnt_out[1:2], self.right, tag=2),
+               dist.P2POp(dist.irecv, cnt_in[1:2], self.right, tag=1), dist.P2POp(dist.irecv, cnt_in[0:1], self.left, tag=2)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        n_l, n_r = (int(v) for v in cnt_in.tolist())
+        from_left = torch.empty((n_l, width), dtype=to_left.dtype, device=dev)
+        from_right = torch.empty((n_r, width), dtype=to_left.dtype, device=dev)
+        ops = []
+        if to_left.shape[0]:
+            ops.append(dist.P2POp(dist.isend, to_left.contiguous(), self.left, tag=3))
+        if to_right.shape[0]:
+            ops.append(dist.P2POp(dist.isend, to_right.contiguous(), self.right, tag=4))
+        if n_r:
+            ops.append(dist.P2POp(dist.irecv, from_right, self.right, tag=3))
+        if n_l:
+            ops.append(dist.P2POp(dist.irecv, from_left, self.left, tag=4))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return from_left, from_right
+
+
+def loopback_exchange(outboxes: list[tuple[torch.Tensor, torch.Tensor]]) -> list[tuple[torch.Tensor, torch.Tensor]]:
+    """All ranks in one process: ``outboxes[r] = (to_left, to_right)`` -> ``[(from_left, from_right)]``."""
+    world = len(outboxes)
+    return [(outboxes[(r - 1) % world][1].clone(), outboxes[(r + 1) % world][0].clone()) for r in range(world)]
+
+
+# ------------------------------------------------------------------------------------------------------
+# the exchange logic (device agnostic)
+# ------------------------------------------------------------------------------------------------------
+class SlabGeometry:
+    """x-slab ``rank`` of ``world`` equal slabs of the periodic square ``[0, L)^2``."""
+
+    def __init__(self, L: float, rank: int, world: int, r: float, halo_width: float | None = None):
+        self.L, self.rank, self.world, self.r = float(L), int(rank), int(world), float(r)
+        self.W = self.L / world
+        self.lo, self.hi = rank * self.W, (rank + 1) * self.W
+        self.halo = float(4.01 * r if halo_width is None else halo_width)
+        if world > 1 and self.W < self.halo:
+            raise ValueError(f"slab width {self.W:g} is smaller than the halo width {self.halo:g}: use fewer GPUs")
+        # across the periodic box face the neighbour's coordinates are shifted by one period
+        self.shift_to_left = self.L if rank == 0 else 0.0            # what WE add when sending to the left rank
+        self.shift_to_right = -self.L if rank == world - 1 else 0.0
+        pad = 0.5 * r
+        self.grid_x0, self.grid_x1 = self.lo - self.halo - pad, self.hi + self.halo + pad
+
+
+def pack_halo(store, geo: SlabGeometry):
+    """Owned cells within the halo width of the two faces, in the receiver's coordinates."""
+    to_left = store.extract(geo.lo, geo.lo + geo.halo, geo.shift_to_left, True, "halo_l")
+    to_right = store.extract(geo.hi - geo.halo, geo.hi, geo.shift_to_right, True, "halo_r")
+    return to_left, to_right
+
+
+def unpack_halo(store, from_left, from_right) -> None:
+    store.append(from_left, True)
+    store.append(from_right, True)
+
+
+def pack_migrants(store, geo: SlabGeometry):
+    """Owned cells that left the slab (removed here), in the receiver's coordinates."""
+    to_left = store.extract(-math.inf, geo.lo, geo.shift_to_left, False, "mig_l")
+    to_right = store.extract(geo.hi, math.inf, geo.shift_to_right, False, "mig_r")
+    return to_left, to_right
+
+
+def unpack_migrants(store, from_left, from_right) -> None:
+    store.append(from_left, False)
+    store.append(from_right, False)
+
+
+# ------------------------------------------------------------------------------------------------------
+# one rank of the sharded simulator
+# ------------------------------------------------------------------------------------------------------
+class SlabShardedSimulator:
+    """One rank's share of a periodic AFV system sharded into x-slabs (one rank per GPU).
+
+    Args:
+        pts: (n,2) positions of the cells this rank owns initially (all inside its slab).
+        theta: (n,) self-propulsion angles, or None.
+        phys: :class:`~pyafv_b200.PhysicalParams`.
+        L: side of the periodic box.
+        rank, world: position in the ring of slabs.
+        gids: (n,) global cell ids (default: ``rank * 2**40 + arange(n)``; any ids unique across ranks work --
+            the Philox noise stream is keyed by them, so results do not depend on the number of GPUs).
+        A0: per-cell preferred areas (default ``phys.A0``).
+        comm: communicator (default :class:`TorchDistComm`); ``None`` with ``world == 1``.
+    """
+
+    def __init__(self, pts, theta, phys, L: float, *, rank: int = 0, world: int = 1, device: int = 0, stream: int | None = None,
+                 gids=None, A0=None, halo_width: float | None = None, comm=None):
+        from . import _lib
+        from .finite_voronoi import _as_params
+        self.phys, self.L, self.rank, self.world = phys, float(L), rank, world
+        self.geo = SlabGeometry(L, rank, world, phys.r, halo_width)
+        self.device = torch.device("cuda", device)
+        self._h = _lib.Handle(_as_params(phys), self.L, device=device, stream=stream)
+        if world > 1:
+            self._h.call("afv_set_slab", self.geo.grid_x0, self.geo.grid_x1)
+        self.store = GpuCellStore(self._h, self.device)
+        self.comm = comm if comm is not None else (TorchDistComm(rank, world) if world > 1 else None)
+        pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+        n = pts.shape[0]
+        rows = np.empty((n, ROW))
+        rows[:, 0:2] = pts
+        rows[:, 2] = 0.0 if theta is None else np.asarray(theta, dtype=np.float64)
+        rows[:, 3] = phys.A0 if A0 is None else np.asarray(A0, dtype=np.float64)
+        rows[:, 4] = (rank * float(2**40) + np.arange(n)) if gids is None else np.asarray(gids, dtype=np.float64)
+        if n and world > 1 and ((pts[:, 0] < self.geo.lo).any() or (pts[:, 0] >= self.geo.hi).any()):
+            raise ValueError("initial cells must lie inside the rank's slab")
+        self.store.set_cells(torch.from_numpy(rows).to(self.device), n)
+        self._step_index = 0
+
+    @property
+    def n_owned(self) -> int:
+        return self.store.n_owned
+
+    def close(self) -> None:
+        self._h.close()
+
+    # -- phases, exposed separately so that a loopback driver can interleave the ranks of one process --------
+    def halo_out(self):
+        return pack_halo(self.store, self.geo)
+
+    def halo_in(self, from_left, from_right) -> None:
+        unpack_halo(self.store, from_left, from_right)
+
+    def compute_step(self, dt, mu, v0, Dr, seed) -> None:
+        self._h.call("afv_step", float(dt), float(mu), float(v0), float(Dr), C.c_uint64(int(seed)), C.c_int64(self._step_index), 1, None)
+        self._step_index += 1
+        self.store.drop_halo()
+
+    def compute_build(self) -> torch.Tensor:
+        from . import _lib
+        self._h.call("afv_build", _lib.BUILD_FORCES)
+        res = self.store.results().clone()
+        self.store.drop_halo()
+        return res
+
+    def migrants_out(self):
+        return pack_migrants(self.store, self.geo)
+
+    def migrants_in(self, from_left, from_right) -> None:
+        unpack_migrants(self.store, from_left, from_right)
+
+    # -- the per-rank drivers (one process per GPU) ---------------------------------------------------------
+    def step(self, dt: float, mu: float = 1.0, v0: float = 0.0, Dr: float = 0.0, *, seed: int = 0, n_steps: int = 1) -> None:
+        """``n_steps`` of halo exchange -> fused build+force+update -> migration."""
+        for _ in range(n_steps):
+            if self.world > 1:
+                self.halo_in(*self.comm.exchange(*self.halo_out()))
+            self.compute_step(dt, mu, v0, Dr, seed)
+            if self.world > 1:
+                self.migrants_in(*self.comm.exchange(*self.migrants_out()))
+
+    def build(self) -> dict[str, np.ndarray]:
+        """Forces and geometry of the owned cells (keys of the reference's merged dict, ``parallel_voronoi.py:596-611``,
+        plus ``gids`` and ``pts``)."""
+        if self.world > 1:
+            self.halo_in(*self.comm.exchange(*self.halo_out()))
+        return results_dict(self.compute_build())
+
+    def e2e_measure(self, k: int, step: dict) -> dict:
+        """End-to-end leg of bench.py for N > 1: every step uploads this rank's cells from pinned host memory,
+        exchanges halos, builds, and reads the forces back."""
+        import time
+        import torch.distributed as dist
+        res = self.build()
+        order = np.argsort(res["gids"])
+        n = len(order)
+        host = torch.empty((n, ROW), dtype=torch.float64).pin_memory()
+        host[:, 0:2] = torch.from_numpy(res["pts"][order])
+        host[:, 2] = 0.0
+        host[:, 3] = self.phys.A0
+        host[:, 4] = torch.from_numpy(res["gids"][order])
+        dev = torch.empty((n, ROW), dtype=torch.float64, device=self.device)
+        out = torch.empty((n, RES_ROW), dtype=torch.float64).pin_memory()
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            dev.copy_(host, non_blocking=True)
+            self.store.set_cells(dev, n)
+            self.halo_in(*self.comm.exchange(*self.halo_out()))
+            r = self.compute_build()
+            out[: r.shape[0]].copy_(r, non_blocking=True)
+            torch.cuda.synchronize()
+        dist.barrier()
+        dt = time.perf_counter() - t0
+        tot = torch.tensor([float(n)], device=self.device, dtype=torch.float64)
+        dist.all_reduce(tot)
+        tmax = torch.tensor([dt], device=self.device, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        return {"value": float(tot.item()) * k / float(tmax.item()), "unit": "cell-steps/s", "h2d_bytes_per_step": 8 * ROW * n,
+                "d2h_bytes_per_step": 8 * RES_ROW * n, "steps": k,
+                "api": "SlabShardedSimulator: H2D cells (pinned) + halo exchange + build + D2H results, per rank"}
+
+
+def results_dict(res: torch.Tensor) -> dict[str, np.ndarray]:
+    a = res.cpu().numpy()
+    return dict(pts=a[:, 0:2].copy(), theta=a[:, 2].copy(), gids=a[:, 4].astype(np.int64), forces=a[:, 5:7].copy(),
+                areas=a[:, 7].copy(), perimeters=a[:, 8].copy(), arclens=a[:, 9].copy(), coord_nums=a[:, 10].astype(np.int64))
+
+
+# ------------------------------------------------------------------------------------------------------
+# all ranks inside one process (tests, and machines with fewer GPUs than slabs)
+# ------------------------------------------------------------------------------------------------------
+class LoopbackShardedSimulator:
+    """``world`` slabs driven from one process on one device; same phases as the distributed run."""
+
+    def __init__(self, pts, theta, phys, L: float, world: int, *, device: int = 0, A0=None, halo_width=None):
+        pts = np.asarray(pts, dtype=np.float64)
+        N = pts.shape[0]
+        theta = np.zeros(N) if theta is None else np.asarray(theta, dtype=np.float64)
+        A0 = np.full(N, phys.A0) if A0 is None else np.broadcast_to(np.asarray(A0, dtype=np.float64), (N,))
+        W = L / world
+        owner = np.minimum((pts[:, 0] // W).astype(int), world - 1)
+        self.ranks = []
+        for rk in range(world):
+            m = owner == rk
+            self.ranks.append(SlabShardedSimulator(pts[m], theta[m], phys, L, rank=rk, world=world, device=device,
+                                                   gids=np.flatnonzero(m), A0=A0[m], halo_width=halo_width, comm=False))
+        self.world, self.N = world, N
+
+    def step(self, dt, mu=1.0, v0=0.0, Dr=0.0, *, seed=0, n_steps=1) -> None:
+        for _ in range(n_steps):
+            if self.world > 1:
+                for sim, inbox in zip(self.ranks, loopback_exchange([s.halo_out() for s in self.ranks])):
+                    sim.halo_in(*inbox)
+            for sim in self.ranks:
+                sim.compute_step(dt, mu, v0, Dr, seed)
+            if self.world > 1:
+                for sim, inbox in zip(self.ranks, loopback_exchange([s.migrants_out() for s in self.ranks])):
+                    sim.migrants_in(*inbox)
+
+    def build(self) -> dict[str, np.ndarray]:
+        """Merged dict in global cell order (the reference's ``_merge_results``)."""
+        if self.world > 1:
+            for sim, inbox in zip(self.ranks, loopback_exchange([s.halo_out() for s in self.ranks])):
+                sim.halo_in(*inbox)
+        parts = [results_dict(sim.compute_build()) for sim in self.ranks]
+        out = {}
+        gids = np.concatenate([p["gids"] for p in parts])
+        order = np.argsort(gids)
+        for k in parts[0]:
+            out[k] = np.concatenate([p[k] for p in parts])[order]
+        return out
+
+    def close(self) -> None:
+        for s in self.ranks:
+            s.close()

@@ -1,0 +1,72 @@
+"""CPU: host-side mirror of the reference interface (parameters, validation, error messages)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import pyafv_b200 as afv
+
+
+def test_physical_params_defaults_and_validation():
+    p = afv.PhysicalParams()
+    assert (p.r, p.A0, p.P0, p.KA, p.KP, p.Lambda, p.seed) == (1.0, np.pi, 4.8, 1.0, 1.0, 0.2, None)
+    assert p.delta == pytest.approx(0.45)
+    assert afv.PhysicalParams(r=2).delta == pytest.approx(0.9)
+    assert afv.PhysicalParams(delta=0.0).delta == 0.0
+    q = p.replace(A0=5.0, delta=0.3)
+    assert q.A0 == 5.0 and q.delta == 0.3 and p.A0 == np.pi
+    with pytest.raises(Exception):
+        p.r = 3.0                      # frozen
+    with pytest.raises(TypeError):
+        afv.PhysicalParams(r=True)
+    with pytest.raises(TypeError):
+        afv.PhysicalParams(KA="1")
+    with pytest.raises(ValueError):
+        afv.PhysicalParams(P0=float("nan"))
+    with pytest.raises(ValueError):
+        afv.PhysicalParams(seed=-1)
+    with pytest.raises(TypeError):
+        afv.PhysicalParams(seed=1.5)
+    with pytest.raises(TypeError):
+        afv.PhysicalParams(delta="x")
+    assert isinstance(afv.PhysicalParams(r=np.float32(1.5)).r, float)
+
+
+def test_doublet_closed_forms():
+    """tests/test_core.py:38-57 of the reference."""
+    phys = afv.PhysicalParams()
+    l, d = phys.get_steady_state()
+    assert abs(l - 0.87) < 1e-3 and abs(d - 0.75) < 1e-3
+    params = phys.with_optimal_radius()
+    assert abs(params.r - l) < 1e-6 and params.delta == pytest.approx(0.45 * params.r)
+    assert abs(afv.target_delta(params, 4.0) - 0.16868) < 1e-4
+    p2 = phys.with_optimal_radius(digits=1, delta=0.5)
+    assert p2.r == round(l, 1) and p2.delta == 0.5
+    with pytest.raises(ValueError):
+        afv.target_delta(params, 1e9)
+
+
+def test_constructor_argument_errors_precede_device_use():
+    with pytest.raises(ValueError, match=r"pts must have shape \(N,2\)"):
+        afv.FiniteVoronoiSimulator(np.zeros((3, 3)), afv.PhysicalParams())
+    with pytest.raises(TypeError, match="phys must be an instance of PhysicalParams"):
+        afv.FiniteVoronoiSimulator(np.zeros((3, 2)), dict(r=1.0))
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        afv.FiniteVoronoiSimulator(np.zeros((3, 2)), afv.PhysicalParams(), backend="python")
+
+
+def test_backend_module_names():
+    from pyafv_b200 import backend
+    assert hasattr(backend, "backend_impl") and hasattr(backend, "_BACKEND_NAME") and hasattr(backend, "_IMPORT_ERROR")
+    assert backend._BACKEND_NAME == "cuda" and backend._IMPORT_ERROR is None
+
+
+def test_slab_geometry_shifts():
+    from pyafv_b200.sharded import SlabGeometry
+    g0, g3 = SlabGeometry(100.0, 0, 4, 1.0), SlabGeometry(100.0, 3, 4, 1.0)
+    assert (g0.lo, g0.hi, g3.lo, g3.hi) == (0.0, 25.0, 75.0, 100.0)
+    assert g0.shift_to_left == 100.0 and g0.shift_to_right == 0.0
+    assert g3.shift_to_left == 0.0 and g3.shift_to_right == -100.0
+    assert g0.halo == pytest.approx(4.01)
+    with pytest.raises(ValueError):
+        SlabGeometry(10.0, 0, 4, 1.0)
