@@ -151,6 +151,15 @@ int afv_drop_halo(AfvHandle h);
 /* append rows (device memory) as owned (is_halo = 0) or halo (is_halo = 1) cells */
 int afv_append_cells(AfvHandle h, const double *rows_dev, int64_t n, int is_halo);
 int64_t afv_num_owned(AfvHandle h);
+/* Pair exchange with the two ring neighbours, no host round trip on the sending side.  A message is a
+ * (cap_rows+1, 5) float64 device buffer: row 0 = [count, 0, 0, 0, 0], rows 1..count = cells.
+ * afv_pack_pair packs the owned cells with x in [lo0,hi0) / [lo1,hi1) (x shifted by shift0 / shift1).
+ * afv_finish_pair, called after the messages were exchanged, reads all four counts with one synchronisation,
+ * removes the cells packed before when remove_packed != 0 (migration), and appends the received cells as halo
+ * (is_halo != 0) or owned cells.  AFV_ERR_CAPACITY when a count exceeds cap_rows. */
+int afv_pack_pair(AfvHandle h, double lo0, double hi0, double shift0, double lo1, double hi1, double shift1,
+                  double *msg0_dev, double *msg1_dev, int64_t cap_rows);
+int afv_finish_pair(AfvHandle h, const double *in0_dev, const double *in1_dev, int64_t cap_rows, int is_halo, int remove_packed);
 /* after afv_build: rows (count,11) of the OWNED cells in device memory:
  * x, y, theta, A0, gid, fx, fy, area, perimeter, arclen, coord_num */
 int afv_pack_owned(AfvHandle h, double *rows_dev_out, int64_t capacity, int64_t *count);

@@ -69,6 +69,11 @@ struct AfvContext {
     int64_t n_conn = -1, n_ring = -1;
     bool built = false;
     int cmax_hint = 32;
+    // pair exchange state (afv_pack_pair -> afv_finish_pair)
+    int *pair_cnt = nullptr;       // device [2]
+    double *pair_host = nullptr;   // pinned [4]
+    double *pair_dev = nullptr;    // device [4]
+    double pair_rng[4] = {0, 0, 0, 0};
     // profiling
     bool profiling = false;
     struct Span { int stage; cudaEvent_t a, b; };
@@ -423,6 +428,10 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
         cudaMalloc((void **)&h->ovf_ro, (size_t)OVF_MAX * RS_SLOW * sizeof(RingOwn)) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
+    if (cudaMalloc((void **)&h->pair_cnt, 2 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 4 * sizeof(double)) != cudaSuccess ||
+        cudaHostAlloc((void **)&h->pair_host, 4 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+        g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
+    }
     cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream);
     cudaFuncSetAttribute(k_geometry_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(int));
     *out = h;
@@ -436,6 +445,7 @@ void afv_destroy(AfvHandle h) {
     free_all(h);
     cudaFree(h->d_grid); cudaFree(h->flags); cudaFree(h->bbox_part);
     cudaFree(h->ovf_cells); cudaFree(h->ovf_len); cudaFree(h->ovf_rs); cudaFree(h->ovf_ro);
+    cudaFree(h->pair_cnt); cudaFree(h->pair_dev); cudaFreeHost(h->pair_host);
     for (DevBuf *b : {&h->scratch_a, &h->scratch_b, &h->noise_buf, &h->conn_buf, &h->ring_types, &h->ring_xy, &h->ring_off}) cudaFree(b->p);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);

@@ -373,6 +373,33 @@ __global__ void k_pack_rows(const int *__restrict__ idx, int m, double x_shift, 
     double *q = rows + 5 * (size_t)i;
     q[0] = xy[s].x + x_shift; q[1] = xy[s].y; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
 }
+// message = (cap+1, 5) rows: row 0 is the header [count, 0, 0, 0, 0], rows 1..count the packed cells.  The count is
+// read on the device (no host round trip between the selection and the packing); rows beyond cap are dropped and
+// the header still carries the true count, so both ends detect the overflow.
+__global__ void k_pack_message(const int *__restrict__ idx, const int *__restrict__ count, int cap, double x_shift,
+                               const double2 *__restrict__ xy, const double *__restrict__ th, const double *__restrict__ a0,
+                               const int64_t *__restrict__ gid, double *__restrict__ msg) {
+    const int m = *count;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { msg[0] = (double)m; msg[1] = msg[2] = msg[3] = msg[4] = 0.0; }
+    if (i >= m || i >= cap) return;
+    const int s = idx[i];
+    double *q = msg + 5 * (size_t)(i + 1);
+    q[0] = xy[s].x + x_shift; q[1] = xy[s].y; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
+}
+// keep = !(owned && x in either range)
+__global__ void k_flag_keep2(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, double lo0, double hi0,
+                             double lo1, double hi1, int *__restrict__ flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double xv = xy[i].x;
+    const bool sel = owned[i] && ((xv >= lo0 && xv < hi0) || (xv >= lo1 && xv < hi1));
+    flag[i] = sel ? 0 : 1;
+}
+__global__ void k_gather_counts(const int *__restrict__ c0, const int *__restrict__ c1, const double *__restrict__ in0,
+                                const double *__restrict__ in1, double *__restrict__ out) {
+    out[0] = (double)*c0; out[1] = (double)*c1; out[2] = in0 ? in0[0] : 0.0; out[3] = in1 ? in1[0] : 0.0;
+}
 // rows (m,11): x, y, theta, A0, gid, fx, fy, area, perimeter, arclen, coord_num of the selected slots
 __global__ void k_pack_results(const int *__restrict__ idx, int m, const double2 *__restrict__ xy, const double *__restrict__ th,
                                const double *__restrict__ a0, const int64_t *__restrict__ gid, const double *__restrict__ fx,

@@ -72,6 +72,23 @@ class GpuCellStore:
     def drop_halo(self) -> None:
         self.h.call("afv_drop_halo")
 
+    def pack_pair(self, r0, r1, cap: int, key: str):
+        """Two messages (cap+1, ROW) with a device-written header row; no host synchronisation."""
+        m0, m1 = self._msg(key + "0", cap), self._msg(key + "1", cap)
+        self.h.call("afv_pack_pair", float(r0[0]), float(r0[1]), float(r0[2]), float(r1[0]), float(r1[1]), float(r1[2]),
+                    m0.data_ptr(), m1.data_ptr(), int(cap))
+        return m0, m1
+
+    def finish_pair(self, in0: torch.Tensor, in1: torch.Tensor, cap: int, is_halo: bool, remove_packed: bool) -> None:
+        self.h.call("afv_finish_pair", in0.data_ptr(), in1.data_ptr(), int(cap), 1 if is_halo else 0, 1 if remove_packed else 0)
+
+    def _msg(self, key: str, cap: int) -> torch.Tensor:
+        t = self._buf.get(key)
+        if t is None or t.shape[0] != cap + 1:
+            t = torch.zeros((cap + 1, ROW), dtype=torch.float64, device=self.device)
+            self._buf[key] = t
+        return t
+
     def results(self) -> torch.Tensor:
         buf = self._rows("res", max(self.n_owned, 1), RES_ROW)
         cnt = C.c_int64()
@@ -119,10 +136,26 @@ class TorchDistComm:
         return from_left, from_right
 
 
+    def exchange_fixed(self, to_left: torch.Tensor, to_right: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """Fixed-capacity messages (header row carries the count): one batch of two sends and two receives."""
+        import torch.distributed as dist
+        key = (tuple(to_left.shape), to_left.device)
+        if getattr(self, "_rx_key", None) != key:
+            self._rx = (torch.zeros_like(to_left), torch.zeros_like(to_right))
+            self._rx_key = key
+        from_left, from_right = self._rx
+        # order matters when both neighbours are the same rank (world == 2): NCCL matches per peer in issue order
+        ops = [dist.P2POp(dist.isend, to_left, self.left), dist.P2POp(dist.isend, to_right, self.right),
+               dist.P2POp(dist.irecv, from_right, self.right), dist.P2POp(dist.irecv, from_left, self.left)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        return from_left, from_right
+
+
 def loopback_exchange(outboxes: list[tuple[torch.Tensor, torch.Tensor]]) -> list[tuple[torch.Tensor, torch.Tensor]]:
     """All ranks in one process: ``outboxes[r] = (to_left, to_right)`` -> ``[(from_left, from_right)]``."""
     world = len(outboxes)
-    return [(outboxes[(r - 1) % world][1].clone(), outboxes[(r + 1) % world][0].clone()) for r in range(world)]
+    return [(outboxes[(r - 1) % world][1], outboxes[(r + 1) % world][0]) for r in range(world)]
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -145,28 +178,24 @@ class SlabGeometry:
         self.grid_x0, self.grid_x1 = self.lo - self.halo - pad, self.hi + self.halo + pad
 
 
-def pack_halo(store, geo: SlabGeometry):
-    """Owned cells within the halo width of the two faces, in the receiver's coordinates."""
-    to_left = store.extract(geo.lo, geo.lo + geo.halo, geo.shift_to_left, True, "halo_l")
-    to_right = store.extract(geo.hi - geo.halo, geo.hi, geo.shift_to_right, True, "halo_r")
-    return to_left, to_right
+def halo_ranges(geo: SlabGeometry):
+    """(lo, hi, shift) of the owned cells each neighbour needs as halo: [left message, right message].  The ranges
+    are open towards the outside so that a cell that drifted past the face before migrating is still sent."""
+    return (-math.inf, geo.lo + geo.halo, geo.shift_to_left), (geo.hi - geo.halo, math.inf, geo.shift_to_right)
 
 
-def unpack_halo(store, from_left, from_right) -> None:
-    store.append(from_left, True)
-    store.append(from_right, True)
+def migrant_ranges(geo: SlabGeometry):
+    """(lo, hi, shift) of the owned cells that left the slab."""
+    return (-math.inf, geo.lo, geo.shift_to_left), (geo.hi, math.inf, geo.shift_to_right)
 
 
-def pack_migrants(store, geo: SlabGeometry):
-    """Owned cells that left the slab (removed here), in the receiver's coordinates."""
-    to_left = store.extract(-math.inf, geo.lo, geo.shift_to_left, False, "mig_l")
-    to_right = store.extract(geo.hi, math.inf, geo.shift_to_right, False, "mig_r")
-    return to_left, to_right
+def halo_capacity(n_owned: int, geo: SlabGeometry) -> int:
+    """Rows per halo message: 2.5 x the uniform-density expectation (checked on arrival)."""
+    return max(1024, int(2.5 * n_owned * geo.halo / geo.W) + 256)
 
 
-def unpack_migrants(store, from_left, from_right) -> None:
-    store.append(from_left, False)
-    store.append(from_right, False)
+def migrant_capacity(n_owned: int, geo: SlabGeometry) -> int:
+    return max(1024, int(0.25 * n_owned * geo.halo / geo.W) + 256)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -210,6 +239,7 @@ class SlabShardedSimulator:
             raise ValueError("initial cells must lie inside the rank's slab")
         self.store.set_cells(torch.from_numpy(rows).to(self.device), n)
         self._step_index = 0
+        self._cap = None
 
     @property
     def n_owned(self) -> int:
@@ -219,11 +249,22 @@ class SlabShardedSimulator:
         self._h.close()
 
     # -- phases, exposed separately so that a loopback driver can interleave the ranks of one process --------
+    def _caps(self):
+        if self._cap is None:   # fixed at first use: every rank must use the same message size
+            n = self.n_owned
+            if self.world > 1 and self.comm:
+                import torch.distributed as dist
+                t = torch.tensor([n], device=self.device, dtype=torch.int64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                n = int(t.item())
+            self._cap = (halo_capacity(n, self.geo), migrant_capacity(n, self.geo))
+        return self._cap
+
     def halo_out(self):
-        return pack_halo(self.store, self.geo)
+        return self.store.pack_pair(*halo_ranges(self.geo), self._caps()[0], "halo")
 
     def halo_in(self, from_left, from_right) -> None:
-        unpack_halo(self.store, from_left, from_right)
+        self.store.finish_pair(from_left, from_right, self._caps()[0], True, False)
 
     def compute_step(self, dt, mu, v0, Dr, seed) -> None:
         self._h.call("afv_step", float(dt), float(mu), float(v0), float(Dr), C.c_uint64(int(seed)), C.c_int64(self._step_index), 1, None)
@@ -238,26 +279,26 @@ class SlabShardedSimulator:
         return res
 
     def migrants_out(self):
-        return pack_migrants(self.store, self.geo)
+        return self.store.pack_pair(*migrant_ranges(self.geo), self._caps()[1], "mig")
 
     def migrants_in(self, from_left, from_right) -> None:
-        unpack_migrants(self.store, from_left, from_right)
+        self.store.finish_pair(from_left, from_right, self._caps()[1], False, True)
 
     # -- the per-rank drivers (one process per GPU) ---------------------------------------------------------
     def step(self, dt: float, mu: float = 1.0, v0: float = 0.0, Dr: float = 0.0, *, seed: int = 0, n_steps: int = 1) -> None:
         """``n_steps`` of halo exchange -> fused build+force+update -> migration."""
         for _ in range(n_steps):
             if self.world > 1:
-                self.halo_in(*self.comm.exchange(*self.halo_out()))
+                self.halo_in(*self.comm.exchange_fixed(*self.halo_out()))
             self.compute_step(dt, mu, v0, Dr, seed)
             if self.world > 1:
-                self.migrants_in(*self.comm.exchange(*self.migrants_out()))
+                self.migrants_in(*self.comm.exchange_fixed(*self.migrants_out()))
 
     def build(self) -> dict[str, np.ndarray]:
         """Forces and geometry of the owned cells (keys of the reference's merged dict, ``parallel_voronoi.py:596-611``,
         plus ``gids`` and ``pts``)."""
         if self.world > 1:
-            self.halo_in(*self.comm.exchange(*self.halo_out()))
+            self.halo_in(*self.comm.exchange_fixed(*self.halo_out()))
         return results_dict(self.compute_build())
 
     def e2e_measure(self, k: int, step: dict) -> dict:
@@ -280,7 +321,7 @@ class SlabShardedSimulator:
         for _ in range(k):
             dev.copy_(host, non_blocking=True)
             self.store.set_cells(dev, n)
-            self.halo_in(*self.comm.exchange(*self.halo_out()))
+            self.halo_in(*self.comm.exchange_fixed(*self.halo_out()))
             r = self.compute_build()
             out[: r.shape[0]].copy_(r, non_blocking=True)
             torch.cuda.synchronize()

@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pyafv_b200.sharded import ROW, SlabGeometry, TorchDistComm, pack_halo, pack_migrants, unpack_halo, unpack_migrants
+from pyafv_b200.sharded import ROW, SlabGeometry, TorchDistComm, halo_capacity, halo_ranges, migrant_ranges
 
 
 class NumpyCellStore:
@@ -40,6 +40,31 @@ class NumpyCellStore:
     def drop_halo(self):
         self.rows, self.owned = self.rows[self.owned], self.owned[self.owned]
 
+    # the message format of afv_pack_pair / afv_finish_pair: (cap+1, ROW), row 0 = [count, 0, 0, 0, 0]
+    def pack_pair(self, r0, r1, cap, key):
+        self._packed = (r0, r1)
+        out = []
+        for lo, hi, shift in (r0, r1):
+            sel = self.owned & (self.rows[:, 0] >= lo) & (self.rows[:, 0] < hi)
+            msg = np.zeros((cap + 1, ROW))
+            k = int(sel.sum())
+            assert k <= cap
+            msg[0, 0] = k
+            msg[1:k + 1] = self.rows[sel]
+            msg[1:k + 1, 0] += shift
+            out.append(torch.from_numpy(msg))
+        return out
+
+    def finish_pair(self, in0, in1, cap, is_halo, remove_packed):
+        if remove_packed:
+            (lo0, hi0, _), (lo1, hi1, _) = self._packed
+            x = self.rows[:, 0]
+            sel = self.owned & (((x >= lo0) & (x < hi0)) | ((x >= lo1) & (x < hi1)))
+            self.rows, self.owned = self.rows[~sel], self.owned[~sel]
+        for m in (in0, in1):
+            k = int(m[0, 0])
+            self.append(m[1:k + 1].clone(), is_halo)
+
 
 def _worker(rank, world, port, L, N, halo, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -55,7 +80,8 @@ def _worker(rank, world, port, L, N, halo, q):
         store, comm = NumpyCellStore(rows), TorchDistComm(rank, world)
         for it in range(4):
             # ---- halo ----
-            unpack_halo(store, *comm.exchange(*pack_halo(store, geo)))
+            cap = halo_capacity(N, geo)
+            store.finish_pair(*comm.exchange_fixed(*store.pack_pair(*halo_ranges(geo), cap, 'halo')), cap, True, False)
             got = {int(g): x for g, x in zip(store.rows[~store.owned, 4], store.rows[~store.owned, 0])}
             # brute force on the global state: minimum-image x distance to the slab
             xs = pts[:, 0]
@@ -81,7 +107,7 @@ def _worker(rank, world, port, L, N, halo, q):
             ids = store.rows[:, 4].astype(int)
             store.rows[:, 0] += drift[ids]                          # local, un-wrapped like the GPU step leaves it
             # ---- migration ----
-            unpack_migrants(store, *comm.exchange(*pack_migrants(store, geo)))
+            store.finish_pair(*comm.exchange_fixed(*store.pack_pair(*migrant_ranges(geo), cap, 'mig')), cap, False, True)
             ids = store.rows[:, 4].astype(int)
             assert store.owned.all()
             assert np.allclose(store.rows[:, 0], pts[ids, 0], atol=1e-9)
