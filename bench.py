@@ -118,11 +118,15 @@ def run_ours(args) -> dict:
         raise SystemExit("bench.py: no CUDA device; the AFV path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner out of the one-JSON-line stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cells = args.cells_per_gpu
     pts, theta, L = make_slab(rank, world, cells, seed=42)
     phys = afv.PhysicalParams()
-    stream = torch.cuda.current_stream()
+    # a dedicated stream: the handle launches on it, the CUDA events are recorded on it, NCCL orders against it
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
 
     def barrier():
         if world > 1:

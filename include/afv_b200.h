@@ -66,7 +66,8 @@ enum AfvField {
 
 /* ---- life cycle ---------------------------------------------------------------------------------- */
 /* device: CUDA ordinal.  box_L: 0 for open boundaries, else the side of the periodic square [0,L)^2
- * (must be >= 4 r).  stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create one. */
+ * (must be >= 4 r).  stream: a cudaStream_t to run on (e.g. torch's current stream; pass cudaStreamLegacy, not 0, for
+ * the default stream), or NULL to let the handle create its own non-blocking stream. */
 int afv_create(int device, const AfvParams *params, double box_L, void *stream, AfvHandle *out);
 void afv_destroy(AfvHandle h);
 /* last error text of the handle (or of the failed afv_create when h is NULL); never NULL */

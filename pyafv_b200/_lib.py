@@ -107,7 +107,10 @@ class Handle:
     def __init__(self, params: AfvParams, box_L: float = 0.0, device: int = 0, stream: int | None = None):
         self.lib = load()
         self._h = C.c_void_p()
-        rc = self.lib.afv_create(int(device), C.byref(params), float(box_L), C.c_void_p(stream or 0), C.byref(self._h))
+        # stream: None -> the library creates its own stream; 0 (torch's default stream) -> cudaStreamLegacy (0x1),
+        # because a NULL pointer means "create one" in the C-ABI; anything else is a raw cudaStream_t
+        sptr = 0 if stream is None else (1 if int(stream) == 0 else int(stream))
+        rc = self.lib.afv_create(int(device), C.byref(params), float(box_L), C.c_void_p(sptr), C.byref(self._h))
         if rc != AFV_OK:
             raise AfvError(rc, self.lib.afv_last_error(None).decode())
 

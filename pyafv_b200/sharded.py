@@ -223,6 +223,8 @@ class SlabShardedSimulator:
         self.phys, self.L, self.rank, self.world = phys, float(L), rank, world
         self.geo = SlabGeometry(L, rank, world, phys.r, halo_width)
         self.device = torch.device("cuda", device)
+        if stream is None:   # run on torch's current stream: the message buffers and NCCL ops are ordered against it
+            stream = torch.cuda.current_stream(self.device).cuda_stream
         self._h = _lib.Handle(_as_params(phys), self.L, device=device, stream=stream)
         if world > 1:
             self._h.call("afv_set_slab", self.geo.grid_x0, self.geo.grid_x1)
@@ -356,10 +358,11 @@ class LoopbackShardedSimulator:
         W = L / world
         owner = np.minimum((pts[:, 0] // W).astype(int), world - 1)
         self.ranks = []
+        stream = torch.cuda.current_stream(torch.device("cuda", device)).cuda_stream   # one stream for every rank
         for rk in range(world):
             m = owner == rk
             self.ranks.append(SlabShardedSimulator(pts[m], theta[m], phys, L, rank=rk, world=world, device=device,
-                                                   gids=np.flatnonzero(m), A0=A0[m], halo_width=halo_width, comm=False))
+                                                   gids=np.flatnonzero(m), A0=A0[m], halo_width=halo_width, comm=False, stream=stream))
         self.world, self.N = world, N
 
     def step(self, dt, mu=1.0, v0=0.0, Dr=0.0, *, seed=0, n_steps=1) -> None:
