@@ -243,7 +243,7 @@ def run_ours(args) -> dict:
                           f"{n_local * 1024 / 1e6:.0f} MB + state) exceeds the 126 MB L2; no explicit flush"},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_fp64": roofline_fp64,
                "cpu_baseline": cpu}
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -346,10 +346,22 @@ def run_reference(args) -> None:
                                       f"an N={n} periodic dense sample of the workload"},
            "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
+
+
+def _emit(line: str) -> None:
+    """The one JSON line goes to the real stdout; everything else any library prints was diverted to stderr."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)       # NCCL / torch banners must not pollute the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

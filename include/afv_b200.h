@@ -161,6 +161,14 @@ int64_t afv_num_owned(AfvHandle h);
 int afv_pack_pair(AfvHandle h, double lo0, double hi0, double shift0, double lo1, double hi1, double shift1,
                   double *msg0_dev, double *msg1_dev, int64_t cap_rows);
 int afv_finish_pair(AfvHandle h, const double *in0_dev, const double *in1_dev, int64_t cap_rows, int is_halo, int remove_packed);
+/* One exchange per step: ownership transfers and halo cells in the same message.  Message = (cap_rows+1, 5): header
+ * [n_transfer, n_halo, 0, 0, 0], then the transfer rows, then the halo rows.  afv_pack_exchange selects, for the slab
+ * [lo, hi): left message = owned cells with x < lo (transfers) and lo <= x < lo+halo (halo), x + shift_left; right
+ * message = x >= hi (transfers) and hi-halo <= x < hi (halo), x + shift_right.  afv_finish_exchange (one
+ * synchronisation) keeps this rank's transferred cells as halo copies and appends the received rows. */
+int afv_pack_exchange(AfvHandle h, double lo, double hi, double halo, double shift_left, double shift_right,
+                      double *msg_left_dev, double *msg_right_dev, int64_t cap_rows);
+int afv_finish_exchange(AfvHandle h, const double *in_left_dev, const double *in_right_dev, int64_t cap_rows);
 /* after afv_build: rows (count,11) of the OWNED cells in device memory:
  * x, y, theta, A0, gid, fx, fy, area, perimeter, arclen, coord_num */
 int afv_pack_owned(AfvHandle h, double *rows_dev_out, int64_t capacity, int64_t *count);

@@ -74,6 +74,8 @@ struct AfvContext {
     double *pair_host = nullptr;   // pinned [4]
     double *pair_dev = nullptr;    // device [4]
     double pair_rng[4] = {0, 0, 0, 0};
+    double xch_lo = 0, xch_hi = 0;  // slab interval of the last afv_pack_exchange
+    int *xch_idx[4] = {nullptr, nullptr, nullptr, nullptr};   // selection lists (views of scratch arrays)
     // profiling
     bool profiling = false;
     struct Span { int stage; cudaEvent_t a, b; };
@@ -428,8 +430,8 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
         cudaMalloc((void **)&h->ovf_ro, (size_t)OVF_MAX * RS_SLOW * sizeof(RingOwn)) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
-    if (cudaMalloc((void **)&h->pair_cnt, 2 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 4 * sizeof(double)) != cudaSuccess ||
-        cudaHostAlloc((void **)&h->pair_host, 4 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaMalloc((void **)&h->pair_cnt, 4 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 8 * sizeof(double)) != cudaSuccess ||
+        cudaHostAlloc((void **)&h->pair_host, 8 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
     cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream);

@@ -387,6 +387,32 @@ __global__ void k_pack_message(const int *__restrict__ idx, const int *__restric
     double *q = msg + 5 * (size_t)(i + 1);
     q[0] = xy[s].x + x_shift; q[1] = xy[s].y; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
 }
+// exchange message = (cap+1, 5) rows: header [nA, nB, 0, 0, 0], then nA "transfer" rows (cells that change owner)
+// followed by nB halo rows.  Counts are read on the device.
+__global__ void k_pack_exchange(const int *__restrict__ idxA, const int *__restrict__ idxB, const int *__restrict__ cntA,
+                                const int *__restrict__ cntB, int cap, double x_shift, const double2 *__restrict__ xy,
+                                const double *__restrict__ th, const double *__restrict__ a0, const int64_t *__restrict__ gid,
+                                double *__restrict__ msg) {
+    const int nA = *cntA, nB = *cntB;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { msg[0] = (double)nA; msg[1] = (double)nB; msg[2] = msg[3] = msg[4] = 0.0; }
+    if (i >= nA + nB || i >= cap) return;
+    const int s = (i < nA) ? idxA[i] : idxB[i - nA];
+    double *q = msg + 5 * (size_t)(i + 1);
+    q[0] = xy[s].x + x_shift; q[1] = xy[s].y; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
+}
+// owned cells outside [lo, hi) stay as halo copies of cells that now belong to a neighbour
+__global__ void k_disown_outside(const double2 *__restrict__ xy, unsigned char *__restrict__ owned, int n, double lo, double hi) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double xv = xy[i].x;
+    if (owned[i] && (xv < lo || xv >= hi)) owned[i] = 0;
+}
+__global__ void k_gather_counts8(const int *__restrict__ c, const double *__restrict__ in0, const double *__restrict__ in1,
+                                 double *__restrict__ out) {
+    out[0] = (double)c[0]; out[1] = (double)c[1]; out[2] = (double)c[2]; out[3] = (double)c[3];
+    out[4] = in0 ? in0[0] : 0.0; out[5] = in0 ? in0[1] : 0.0; out[6] = in1 ? in1[0] : 0.0; out[7] = in1 ? in1[1] : 0.0;
+}
 // keep = !(owned && x in either range)
 __global__ void k_flag_keep2(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, double lo0, double hi0,
                              double lo1, double hi1, int *__restrict__ flag) {

@@ -7,9 +7,11 @@ pickling them to workers every step, every rank keeps its x-slab resident on its
 1. a halo: the owned cells within ``halo_width`` (default 4.01 l, the reference's default at
    ``parallel_voronoi.py:485`` -- forces need a 4 l dependence range, ``_connectutil.py:19``) of each slab face go
    to the neighbouring rank, shifted by +-L across the periodic box face;
-2. migrants: cells that crossed a face during the update change owner.
+2. ownership transfers: cells that crossed a face during the previous update change owner (the old owner keeps a
+   halo copy for this step -- the cell is still within the halo of the face it crossed).
 
-Both are point-to-point messages with the two ring neighbours (NCCL send/recv under ``torch.distributed``); there
+Both travel in ONE fixed-capacity message per neighbour and step (header row = the two counts, written on the device),
+point-to-point with the two ring neighbours (NCCL send/recv under ``torch.distributed``); there
 is no collective on the data path.  The exchange logic is written against two small interfaces so that it can be
 exercised without GPUs: a *cell store* (``GpuCellStore`` over the C-ABI handle; the tests use a numpy one) and a
 *communicator* (``TorchDistComm``; ``LoopbackComm`` runs all ranks inside one process).
@@ -81,6 +83,16 @@ class GpuCellStore:
 
     def finish_pair(self, in0: torch.Tensor, in1: torch.Tensor, cap: int, is_halo: bool, remove_packed: bool) -> None:
         self.h.call("afv_finish_pair", in0.data_ptr(), in1.data_ptr(), int(cap), 1 if is_halo else 0, 1 if remove_packed else 0)
+
+    def pack_exchange(self, geo, cap: int):
+        """(to_left, to_right) messages carrying ownership transfers + halo rows; no host synchronisation."""
+        ml, mr = self._msg("xl", cap), self._msg("xr", cap)
+        self.h.call("afv_pack_exchange", float(geo.lo), float(geo.hi), float(geo.halo), float(geo.shift_to_left),
+                    float(geo.shift_to_right), ml.data_ptr(), mr.data_ptr(), int(cap))
+        return ml, mr
+
+    def finish_exchange(self, from_left: torch.Tensor, from_right: torch.Tensor, cap: int) -> None:
+        self.h.call("afv_finish_exchange", from_left.data_ptr(), from_right.data_ptr(), int(cap))
 
     def _msg(self, key: str, cap: int) -> torch.Tensor:
         t = self._buf.get(key)
@@ -190,7 +202,7 @@ def migrant_ranges(geo: SlabGeometry):
 
 
 def halo_capacity(n_owned: int, geo: SlabGeometry) -> int:
-    """Rows per halo message: 2.5 x the uniform-density expectation (checked on arrival)."""
+    """Rows per message: 2.5 x the uniform-density expectation of the halo (+ transfers); checked on arrival."""
     return max(1024, int(2.5 * n_owned * geo.halo / geo.W) + 256)
 
 
@@ -262,11 +274,12 @@ class SlabShardedSimulator:
             self._cap = (halo_capacity(n, self.geo), migrant_capacity(n, self.geo))
         return self._cap
 
-    def halo_out(self):
-        return self.store.pack_pair(*halo_ranges(self.geo), self._caps()[0], "halo")
+    def exchange_out(self):
+        """Messages for the (left, right) neighbour: cells that left the slab (ownership transfer) + halo cells."""
+        return self.store.pack_exchange(self.geo, self._caps()[0])
 
-    def halo_in(self, from_left, from_right) -> None:
-        self.store.finish_pair(from_left, from_right, self._caps()[0], True, False)
+    def exchange_in(self, from_left, from_right) -> None:
+        self.store.finish_exchange(from_left, from_right, self._caps()[0])
 
     def compute_step(self, dt, mu, v0, Dr, seed) -> None:
         self._h.call("afv_step", float(dt), float(mu), float(v0), float(Dr), C.c_uint64(int(seed)), C.c_int64(self._step_index), 1, None)
@@ -280,27 +293,20 @@ class SlabShardedSimulator:
         self.store.drop_halo()
         return res
 
-    def migrants_out(self):
-        return self.store.pack_pair(*migrant_ranges(self.geo), self._caps()[1], "mig")
-
-    def migrants_in(self, from_left, from_right) -> None:
-        self.store.finish_pair(from_left, from_right, self._caps()[1], False, True)
-
     # -- the per-rank drivers (one process per GPU) ---------------------------------------------------------
     def step(self, dt: float, mu: float = 1.0, v0: float = 0.0, Dr: float = 0.0, *, seed: int = 0, n_steps: int = 1) -> None:
-        """``n_steps`` of halo exchange -> fused build+force+update -> migration."""
+        """``n_steps`` of: one exchange with the ring neighbours (cells that left the slab during the previous update
+        change owner, halo cells are refreshed), then the fused build + force + update."""
         for _ in range(n_steps):
             if self.world > 1:
-                self.halo_in(*self.comm.exchange_fixed(*self.halo_out()))
+                self.exchange_in(*self.comm.exchange_fixed(*self.exchange_out()))
             self.compute_step(dt, mu, v0, Dr, seed)
-            if self.world > 1:
-                self.migrants_in(*self.comm.exchange_fixed(*self.migrants_out()))
 
     def build(self) -> dict[str, np.ndarray]:
         """Forces and geometry of the owned cells (keys of the reference's merged dict, ``parallel_voronoi.py:596-611``,
         plus ``gids`` and ``pts``)."""
         if self.world > 1:
-            self.halo_in(*self.comm.exchange_fixed(*self.halo_out()))
+            self.exchange_in(*self.comm.exchange_fixed(*self.exchange_out()))
         return results_dict(self.compute_build())
 
     def e2e_measure(self, k: int, step: dict) -> dict:
@@ -323,7 +329,7 @@ class SlabShardedSimulator:
         for _ in range(k):
             dev.copy_(host, non_blocking=True)
             self.store.set_cells(dev, n)
-            self.halo_in(*self.comm.exchange_fixed(*self.halo_out()))
+            self.exchange_in(*self.comm.exchange_fixed(*self.exchange_out()))
             r = self.compute_build()
             out[: r.shape[0]].copy_(r, non_blocking=True)
             torch.cuda.synchronize()
@@ -368,19 +374,16 @@ class LoopbackShardedSimulator:
     def step(self, dt, mu=1.0, v0=0.0, Dr=0.0, *, seed=0, n_steps=1) -> None:
         for _ in range(n_steps):
             if self.world > 1:
-                for sim, inbox in zip(self.ranks, loopback_exchange([s.halo_out() for s in self.ranks])):
-                    sim.halo_in(*inbox)
+                for sim, inbox in zip(self.ranks, loopback_exchange([s.exchange_out() for s in self.ranks])):
+                    sim.exchange_in(*inbox)
             for sim in self.ranks:
                 sim.compute_step(dt, mu, v0, Dr, seed)
-            if self.world > 1:
-                for sim, inbox in zip(self.ranks, loopback_exchange([s.migrants_out() for s in self.ranks])):
-                    sim.migrants_in(*inbox)
 
     def build(self) -> dict[str, np.ndarray]:
         """Merged dict in global cell order (the reference's ``_merge_results``)."""
         if self.world > 1:
-            for sim, inbox in zip(self.ranks, loopback_exchange([s.halo_out() for s in self.ranks])):
-                sim.halo_in(*inbox)
+            for sim, inbox in zip(self.ranks, loopback_exchange([s.exchange_out() for s in self.ranks])):
+                sim.exchange_in(*inbox)
         parts = [results_dict(sim.compute_build()) for sim in self.ranks]
         out = {}
         gids = np.concatenate([p["gids"] for p in parts])
