@@ -7,7 +7,7 @@ from pathlib import Path
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libafv_b200.so"
+LIB_PATH = Path(__import__("os").environ.get("AFV_B200_LIB", PKG / "libafv_b200.so"))   # override for A/B builds
 
 AFV_OK, AFV_ERR_CUDA, AFV_ERR_ARG, AFV_ERR_CAPACITY, AFV_ERR_STATE = 0, -1, -2, -3, -4
 BUILD_FORCES, BUILD_CONNECT, BUILD_RINGS = 1, 2, 4

@@ -56,6 +56,7 @@ struct AfvContext {
     double *fx = nullptr, *fy = nullptr, *area = nullptr, *perim = nullptr, *arcl = nullptr;
     int *coord = nullptr;
     unsigned char *ring_len = nullptr;
+    int *ring_key = nullptr;
     RingShared *rs = nullptr;
     RingOwn *ro = nullptr;
     int *flags = nullptr;         // device: [0] slow-path cells, [1] lookup misses, [2] max ring length, [3] hard overflows
@@ -132,6 +133,7 @@ void free_all(AfvHandle h) {
     cudaFree(h->cub_tmp); cudaFree(h->fx); cudaFree(h->fy); cudaFree(h->area); cudaFree(h->perim); cudaFree(h->arcl);
     cudaFree(h->coord); cudaFree(h->ring_len); cudaFree(h->rs); cudaFree(h->ro); cudaFree(h->cnt); cudaFree(h->off);
     cudaFree(h->ovf_index); h->ovf_index = nullptr;
+    cudaFree(h->ring_key); h->ring_key = nullptr;
     h->keys = h->keys_sorted = nullptr; h->iota = h->perm = h->bin_start = nullptr; h->cub_tmp = nullptr;
     h->fx = h->fy = h->area = h->perim = h->arcl = nullptr; h->coord = nullptr; h->ring_len = nullptr;
     h->rs = nullptr; h->ro = nullptr; h->cnt = h->off = nullptr;
@@ -187,6 +189,7 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     if ((rc = dev_alloc(h, &h->arcl, cap))) return rc;
     if ((rc = dev_alloc(h, &h->coord, cap))) return rc;
     if ((rc = dev_alloc(h, &h->ring_len, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->ring_key, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->rs, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->ro, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->ovf_index, cap))) return rc;
@@ -307,7 +310,7 @@ int stage_geometry(AfvHandle h) {
     const int c = h->cur;
     GeomArgs a;
     a.xy = h->xy[c]; a.a0 = h->a0[c]; a.keys = h->keys_sorted; a.bin_start = h->bin_start; a.grid = h->d_grid;
-    a.n = n; a.ph = phys_dev(h->prm); a.rs = h->rs; a.ro = h->ro; a.ring_len = h->ring_len;
+    a.n = n; a.ph = phys_dev(h->prm); a.rs = h->rs; a.ro = h->ro; a.ring_len = h->ring_len; a.ring_key = h->ring_key;
     a.area = h->area; a.perim = h->perim; a.arcl = h->arcl; a.coord = h->coord; a.flags = h->flags;
     a.ovf_cells = h->ovf_cells; a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
     // candidate-list capacity per cell (shared memory scales with it): for a periodic box the mean number of cells
@@ -333,7 +336,7 @@ int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, doub
     const int n = (int)h->n;
     const int c = h->cur;
     ForceArgs a;
-    a.rs = h->rs; a.ro = h->ro; a.ring_len = h->ring_len; a.owned = h->owned[c]; a.gid = h->gid[c]; a.n = n;
+    a.rs = h->rs; a.ro = h->ro; a.ring_len = h->ring_len; a.ring_key = h->ring_key; a.owned = h->owned[c]; a.gid = h->gid[c]; a.n = n;
     a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
     a.ph = phys_dev(h->prm); a.fx = h->fx; a.fy = h->fy; a.flags = h->flags;
     a.do_step = do_step ? 1 : 0; a.xy = h->xy[c]; a.theta = h->th[c];

@@ -26,6 +26,7 @@ struct GeomArgs {
     RingShared *rs;
     RingOwn *ro;
     unsigned char *ring_len;
+    int *ring_key;             // [n * RS] neighbour slot of every ring entry (ARC for arcs; stale beyond ring_len): what k_force scans
     double *area, *perim, *arcl;
     int *coord;
     int *flags;                // [0] cells sent to the slow path, [1] lookup misses, [2] max ring length, [3] hard overflows
@@ -187,6 +188,10 @@ __device__ __forceinline__ void finish_cell(const GeomArgs &a, const int s, cons
             ro[e] = q;
         }
     }
+    if (ringed && E <= RS) {   // the compact key row that k_force scans (entries beyond ring_len are stale)
+        int *key = a.ring_key + (size_t)s * RS;
+        for (int e = 0; e < EE; ++e) key[e] = nbr[e];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -240,7 +245,10 @@ __device__ __forceinline__ void virtual_nbr(int v, double B4, double &x, double 
     y = (v == 0) ? -B4 : ((v == 2) ? B4 : 0.0);
 }
 
-__global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const int cmax) {
+#ifndef HULL_MIN_BLOCKS
+#define HULL_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_geometry_hull(GeomArgs a, const int cmax) {
     extern __shared__ int s_idx[];               // [cmax][HULL_TPB]: sorted slots of the in-range neighbours of each lane's cell
     const int tid = threadIdx.x;
     const int s = blockIdx.x * HULL_TPB + tid;
@@ -359,6 +367,7 @@ __global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const in
     const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
     RingShared *const rs = a.rs + (size_t)s * RS;
     RingOwn *const ro = a.ro + (size_t)s * RS;
+    int *const key = a.ring_key + (size_t)s * RS;
     const int mm = (wrap && ok) ? m : 0;
     const int mloop = __reduce_max_sync(FULL_MASK, mm);
     auto hull_at = [&](int k) { return (int)(((k < 8) ? (hull_lo >> (8 * k)) : (hull_hi >> (8 * (k - 8)))) & 0xffull); };
@@ -389,6 +398,7 @@ __global__ void __launch_bounds__(HULL_TPB) k_geometry_hull(GeomArgs a, const in
             o.gy = xp * x + yp * y;              // v1 . v2
         }
         rs[E - 1] = o;
+        key[E - 1] = nbr_p;
     };
     auto emit = [&](double x, double y, double ex, double ey, int nb) {
         if (E >= RS) { ok = false; return; }

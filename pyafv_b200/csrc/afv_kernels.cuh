@@ -120,6 +120,7 @@ struct ForceArgs {
     const RingShared *rs;
     const RingOwn *ro;
     const unsigned char *ring_len;
+    const int *ring_key;
     const int *ovf_index, *ovf_len;
     const RingShared *ovf_rs;
     const RingOwn *ovf_ro;
@@ -145,17 +146,32 @@ struct NbrRec { double gx, gy, w; };
 __device__ __forceinline__ bool lookup_edge(const ForceArgs &a, int j, int self, NbrRec &at_start, NbrRec &at_end) {
     // edge (j -> self) in j's ring runs from slot t to slot t+1; seen from `self` the same edge runs the other
     // way, so j's slot t is the END of self's edge and j's slot t+1 its START.
-    int Ej = a.ring_len[j];
+    // The 16 keys of j's ring are one 64-byte row: four independent 16-byte loads, then register compares.
+    const int4 *kj = reinterpret_cast<const int4 *>(a.ring_key + (size_t)j * RS);
+    int Ej = a.ring_len[j];                       // independent of the key loads: all five are in flight together
+    const int4 k0 = kj[0], k1 = kj[1], k2 = kj[2], k3 = kj[3];
     const RingShared *rj = a.rs + (size_t)j * RS;
-    if (Ej == RING_IN_POOL) { const int pi = a.ovf_index[j]; Ej = a.ovf_len[pi]; rj = a.ovf_rs + (size_t)pi * RS_SLOW; }
-    for (int t = 0; t < Ej; ++t) {
-        const int2 kt = *reinterpret_cast<const int2 *>(&rj[t]);
-        if (kt.x == self && kt.y == 1) {
-            const int t1 = (t + 1 == Ej) ? 0 : t + 1;
-            at_end.gx = rj[t].gx; at_end.gy = rj[t].gy; at_end.w = rj[t].w;
-            at_start.gx = rj[t1].gx; at_start.gy = rj[t1].gy; at_start.w = rj[t1].w;
-            return true;
+    int t = -1;
+    if (Ej != RING_IN_POOL) {
+        const int kk[RS] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
+        unsigned match = 0u;
+#pragma unroll
+        for (int e = 0; e < RS; ++e) match |= (kk[e] == self ? 1u : 0u) << e;
+        match &= (1u << Ej) - 1u;                 // slots beyond the ring hold stale keys
+        t = __ffs(match) - 1;
+    } else {   // pooled ring: generic scan
+        const int pi = a.ovf_index[j];
+        Ej = a.ovf_len[pi]; rj = a.ovf_rs + (size_t)pi * RS_SLOW;
+        for (int q = 0; q < Ej; ++q) {
+            const int2 kt = *reinterpret_cast<const int2 *>(&rj[q]);
+            if (kt.x == self && kt.y == 1) { t = q; break; }
         }
+    }
+    if (t >= 0) {
+        const int t1 = (t + 1 == Ej) ? 0 : t + 1;
+        at_end.gx = rj[t].gx; at_end.gy = rj[t].gy; at_end.w = rj[t].w;
+        at_start.gx = rj[t1].gx; at_start.gy = rj[t1].gy; at_start.w = rj[t1].w;
+        return true;
     }
     at_start.gx = at_start.gy = at_start.w = 0.0;
     at_end.gx = at_end.gy = at_end.w = 0.0;

@@ -1,0 +1,21 @@
+#!/usr/bin/env python
+"""Stage times of the step loop (ms per step) for the library selected by AFV_B200_LIB: N dens steps"""
+import sys, os
+from pathlib import Path
+import numpy as np
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import pyafv_b200 as afv
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+dens = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+L = float(np.sqrt(N / dens))
+rng = np.random.default_rng(42)
+sim = afv.FiniteVoronoiSimulator(rng.random((N, 2)) * L, afv.PhysicalParams(), periodic=L)
+sim.step(0.01, 1.0, 2.4, 0.3, theta=2 * np.pi * rng.random(N) - np.pi, seed=7, n_steps=5)
+h = sim._h
+h.call("afv_set_profiling", 1)
+ms, l = np.zeros(4), np.zeros(4, dtype=np.int64)
+h.call("afv_get_stage_times", ms.ctypes.data, l.ctypes.data, 1)
+sim.step(0.01, 1.0, 2.4, 0.3, seed=7, n_steps=steps)
+h.call("afv_get_stage_times", ms.ctypes.data, l.ctypes.data, 1)
+print(os.environ.get("AFV_B200_LIB", "default"), "N", N, "dens", dens, "sort %.3f geom %.3f force %.3f total %.3f ms/step" % (ms[0]/steps, ms[1]/steps, ms[2]/steps, ms[:3].sum()/steps), sim.diagnostics())
