@@ -204,3 +204,19 @@ def test_many_neighbour_cell_uses_overflow_pool(n_ring, radius):
     diag = sim.diagnostics()
     assert diag["slow_path_cells"] >= 1 and diag["lookup_misses"] == 0 and diag["max_ring_len"] == n_expect
     sim.close()
+
+
+def test_parallel_simulator_equals_serial():
+    """tests/test_parallel.py:112-176 of the reference: the parallel API returns the serial results."""
+    import pyafv_b200 as afv
+    g = load_golden("rand_dense")
+    phys = phys_from(g)
+    with afv.ParallelFiniteVoronoiSimulator(g["pts"], phys, grid_shape=(3, 2), n_workers=4, decomposition_method="binned") as sim:
+        d = sim.build(connect=True, plot_mode=True)
+    for k in ("forces", "areas", "perimeters", "arclens"):
+        _close(d[k], g[k], k)
+    assert np.array_equal(d["coord_nums"], g["coord_nums"]) and np.array_equal(d["connections"], g["connections"])
+    assert d["plot_mode"] is True and len(d["diag_plot"]) == 1 and len(d["owned_global_ids"][0]) == len(g["pts"])
+    assert set(d["diag_plot"][0]) == {"vertices", "edges_type", "regions"}
+    d2 = afv.ParallelFiniteVoronoiSimulator(g["pts"], phys).build()
+    assert d2["connections"].shape == (0, 2) and d2["plot_mode"] is False

@@ -70,3 +70,34 @@ def test_slab_geometry_shifts():
     assert g0.halo == pytest.approx(4.01)
     with pytest.raises(ValueError):
         SlabGeometry(10.0, 0, 4, 1.0)
+
+
+def test_tile_pbc_matches_reference_semantics():
+    """Originals first, x images, then y images of the augmented set (pyafv/_connectutil.py:12-96)."""
+    rng = np.random.default_rng(0)
+    L, r = 12.0, 1.0
+    pts = rng.random((200, 2)) * L
+    pos, idx = afv.tile_pbc(pts, L, r)
+    assert np.array_equal(pos[:200], pts) and np.array_equal(idx[:200], np.arange(200))
+    d = pos - pts[idx]
+    assert np.all(np.isin(np.round(d / L), (-1, 0, 1))) and np.allclose(d, np.round(d / L) * L)
+    # every image within 4.01 r outside the box is present exactly once
+    want = 0
+    for sx in (-1, 0, 1):
+        for sy in (-1, 0, 1):
+            if sx or sy:
+                q = pts + np.array([sx, sy]) * L
+                want += int(((q[:, 0] >= -4.01 * r) & (q[:, 0] <= L + 4.01 * r) & (q[:, 1] >= -4.01 * r) & (q[:, 1] <= L + 4.01 * r)).sum())
+    assert len(pos) - 200 == want
+
+
+def test_parallel_simulator_argument_validation():
+    P = afv.ParallelFiniteVoronoiSimulator
+    with pytest.raises(ValueError, match=r"pts must have shape \(N,2\)"):
+        P(np.zeros((3, 3)), afv.PhysicalParams())
+    with pytest.raises(TypeError):
+        P(np.zeros((3, 2)), None)
+    with pytest.raises(ValueError, match="grid_shape"):
+        P(np.zeros((3, 2)), afv.PhysicalParams(), grid_shape=(0, 2))
+    with pytest.raises(ValueError, match="decomposition_method"):
+        P(np.zeros((3, 2)), afv.PhysicalParams(), decomposition_method="fancy")
