@@ -205,7 +205,9 @@ def run_ours(args) -> dict:
         except Exception:
             pass
 
-    # ---- end to end through the public API: pinned host buffers, H2D + build + D2H every step ----
+    # ---- end to end through the public API with HOST buffers (pinned): every step uploads the positions, advances one
+    #      fused step on the device and reads the new positions back; the literal reference loop (build + host Euler
+    #      update, examples/active_FV.py:43-54) is timed as well ----
     e2e = None
     if world == 1:
         pin = _lib.PinnedArray((cells, 2))
@@ -213,20 +215,30 @@ def run_ours(args) -> dict:
         k_e2e = max(3, min(args.steps, 10))
         for _ in range(2):
             sim.update_positions(pin.array)
-            d = sim.build(connect=False, rings=False)
+            sim.step(STEP["dt"], STEP["mu"], STEP["v0"], STEP["Dr"], seed=7, n_steps=1)
+            sim.positions_into(pin.array)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(k_e2e):
-            sim.update_positions(pin.array)                 # H2D 16 B / cell from pinned memory
-            d = sim.build(connect=False, rings=False)       # D2H forces, areas, perimeters, arclens, coord_nums
-            pin.array += STEP["mu"] * d["forces"] * STEP["dt"]
-            if L > 0:
-                np.mod(pin.array, L, out=pin.array)
+            sim.update_positions(pin.array)                                              # H2D 16 B / cell
+            sim.step(STEP["dt"], STEP["mu"], STEP["v0"], STEP["Dr"], seed=7, n_steps=1)  # bin, sort, geometry, force, update
+            sim.positions_into(pin.array)                                                # D2H 16 B / cell
         torch.cuda.synchronize()
         dt_e2e = time.perf_counter() - t0
         e2e = {"value": cells * k_e2e / dt_e2e, "unit": "cell-steps/s", "h2d_bytes_per_step": 16 * cells,
-               "d2h_bytes_per_step": 56 * cells, "steps": k_e2e,
-               "api": "FiniteVoronoiSimulator.update_positions + build(connect=False, rings=False) + host Euler update"}
+               "d2h_bytes_per_step": 16 * cells, "steps": k_e2e,
+               "api": "FiniteVoronoiSimulator.update_positions(pinned) + step(n_steps=1) + positions_into(pinned)"}
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            sim.update_positions(pin.array)                 # H2D 16 B / cell
+            d = sim.build(connect=False, rings=False)       # D2H forces, areas, perimeters, arclens, coord_nums (56 B / cell)
+            pin.array += STEP["mu"] * d["forces"] * STEP["dt"]
+            np.mod(pin.array, L, out=pin.array)
+        torch.cuda.synchronize()
+        dt_ref_loop = time.perf_counter() - t0
+        e2e["reference_style_loop"] = {"value": cells * k_e2e / dt_ref_loop, "unit": "cell-steps/s", "h2d_bytes_per_step": 16 * cells,
+                                       "d2h_bytes_per_step": 56 * cells,
+                                       "api": "update_positions + build(connect=False, rings=False) + numpy Euler update on the host"}
         pin.free()
     else:
         e2e = sim.e2e_measure(max(3, min(args.steps, 10)), STEP)

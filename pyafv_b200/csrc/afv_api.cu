@@ -56,7 +56,8 @@ struct AfvContext {
     double *fx = nullptr, *fy = nullptr, *area = nullptr, *perim = nullptr, *arcl = nullptr;
     int *coord = nullptr;
     unsigned char *ring_len = nullptr;
-    int *ring_key = nullptr;
+    int *ring_key = nullptr, *hull_slot = nullptr;
+    unsigned char *hull_len = nullptr;
     RingShared *rs = nullptr;
     RingOwn *ro = nullptr;
     int *flags = nullptr;         // device: [0] slow-path cells, [1] lookup misses, [2] max ring length, [3] hard overflows
@@ -134,6 +135,7 @@ void free_all(AfvHandle h) {
     cudaFree(h->coord); cudaFree(h->ring_len); cudaFree(h->rs); cudaFree(h->ro); cudaFree(h->cnt); cudaFree(h->off);
     cudaFree(h->ovf_index); h->ovf_index = nullptr;
     cudaFree(h->ring_key); h->ring_key = nullptr;
+    cudaFree(h->hull_slot); h->hull_slot = nullptr; cudaFree(h->hull_len); h->hull_len = nullptr;
     h->keys = h->keys_sorted = nullptr; h->iota = h->perm = h->bin_start = nullptr; h->cub_tmp = nullptr;
     h->fx = h->fy = h->area = h->perim = h->arcl = nullptr; h->coord = nullptr; h->ring_len = nullptr;
     h->rs = nullptr; h->ro = nullptr; h->cnt = h->off = nullptr;
@@ -190,6 +192,8 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     if ((rc = dev_alloc(h, &h->coord, cap))) return rc;
     if ((rc = dev_alloc(h, &h->ring_len, cap))) return rc;
     if ((rc = dev_alloc(h, &h->ring_key, (size_t)cap * RS))) return rc;
+    if ((rc = dev_alloc(h, &h->hull_slot, (size_t)cap * KHULL_STRIDE))) return rc;
+    if ((rc = dev_alloc(h, &h->hull_len, cap))) return rc;
     if ((rc = dev_alloc(h, &h->rs, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->ro, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->ovf_index, cap))) return rc;
@@ -310,7 +314,7 @@ int stage_geometry(AfvHandle h) {
     const int c = h->cur;
     GeomArgs a;
     a.xy = h->xy[c]; a.a0 = h->a0[c]; a.keys = h->keys_sorted; a.bin_start = h->bin_start; a.grid = h->d_grid;
-    a.n = n; a.ph = phys_dev(h->prm); a.rs = h->rs; a.ro = h->ro; a.ring_len = h->ring_len; a.ring_key = h->ring_key;
+    a.n = n; a.ph = phys_dev(h->prm); a.rs = h->rs; a.ro = h->ro; a.ring_len = h->ring_len; a.ring_key = h->ring_key; a.hull_slot = h->hull_slot; a.hull_len = h->hull_len;
     a.area = h->area; a.perim = h->perim; a.arcl = h->arcl; a.coord = h->coord; a.flags = h->flags;
     a.ovf_cells = h->ovf_cells; a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
     // candidate-list capacity per cell (shared memory scales with it): for a periodic box the mean number of cells
@@ -322,10 +326,11 @@ int stage_geometry(AfvHandle h) {
     }
     int cmax = h->cmax_hint;
     const size_t smem = (size_t)cmax * HULL_TPB * sizeof(int);
-    k_geometry_hull<<<nblk(n, HULL_TPB), HULL_TPB, smem, h->stream>>>(a, cmax);
+    k_hull<<<nblk(n, HULL_TPB), HULL_TPB, smem, h->stream>>>(a, cmax);
+    k_ring<<<nblk(n, HULL_TPB), HULL_TPB, 0, h->stream>>>(a);
     // cells queued by the fast kernel (usually none): large-capacity path, reads the queue length on the device
     k_geometry_slow<<<16, 64, 0, h->stream>>>(a);
-    h->launches += 2;
+    h->launches += 3;
     CK(cudaGetLastError());
     return AFV_OK;
 }
@@ -438,7 +443,7 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
     cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream);
-    cudaFuncSetAttribute(k_geometry_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(int));
+    cudaFuncSetAttribute(k_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(int));
     *out = h;
     return AFV_OK;
 }

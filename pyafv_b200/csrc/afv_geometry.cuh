@@ -26,6 +26,8 @@ struct GeomArgs {
     RingShared *rs;
     RingOwn *ro;
     unsigned char *ring_len;
+    int *hull_slot;            // [n * KHULL_STRIDE] polygon edges found by k_hull (neighbour slot, or -2 - v for virtual neighbour v)
+    unsigned char *hull_len;   // [n] number of polygon edges; HULL_QUEUED when the cell went to the slow path
     int *ring_key;             // [n * RS] neighbour slot of every ring entry (ARC for arcs; stale beyond ring_len): what k_force scans
     double *area, *perim, *arcl;
     int *coord;
@@ -39,6 +41,8 @@ struct GeomArgs {
 };
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
+constexpr int KHULL_STRIDE = 16;
+constexpr int HULL_QUEUED = 255;
 
 // ------------------------------------------------------------------------------------------------------
 // Shared second half.  Input: the convex polygon of the cell, counter-clockwise, relative to the centre: vertex k,
@@ -246,9 +250,9 @@ __device__ __forceinline__ void virtual_nbr(int v, double B4, double &x, double 
 }
 
 #ifndef HULL_MIN_BLOCKS
-#define HULL_MIN_BLOCKS 6
+#define HULL_MIN_BLOCKS 10
 #endif
-__global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_geometry_hull(GeomArgs a, const int cmax) {
+__global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_hull(GeomArgs a, const int cmax) {
     extern __shared__ int s_idx[];               // [cmax][HULL_TPB]: sorted slots of the in-range neighbours of each lane's cell
     const int tid = threadIdx.x;
     const int s = blockIdx.x * HULL_TPB + tid;
@@ -358,6 +362,63 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_geometry_hull(Geo
         }
     }
 
+    // ---- hand the polygon to k_ring ----
+    if (live) {
+        if (!ok) {   // too many neighbours / hull vertices for the fast path: queue for the large-capacity kernel
+            const int idx = atomicAdd(&a.flags[0], 1);
+            if (idx < OVF_MAX) a.ovf_cells[idx] = s; else atomicAdd(&a.flags[3], 1);
+            a.hull_len[s] = HULL_QUEUED;
+        } else {
+            const int mm = wrap ? m : 0;
+            a.hull_len[s] = (unsigned char)mm;
+            int *hs = a.hull_slot + (size_t)s * KHULL_STRIDE;
+            for (int k = 0; k < mm; ++k) {
+                const int h = (int)(((k < 8) ? (hull_lo >> (8 * k)) : (hull_hi >> (8 * (k - 8)))) & 0xffull);
+                hs[k] = (h < n) ? s_idx[h * HULL_TPB + tid] : -2 - (h - n);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2b: ring, measures and per-vertex gradients from the polygon found by k_hull.  One thread per cell, no shared
+// memory, no per-thread arrays.
+// ------------------------------------------------------------------------------------------------------
+#ifndef RING_MIN_BLOCKS
+#define RING_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) {
+    const int s = blockIdx.x * HULL_TPB + threadIdx.x;
+    const bool live = s < a.n;
+    const double r = a.ph.r, B4 = 4.0 * r;
+    const GridDesc g = *a.grid;
+    double xi = 0.0, yi = 0.0;
+    bool wrapx = false, wrapy = false;
+    int m = 0;
+    bool ok = true;
+    const int *hs = a.hull_slot + (size_t)(live ? s : 0) * KHULL_STRIDE;
+    if (live) {
+        const double2 pi_ = a.xy[s];
+        xi = pi_.x; yi = pi_.y;
+        const unsigned key_ = a.keys[s];
+        const int by = (int)(key_ / (unsigned)g.nbx), bx = (int)(key_ - (unsigned)by * (unsigned)g.nbx);
+        wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);
+        wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
+        m = a.hull_len[s];
+    }
+    const bool queued = (m == HULL_QUEUED);
+    if (queued) m = 0;
+    // displacement of polygon edge k's neighbour
+    auto disp = [&](int k, double &dx, double &dy, int &slot) {
+        slot = hs[k];
+        if (slot >= 0) {
+            const double2 pc = a.xy[slot];
+            dx = pc.x - xi; dy = pc.y - yi;
+            if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
+            if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
+        } else virtual_nbr(-2 - slot, B4, dx, dy);
+    };
+
     // ---- ring, streamed.  The polygon edges are the hull vertices h_0..h_{m-1} (counter-clockwise); the ring is
     //      clockwise, so edge k is walked from vertex k+1 to vertex k for k = m-1 .. 0 (finite_voronoi.py:363-459).
     //      Ring records are written as they are produced; their gx/gy slots double as scratch (1/length of a
@@ -368,12 +429,11 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_geometry_hull(Geo
     RingShared *const rs = a.rs + (size_t)s * RS;
     RingOwn *const ro = a.ro + (size_t)s * RS;
     int *const key = a.ring_key + (size_t)s * RS;
-    const int mm = (wrap && ok) ? m : 0;
+    const int mm = m;
     const int mloop = __reduce_max_sync(FULL_MASK, mm);
-    auto hull_at = [&](int k) { return (int)(((k < 8) ? (hull_lo >> (8 * k)) : (hull_hi >> (8 * (k - 8)))) & 0xffull); };
     auto isect = [](double ax, double ay, double bx_, double by_, double &x, double &y) {
         const double ca = 0.5 * (ax * ax + ay * ay), cb = 0.5 * (bx_ * bx_ + by_ * by_);
-        const double idet = 1.0 / (ax * by_ - ay * bx_);
+        const double idet = __drcp_rn(ax * by_ - ay * bx_);
         x = (ca * by_ - cb * ay) * idet;
         y = (ax * cb - bx_ * ca) * idet;
     };
@@ -388,10 +448,11 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_geometry_hull(Geo
         RingShared o; o.nbr = nbr_p; o.type = (nbr_p != ARC) ? 1 : 0; o.w = 0.0;
         if (nbr_p != ARC) {
             const double sx = xp - x, sy = yp - y;
-            const double l = sqrt(sx * sx + sy * sy);
-            P += l;
+            const double l2 = sx * sx + sy * sy;
+            const double il = l2 > 0.0 ? rsqrt(l2) : 0.0;
+            P += l2 * il;
             A += -0.5 * (xp * y - yp * x);
-            o.gx = l > 0.0 ? 1.0 / l : 0.0; o.gy = 0.0;
+            o.gx = il; o.gy = 0.0;
             ++z;
         } else {
             o.gx = x * yp - y * xp;              // v2 x v1
@@ -410,26 +471,25 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_geometry_hull(Geo
     };
     {
         double pcx = 0.0, pcy = 0.0, pnx = 0.0, pny = 0.0, V1x = 0.0, V1y = 0.0;
-        int hc = 0;
+        int jc = -2, jtmp;
         if (mm > 0) {
-            hc = hull_at(mm - 1);
-            disp(hc, pcx, pcy);
-            disp(hull_at(0), pnx, pny);
+            disp(mm - 1, pcx, pcy, jc);
+            disp(0, pnx, pny, jtmp);
             isect(pcx, pcy, pnx, pny, V1x, V1y);           // vertex m = vertex 0 = edge(m-1) ^ edge(0)
         }
         for (int kk = 0; kk < mloop; ++kk) {
             if (kk < mm) {
                 const int k = mm - 1 - kk;
-                const int hp = hull_at(k == 0 ? mm - 1 : k - 1);
                 double ppx, ppy, V2x, V2y;
-                disp(hp, ppx, ppy);
+                int jp;
+                disp(k == 0 ? mm - 1 : k - 1, ppx, ppy, jp);
                 isect(ppx, ppy, pcx, pcy, V2x, V2y);       // vertex k = edge(k-1) ^ edge(k)
-                if (hc < n && ok) {                        // a real neighbour (virtual edges emit nothing)
-                    const int j = s_idx[hc * HULL_TPB + tid];
+                if (jc >= 0 && ok) {                       // a real neighbour (virtual edges emit nothing)
+                    const int j = jc;
                     if (V1x * V1x + V1y * V1y <= r2) emit(V1x, V1y, pcx, pcy, j);      // inner start vertex, d1 <= r
                     const double d2c = 0.25 * (pcx * pcx + pcy * pcy);               // |C|^2, C = p/2
                     if (d2c < r2) {                        // the bisector crosses the disk
-                        const double inv = 0.5 / sqrt(d2c);
+                        const double inv = 0.5 * rsqrt(d2c);
                         const double ux = pcy * inv, uy = -pcx * inv;                  // clockwise unit vector along the edge
                         const double t1 = V1x * ux + V1y * uy, t2 = V2x * ux + V2y * uy;
                         const double tr = sqrt(r2 - d2c);
@@ -437,19 +497,20 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_geometry_hull(Geo
                         if (tr < t2 && tr > t1) emit(0.5 * pcx + tr * ux, 0.5 * pcy + tr * uy, pcx, pcy, ARC);  // exit point
                     }
                 }
-                pcx = ppx; pcy = ppy; hc = hp; V1x = V2x; V1y = V2y;
+                pcx = ppx; pcy = ppy; jc = jp; V1x = V2x; V1y = V2y;
             }
         }
     }
-    const bool ringed = live && ok && E >= 2;
+    const bool ringed = live && ok && !queued && E >= 2;
     if (ringed) close_prev(x0, y0);              // closing edge: last entry -> first entry
 
-    if (live && !ok) {                           // queue the cell for the large-capacity kernel
+    if (live && !ok) {                           // ring longer than the stride: queue the cell for the large-capacity kernel
         const int idx = atomicAdd(&a.flags[0], 1);
         if (idx < OVF_MAX) a.ovf_cells[idx] = s; else atomicAdd(&a.flags[3], 1);
         a.ring_len[s] = 0;
     }
-    if (live && ok && E < 2) {                   // isolated cell (cell_geom.pyx:402-406)
+    if (live && queued) a.ring_len[s] = 0;       // k_geometry_slow fills everything in
+    if (live && ok && !queued && E < 2) {                   // isolated cell (cell_geom.pyx:402-406)
         a.area[s] = PI * r2; a.perim[s] = TWO_PI * r; a.arcl[s] = TWO_PI * r; a.coord[s] = 0;
         a.ring_len[s] = 0;
     }

@@ -178,7 +178,10 @@ __device__ __forceinline__ bool lookup_edge(const ForceArgs &a, int j, int self,
     return false;
 }
 
-__global__ void __launch_bounds__(128) k_force(ForceArgs a) {
+#ifndef FORCE_MIN_BLOCKS
+#define FORCE_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n) return;
     if (!a.owned[s]) { a.fx[s] = 0.0; a.fy[s] = 0.0; return; }

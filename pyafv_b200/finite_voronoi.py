@@ -89,6 +89,14 @@ class FiniteVoronoiSimulator:
     def pts(self, value) -> None:
         self.update_positions(value)
 
+    def positions_into(self, out: np.ndarray) -> np.ndarray:
+        """Copy the current cell centres from the device into ``out`` ((N,2) float64, C-contiguous; e.g. a pinned
+        host buffer) without allocating."""
+        if out.shape != (self.N, 2) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous float64 array of shape ({self.N},2)")
+        self._h.call("afv_get_positions", out.ctypes.data)
+        return out
+
     @property
     def theta(self) -> np.ndarray:
         """(N,) self-propulsion angles held on the device."""

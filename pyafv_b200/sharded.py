@@ -281,10 +281,12 @@ class SlabShardedSimulator:
     def exchange_in(self, from_left, from_right) -> None:
         self.store.finish_exchange(from_left, from_right, self._caps()[0])
 
-    def compute_step(self, dt, mu, v0, Dr, seed) -> None:
+    def compute_step(self, dt, mu, v0, Dr, seed, want_results: bool = False):
         self._h.call("afv_step", float(dt), float(mu), float(v0), float(Dr), C.c_uint64(int(seed)), C.c_int64(self._step_index), 1, None)
         self._step_index += 1
+        res = self.store.results() if want_results else None   # rows of the owned cells: updated x, y, theta + F, A, P, L, z
         self.store.drop_halo()
+        return res
 
     def compute_build(self) -> torch.Tensor:
         from . import _lib
@@ -311,7 +313,7 @@ class SlabShardedSimulator:
 
     def e2e_measure(self, k: int, step: dict) -> dict:
         """End-to-end leg of bench.py for N > 1: every step uploads this rank's cells from pinned host memory,
-        exchanges halos, builds, and reads the forces back."""
+        exchanges halos, advances one step, and reads the updated cells (and forces) back."""
         import time
         import torch.distributed as dist
         res = self.build()
@@ -330,7 +332,7 @@ class SlabShardedSimulator:
             dev.copy_(host, non_blocking=True)
             self.store.set_cells(dev, n)
             self.exchange_in(*self.comm.exchange_fixed(*self.exchange_out()))
-            r = self.compute_build()
+            r = self.compute_step(step["dt"], step["mu"], step["v0"], step["Dr"], 7, want_results=True)
             out[: r.shape[0]].copy_(r, non_blocking=True)
             torch.cuda.synchronize()
         dist.barrier()
@@ -341,7 +343,7 @@ class SlabShardedSimulator:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         return {"value": float(tot.item()) * k / float(tmax.item()), "unit": "cell-steps/s", "h2d_bytes_per_step": 8 * ROW * n,
                 "d2h_bytes_per_step": 8 * RES_ROW * n, "steps": k,
-                "api": "SlabShardedSimulator: H2D cells (pinned) + halo exchange + build + D2H results, per rank"}
+                "api": "SlabShardedSimulator: H2D cells (pinned) + halo exchange + step + D2H updated cells and forces, per rank"}
 
 
 def results_dict(res: torch.Tensor) -> dict[str, np.ndarray]:
