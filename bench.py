@@ -150,7 +150,7 @@ def run_ours(args) -> dict:
         one_step(i)
     # ---- device-timed region ----
     h.call("afv_set_profiling", 1)
-    ms4, l4 = np.zeros(4), np.zeros(4, dtype=np.int64)
+    ms4, l4 = np.zeros(6), np.zeros(6, dtype=np.int64)
     h.call("afv_get_stage_times", ms4.ctypes.data, l4.ctypes.data, 1)
     launches0 = int(h.lib.afv_launch_count(h._h))
     sampler = ClockSampler(local)
@@ -181,8 +181,8 @@ def run_ours(args) -> dict:
 
     # ---- roofline of the dominant kernel (rank 0's stage timers; events on the launching stream) ----
     peaks, peak_src = measured_peaks()
-    stage_names = ["bin+sort+reorder", "k_geometry", "k_force(+step)", "other"]
-    dom = int(np.argmax(ms4[1:3])) + 1
+    stage_names = ["bin+sort+reorder+bin_start", "k_hull", "k_ring", "k_force(+update)", "export", "k_geometry_slow"]
+    dom = int(np.argmax(ms4[1:4])) + 1
     dom_ms = float(ms4[dom] / max(int(l4[dom]), 1))
     n_local = int(h.n)
     fp64 = _lib.C.c_double()

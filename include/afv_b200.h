@@ -120,9 +120,11 @@ int afv_get_diagnostics(AfvHandle h, int64_t out[4]);
 /* ---- measurement --------------------------------------------------------------------------------- */
 /* when enabled, every stage of build/step is bracketed by CUDA events on the handle's stream */
 int afv_set_profiling(AfvHandle h, int enabled);
-/* accumulated milliseconds and launch counts since the last reset:
- * stage 0 bin+sort+reorder, 1 geometry kernel, 2 force(+step) kernel, 3 everything else */
-int afv_get_stage_times(AfvHandle h, double ms_out[4], int64_t launches_out[4], int reset);
+/* accumulated milliseconds and span counts since the last reset, per stage:
+ * 0 bin + sort + reorder + bin starts, 1 k_hull, 2 k_ring, 3 k_force (+ update), 4 connections / ring export,
+ * 5 k_geometry_slow (queued cells) */
+#define AFV_N_STAGES 6
+int afv_get_stage_times(AfvHandle h, double ms_out[AFV_N_STAGES], int64_t launches_out[AFV_N_STAGES], int reset);
 /* number of kernel launches issued by this handle since creation */
 int64_t afv_launch_count(AfvHandle h);
 /* pinned host memory for end-to-end runs */

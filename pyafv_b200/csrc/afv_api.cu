@@ -83,8 +83,8 @@ struct AfvContext {
     struct Span { int stage; cudaEvent_t a, b; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
-    double stage_ms[4] = {0, 0, 0, 0};
-    int64_t stage_launches[4] = {0, 0, 0, 0};
+    double stage_ms[AFV_N_STAGES] = {0, 0, 0, 0, 0, 0};
+    int64_t stage_launches[AFV_N_STAGES] = {0, 0, 0, 0, 0, 0};
     int64_t launches = 0;
     std::string err;
 };
@@ -309,7 +309,6 @@ int stage_sort(AfvHandle h) {
 }
 
 int stage_geometry(AfvHandle h) {
-    StageTimer t(h, 1);
     const int n = (int)h->n;
     const int c = h->cur;
     GeomArgs a;
@@ -326,8 +325,15 @@ int stage_geometry(AfvHandle h) {
     }
     int cmax = h->cmax_hint;
     const size_t smem = (size_t)cmax * HULL_TPB * sizeof(int);
-    k_hull<<<nblk(n, HULL_TPB), HULL_TPB, smem, h->stream>>>(a, cmax);
-    k_ring<<<nblk(n, HULL_TPB), HULL_TPB, 0, h->stream>>>(a);
+    {
+        StageTimer t(h, 1);
+        k_hull<<<nblk(n, HULL_TPB), HULL_TPB, smem, h->stream>>>(a, cmax);
+    }
+    {
+        StageTimer t(h, 2);
+        k_ring<<<nblk(n, HULL_TPB), HULL_TPB, 0, h->stream>>>(a);
+    }
+    StageTimer t(h, 5);
     // cells queued by the fast kernel (usually none): large-capacity path, reads the queue length on the device
     k_geometry_slow<<<16, 64, 0, h->stream>>>(a);
     h->launches += 3;
@@ -337,7 +343,7 @@ int stage_geometry(AfvHandle h) {
 
 int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, double Dr, uint64_t seed, int64_t step,
                 const double *noise_row) {
-    StageTimer t(h, 2);
+    StageTimer t(h, 3);
     const int n = (int)h->n;
     const int c = h->cur;
     ForceArgs a;
@@ -547,7 +553,7 @@ int afv_build(AfvHandle h, unsigned flags) {
     const int n = (int)h->n;
     const int c = h->cur;
     if (flags & AFV_BUILD_CONNECT) {
-        StageTimer t(h, 3);
+        StageTimer t(h, 4);
         k_conn_count<<<nblk(n), TPB, 0, h->stream>>>(ring_view(h), h->gid[c], h->owned[c], n, h->cnt);
         size_t tmp = h->cub_tmp_bytes;
         CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp, tmp, h->cnt, h->off, n + 1, h->stream));
@@ -561,7 +567,7 @@ int afv_build(AfvHandle h, unsigned flags) {
     }
     if (flags & AFV_BUILD_RINGS) {
         if (!h->gid_is_perm) { h->err = "ring export needs a handle filled by afv_set_positions"; return AFV_ERR_STATE; }
-        StageTimer t(h, 3);
+        StageTimer t(h, 4);
         k_ring_len_by_gid<<<nblk(n, 256), 256, 0, h->stream>>>(ring_view(h), h->gid[c], n, h->cnt);
         CK(cudaMemsetAsync(h->cnt + n, 0, sizeof(int), h->stream));
         size_t tmp = h->cub_tmp_bytes;
@@ -717,11 +723,11 @@ int afv_set_profiling(AfvHandle h, int enabled) {
     return AFV_OK;
 }
 
-int afv_get_stage_times(AfvHandle h, double ms_out[4], int64_t launches_out[4], int reset) {
+int afv_get_stage_times(AfvHandle h, double ms_out[AFV_N_STAGES], int64_t launches_out[AFV_N_STAGES], int reset) {
     CHECK_H(h);
     collect_spans(h);
-    for (int i = 0; i < 4; ++i) { ms_out[i] = h->stage_ms[i]; launches_out[i] = h->stage_launches[i]; }
-    if (reset) for (int i = 0; i < 4; ++i) { h->stage_ms[i] = 0; h->stage_launches[i] = 0; }
+    for (int i = 0; i < AFV_N_STAGES; ++i) { ms_out[i] = h->stage_ms[i]; launches_out[i] = h->stage_launches[i]; }
+    if (reset) for (int i = 0; i < AFV_N_STAGES; ++i) { h->stage_ms[i] = 0; h->stage_launches[i] = 0; }
     return AFV_OK;
 }
 

@@ -14,8 +14,8 @@ sim = afv.FiniteVoronoiSimulator(rng.random((N, 2)) * L, afv.PhysicalParams(), p
 sim.step(0.01, 1.0, 2.4, 0.3, theta=2 * np.pi * rng.random(N) - np.pi, seed=7, n_steps=5)
 h = sim._h
 h.call("afv_set_profiling", 1)
-ms, l = np.zeros(4), np.zeros(4, dtype=np.int64)
+ms, l = np.zeros(6), np.zeros(6, dtype=np.int64)
 h.call("afv_get_stage_times", ms.ctypes.data, l.ctypes.data, 1)
 sim.step(0.01, 1.0, 2.4, 0.3, seed=7, n_steps=steps)
 h.call("afv_get_stage_times", ms.ctypes.data, l.ctypes.data, 1)
-print(os.environ.get("AFV_B200_LIB", "default"), "N", N, "dens", dens, "sort %.3f geom %.3f force %.3f total %.3f ms/step" % (ms[0]/steps, ms[1]/steps, ms[2]/steps, ms[:3].sum()/steps), sim.diagnostics())
+print(os.environ.get("AFV_B200_LIB", "default"), "N", N, "dens", dens, "sort %.3f hull %.3f ring %.3f force %.3f slow %.3f total %.3f ms/step" % (ms[0]/steps, ms[1]/steps, ms[2]/steps, ms[3]/steps, ms[5]/steps, ms.sum()/steps), sim.diagnostics())
