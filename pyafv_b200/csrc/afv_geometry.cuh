@@ -469,6 +469,10 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
         if (nb == ARC) arcmask |= 1u << E;
         xp = x; yp = y; nbr_p = nb; ++E;
     };
+    for (int k = 0; k < mm; ++k) {               // pull the neighbours' positions towards L1 before the dependent walk
+        const int sl = hs[k];
+        if (sl >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.xy + sl));
+    }
     {
         double pcx = 0.0, pcy = 0.0, pnx = 0.0, pny = 0.0, V1x = 0.0, V1y = 0.0;
         int jc = -2, jtmp;
@@ -546,22 +550,24 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     {
         const int EE = ringed ? E : 0;
         const int Eloop = __reduce_max_sync(FULL_MASK, EE);
-        double hpx = 0.0, hpy = 0.0, hcx = 0.0, hcy = 0.0, ilp = 0.0, ilc = 0.0;
+        // software pipeline: the record of entry e+2 (vertex position, 1/length scratch) is requested while vertex e is
+        // being processed; entry e's scratch is only overwritten after its last use
+        double hpx = 0.0, hpy = 0.0, hcx = 0.0, hcy = 0.0, hnx = 0.0, hny = 0.0, ilp = 0.0, ilc = 0.0, iln = 0.0;
+        auto load_h = [&](int e, double &x, double &y) { const double2 v = *reinterpret_cast<const double2 *>(&ro[e]); x = v.x; y = v.y; };
+        auto load_il = [&](int e) { return ((arcmask >> e) & 1u) ? 0.0 : rs[e].gx; };
         if (EE > 0) {
-            const double2 a0_ = *reinterpret_cast<const double2 *>(&ro[EE - 1]);
-            const double2 a1_ = *reinterpret_cast<const double2 *>(&ro[0]);
-            hpx = a0_.x; hpy = a0_.y; hcx = a1_.x; hcy = a1_.y;
-            ilp = ((arcmask >> (EE - 1)) & 1u) ? 0.0 : rs[EE - 1].gx;
-            ilc = (arcmask & 1u) ? 0.0 : rs[0].gx;
+            const int e1 = (1 == EE) ? 0 : 1;
+            load_h(EE - 1, hpx, hpy); load_h(0, hcx, hcy); load_h(e1, hnx, hny);
+            ilp = load_il(EE - 1); ilc = load_il(0); iln = load_il(e1);
         }
         for (int e = 0; e < Eloop; ++e) {
             if (e < EE) {
-                const int e2 = (e + 1 == EE) ? 0 : e + 1, e0 = (e == 0) ? EE - 1 : e - 1;
-                const double2 nx_ = *reinterpret_cast<const double2 *>(&ro[e2]);
-                const double hnx = nx_.x, hny = nx_.y;
+                const int e0 = (e == 0) ? EE - 1 : e - 1;
+                int e3 = e + 2; if (e3 >= EE) e3 -= EE; if (e3 >= EE) e3 -= EE;
+                double hqx, hqy;
+                load_h(e3, hqx, hqy);
+                const double ilq = load_il(e3);
                 const bool arc_c = (arcmask >> e) & 1u, arc_p = (arcmask >> e0) & 1u;
-                // next edge's 1/length must be read before this entry's record is overwritten when e2 == e (never: EE >= 2)
-                const double iln = ((arcmask >> e2) & 1u) ? 0.0 : rs[e2].gx;
                 // u(e) = (v1 - v2)/|v1 - v2| for straight edges, 0 for arcs;  dP/dv1 = u(e) - u(e-1);  dA/dv1 = 0.5 (perp(v0) - perp(v2))
                 const double uex = (hcx - hnx) * ilc, uey = (hcy - hny) * ilc;
                 const double upx = (hpx - hcx) * ilp, upy = (hpy - hcy) * ilp;
@@ -573,9 +579,8 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
                 else if (arc_p)  // an arc ends here
                     w = -(cA * 0.5 * (r2 - (hpx * hcx + hpy * hcy)) + cL * r);
                 double *dst = reinterpret_cast<double *>(&rs[e]);
-                // entry 0's scratch is still needed by the last entry (as "next"): keep it in a register
                 dst[1] = gx; dst[2] = gy; dst[3] = w;
-                hpx = hcx; hpy = hcy; hcx = hnx; hcy = hny; ilp = ilc; ilc = iln;
+                hpx = hcx; hpy = hcy; hcx = hnx; hcy = hny; hnx = hqx; hny = hqy; ilp = ilc; ilc = iln; iln = ilq;
             }
         }
     }
