@@ -26,16 +26,24 @@ struct GridDesc {
 
 // Shared part of a ring entry: what OTHER cells read during the force gather.  32 B = one DRAM sector.
 struct __align__(16) RingShared {
+    double gx, gy; // 2KA(A-A0) dA/dh + 2KP(P-P0) dP/dh of the OWNING cell at this vertex  (one 16-byte load)
+    double w;    // arc-end weight 2KA(A-A0) da + (2KP(P-P0) + Lambda) dl of the owning cell (outer vertices only)
     int nbr;     // sorted slot of the neighbour across the edge LEAVING this vertex, ARC for an arc
     int type;    // 1 straight contact edge, 0 arc  (finite_voronoi.py:441-459)
-    double gx, gy; // 2KA(A-A0) dA/dh + 2KP(P-P0) dP/dh of the OWNING cell at this vertex
-    double w;    // arc-end weight 2KA(A-A0) da + (2KP(P-P0) + Lambda) dl of the owning cell (outer vertices)
 };
 
-// Private part of a ring entry: only the owning cell reads it back.
+// Private part of a ring entry: only the owning cell reads it back.  Stored SLOT-MAJOR, entry e of cell s at
+// [e * stride + s] (stride = allocated cells), so that the lanes of a warp -- consecutive cells working on the same
+// entry -- touch consecutive 32-byte records instead of 32 different cache lines.
 struct __align__(16) RingOwn {
     double hx, hy;  // vertex position relative to the cell centre
     double px, py;  // r_nbr - r_cell (minimum image) for the edge leaving this vertex (undefined for arcs)
+};
+// The owner's copy of its own gradient record, slot-major like RingOwn.  While k_ring runs, gx/gy hold scratch
+// (1/length of the straight edge leaving the vertex, or the cross/dot of an arc's end points).
+struct __align__(16) RingSelf {
+    double gx, gy, w;
+    int nbr, type;
 };
 
 __device__ __forceinline__ double min_image(double d, double L, double halfL) {

@@ -23,10 +23,12 @@ struct GeomArgs {
     const GridDesc *grid;
     int n;
     PhysDev ph;
-    RingShared *rs;
-    RingOwn *ro;
+    RingShared *rs;            // [n * RS] per cell: what neighbours gather
+    RingOwn *ro;               // slot-major, stride `stride`
+    RingSelf *self;            // slot-major, stride `stride`
+    size_t stride;             // allocated cells
     unsigned char *ring_len;
-    int *hull_slot;            // [n * KHULL_STRIDE] polygon edges found by k_hull (neighbour slot, or -2 - v for virtual neighbour v)
+    int *hull_slot;            // [KHULL_STRIDE * stride], slot-major: polygon edges found by k_hull (neighbour slot, or -2 - v for virtual neighbour v)
     unsigned char *hull_len;   // [n] number of polygon edges; HULL_QUEUED when the cell went to the slow path
     int *ring_key;             // [n * RS] neighbour slot of every ring entry (ARC for arcs; stale beyond ring_len): what k_force scans
     double *area, *perim, *arcl;
@@ -158,13 +160,15 @@ __device__ __forceinline__ void finish_cell(const GeomArgs &a, const int s, cons
     P += Larc;
 
     RingShared *rs = a.rs + (size_t)s * RS;
-    RingOwn *ro = a.ro + (size_t)s * RS;
+    RingOwn *ro = a.ro + s;
+    size_t ros = a.stride;          // RingOwn / RingSelf element stride (slot-major), 1 inside the overflow pool
+    bool pooled = false;
     double cA = 0.0, cP = 0.0, cL = 0.0;
     if (ringed) {
         a.area[s] = A; a.perim[s] = P; a.arcl[s] = Larc; a.coord[s] = z;
         if (SLOW && E > RS) {
             a.ring_len[s] = RING_IN_POOL; a.ovf_index[s] = pool_idx; a.ovf_len[pool_idx] = E;
-            rs = a.ovf_rs + (size_t)pool_idx * RS_SLOW; ro = a.ovf_ro + (size_t)pool_idx * RS_SLOW;
+            rs = a.ovf_rs + (size_t)pool_idx * RS_SLOW; ro = a.ovf_ro + (size_t)pool_idx * RS_SLOW; ros = 1; pooled = true;
         } else {
             a.ring_len[s] = (unsigned char)E;
         }
@@ -189,7 +193,8 @@ __device__ __forceinline__ void finish_cell(const GeomArgs &a, const int s, cons
             RingShared o; o.nbr = nbr[e]; o.type = typ[e]; o.gx = gx; o.gy = gy; o.w = w;
             rs[e] = o;
             RingOwn q; q.hx = hx[e]; q.hy = hy[e]; q.px = qx[e]; q.py = qy[e];
-            ro[e] = q;
+            ro[e * ros] = q;
+            if (!pooled) { RingSelf f; f.gx = gx; f.gy = gy; f.w = w; f.nbr = nbr[e]; f.type = typ[e]; a.self[e * a.stride + s] = f; }
         }
     }
     if (ringed && E <= RS) {   // the compact key row that k_force scans (entries beyond ring_len are stale)
@@ -371,10 +376,10 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_hull(GeomArgs a, 
         } else {
             const int mm = wrap ? m : 0;
             a.hull_len[s] = (unsigned char)mm;
-            int *hs = a.hull_slot + (size_t)s * KHULL_STRIDE;
+            int *hs = a.hull_slot + s;                       // slot-major: edge k at hs[k * stride]
             for (int k = 0; k < mm; ++k) {
                 const int h = (int)(((k < 8) ? (hull_lo >> (8 * k)) : (hull_hi >> (8 * (k - 8)))) & 0xffull);
-                hs[k] = (h < n) ? s_idx[h * HULL_TPB + tid] : -2 - (h - n);
+                hs[k * a.stride] = (h < n) ? s_idx[h * HULL_TPB + tid] : -2 - (h - n);
             }
         }
     }
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     bool wrapx = false, wrapy = false;
     int m = 0;
     bool ok = true;
-    const int *hs = a.hull_slot + (size_t)(live ? s : 0) * KHULL_STRIDE;
+    const int *hs = a.hull_slot + (live ? s : 0);      // slot-major: edge k at hs[k * a.stride]
     if (live) {
         const double2 pi_ = a.xy[s];
         xi = pi_.x; yi = pi_.y;
@@ -410,7 +415,7 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     if (queued) m = 0;
     // displacement of polygon edge k's neighbour
     auto disp = [&](int k, double &dx, double &dy, int &slot) {
-        slot = hs[k];
+        slot = hs[k * a.stride];
         if (slot >= 0) {
             const double2 pc = a.xy[slot];
             dx = pc.x - xi; dy = pc.y - yi;
@@ -427,7 +432,9 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     const double r2 = r * r;
     const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
     RingShared *const rs = a.rs + (size_t)s * RS;
-    RingOwn *const ro = a.ro + (size_t)s * RS;
+    RingOwn *const ro = a.ro + s;                 // slot-major: entry e at ro[e * ros]
+    RingSelf *const self = a.self + s;
+    const size_t ros = a.stride;
     int *const key = a.ring_key + (size_t)s * RS;
     const int mm = m;
     const int mloop = __reduce_max_sync(FULL_MASK, mm);
@@ -445,7 +452,7 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     int nbr_p = ARC;
     // connect the previous entry to (x, y): measure the edge, then write the previous entry's shared record
     auto close_prev = [&](double x, double y) {
-        RingShared o; o.nbr = nbr_p; o.type = (nbr_p != ARC) ? 1 : 0; o.w = 0.0;
+        RingSelf o; o.nbr = nbr_p; o.type = (nbr_p != ARC) ? 1 : 0; o.w = 0.0;
         if (nbr_p != ARC) {
             const double sx = xp - x, sy = yp - y;
             const double l2 = sx * sx + sy * sy;
@@ -458,19 +465,19 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
             o.gx = x * yp - y * xp;              // v2 x v1
             o.gy = xp * x + yp * y;              // v1 . v2
         }
-        rs[E - 1] = o;
+        self[(E - 1) * ros] = o;
         key[E - 1] = nbr_p;
     };
     auto emit = [&](double x, double y, double ex, double ey, int nb) {
         if (E >= RS) { ok = false; return; }
         if (E > 0) close_prev(x, y); else { x0 = x; y0 = y; }
         RingOwn q; q.hx = x; q.hy = y; q.px = ex; q.py = ey;
-        ro[E] = q;
+        ro[E * ros] = q;
         if (nb == ARC) arcmask |= 1u << E;
         xp = x; yp = y; nbr_p = nb; ++E;
     };
     for (int k = 0; k < mm; ++k) {               // pull the neighbours' positions towards L1 before the dependent walk
-        const int sl = hs[k];
+        const int sl = hs[k * a.stride];
         if (sl >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.xy + sl));
     }
     {
@@ -528,7 +535,8 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
             if (rem) {
                 const int e = __ffs(rem) - 1;
                 rem &= rem - 1;
-                double ang = atan2(rs[e].gx, rs[e].gy);   // angle(v1) - angle(v2)
+                const RingSelf sc = self[e * ros];
+                double ang = atan2(sc.gx, sc.gy);         // angle(v1) - angle(v2)
                 if (ang < 0.0) ang += TWO_PI;
                 Larc += r * ang;
                 A += 0.5 * r2 * ang;
@@ -553,8 +561,8 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
         // software pipeline: the record of entry e+2 (vertex position, 1/length scratch) is requested while vertex e is
         // being processed; entry e's scratch is only overwritten after its last use
         double hpx = 0.0, hpy = 0.0, hcx = 0.0, hcy = 0.0, hnx = 0.0, hny = 0.0, ilp = 0.0, ilc = 0.0, iln = 0.0;
-        auto load_h = [&](int e, double &x, double &y) { const double2 v = *reinterpret_cast<const double2 *>(&ro[e]); x = v.x; y = v.y; };
-        auto load_il = [&](int e) { return ((arcmask >> e) & 1u) ? 0.0 : rs[e].gx; };
+        auto load_h = [&](int e, double &x, double &y) { const double2 v = *reinterpret_cast<const double2 *>(&ro[e * ros]); x = v.x; y = v.y; };
+        auto load_il = [&](int e) { return ((arcmask >> e) & 1u) ? 0.0 : self[e * ros].gx; };
         if (EE > 0) {
             const int e1 = (1 == EE) ? 0 : 1;
             load_h(EE - 1, hpx, hpy); load_h(0, hcx, hcy); load_h(e1, hnx, hny);
@@ -578,8 +586,12 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
                     w = cA * 0.5 * (r2 - (hcx * hnx + hcy * hny)) + cL * r;
                 else if (arc_p)  // an arc ends here
                     w = -(cA * 0.5 * (r2 - (hpx * hcx + hpy * hcy)) + cL * r);
-                double *dst = reinterpret_cast<double *>(&rs[e]);
-                dst[1] = gx; dst[2] = gy; dst[3] = w;
+                // final records: the neighbour-visible one (per cell) and the owner's slot-major copy
+                const int2 nt = *reinterpret_cast<const int2 *>(&self[e * ros].nbr);
+                RingShared o; o.nbr = nt.x; o.type = nt.y; o.gx = gx; o.gy = gy; o.w = w;
+                rs[e] = o;
+                double *dst = reinterpret_cast<double *>(&self[e * ros]);
+                dst[0] = gx; dst[1] = gy; dst[2] = w;
                 hpx = hcx; hpy = hcy; hcx = hnx; hcy = hny; hnx = hqx; hny = hqy; ilp = ilc; ilc = iln; iln = ilq;
             }
         }

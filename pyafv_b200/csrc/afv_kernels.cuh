@@ -118,7 +118,9 @@ __global__ void k_bin_start(const unsigned *__restrict__ keys_sorted, int n, con
 // ------------------------------------------------------------------------------------------------------
 struct ForceArgs {
     const RingShared *rs;
-    const RingOwn *ro;
+    const RingOwn *ro;             // slot-major
+    const RingSelf *self;          // slot-major
+    size_t stride;
     const unsigned char *ring_len;
     const int *ring_key;
     const int *ovf_index, *ovf_len;
@@ -141,40 +143,45 @@ struct ForceArgs {
     double Lx, Ly;                 // periodic wrap of the updated positions per direction (0 = none)
 };
 
-struct NbrRec { double gx, gy, w; };
+struct NbrRec { double gx, gy; const double *pw; };   // the arc weight is fetched only at outer vertices
 
 __device__ __forceinline__ bool lookup_edge(const ForceArgs &a, int j, int self, NbrRec &at_start, NbrRec &at_end) {
     // edge (j -> self) in j's ring runs from slot t to slot t+1; seen from `self` the same edge runs the other
     // way, so j's slot t is the END of self's edge and j's slot t+1 its START.
-    // The 16 keys of j's ring are one 64-byte row: four independent 16-byte loads, then register compares.
+    // The 16 keys of j's ring are one 64-byte row: independent 16-byte loads, then register compares; rings of
+    // <= 8 entries (the common case) need only the first half.
     const int4 *kj = reinterpret_cast<const int4 *>(a.ring_key + (size_t)j * RS);
-    int Ej = a.ring_len[j];                       // independent of the key loads: all five are in flight together
-    const int4 k0 = kj[0], k1 = kj[1], k2 = kj[2], k3 = kj[3];
+    int Ej = a.ring_len[j];                       // independent of the key loads: all are in flight together
+    const int4 k0 = kj[0], k1 = kj[1];
     const RingShared *rj = a.rs + (size_t)j * RS;
     int t = -1;
     if (Ej != RING_IN_POOL) {
-        const int kk[RS] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
-        unsigned match = 0u;
-#pragma unroll
-        for (int e = 0; e < RS; ++e) match |= (kk[e] == self ? 1u : 0u) << e;
+        unsigned match = (k0.x == self ? 1u : 0u) | (k0.y == self ? 2u : 0u) | (k0.z == self ? 4u : 0u) | (k0.w == self ? 8u : 0u) |
+                         (k1.x == self ? 16u : 0u) | (k1.y == self ? 32u : 0u) | (k1.z == self ? 64u : 0u) | (k1.w == self ? 128u : 0u);
+        if (Ej > 8) {
+            const int4 k2 = kj[2], k3 = kj[3];
+            match |= (k2.x == self ? 1u : 0u) << 8 | (k2.y == self ? 1u : 0u) << 9 | (k2.z == self ? 1u : 0u) << 10 | (k2.w == self ? 1u : 0u) << 11 |
+                     (k3.x == self ? 1u : 0u) << 12 | (k3.y == self ? 1u : 0u) << 13 | (k3.z == self ? 1u : 0u) << 14 | (k3.w == self ? 1u : 0u) << 15;
+        }
         match &= (1u << Ej) - 1u;                 // slots beyond the ring hold stale keys
         t = __ffs(match) - 1;
     } else {   // pooled ring: generic scan
         const int pi = a.ovf_index[j];
         Ej = a.ovf_len[pi]; rj = a.ovf_rs + (size_t)pi * RS_SLOW;
         for (int q = 0; q < Ej; ++q) {
-            const int2 kt = *reinterpret_cast<const int2 *>(&rj[q]);
+            const int2 kt = *reinterpret_cast<const int2 *>(&rj[q].nbr);
             if (kt.x == self && kt.y == 1) { t = q; break; }
         }
     }
     if (t >= 0) {
         const int t1 = (t + 1 == Ej) ? 0 : t + 1;
-        at_end.gx = rj[t].gx; at_end.gy = rj[t].gy; at_end.w = rj[t].w;
-        at_start.gx = rj[t1].gx; at_start.gy = rj[t1].gy; at_start.w = rj[t1].w;
+        const double2 ge = *reinterpret_cast<const double2 *>(&rj[t]), gs = *reinterpret_cast<const double2 *>(&rj[t1]);
+        at_end.gx = ge.x; at_end.gy = ge.y; at_end.pw = &rj[t].w;
+        at_start.gx = gs.x; at_start.gy = gs.y; at_start.pw = &rj[t1].w;
         return true;
     }
-    at_start.gx = at_start.gy = at_start.w = 0.0;
-    at_end.gx = at_end.gy = at_end.w = 0.0;
+    at_start.gx = at_start.gy = 0.0; at_start.pw = nullptr;
+    at_end.gx = at_end.gy = 0.0; at_end.pw = nullptr;
     return false;
 }
 
@@ -189,22 +196,31 @@ __global__ void __launch_bounds__(128, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
     const double r = a.ph.r, r2 = r * r;
     double dEx = 0.0, dEy = 0.0;
     if (E >= 2) {
-        const RingShared *rs = a.rs + (size_t)s * RS;
-        const RingOwn *ro = a.ro + (size_t)s * RS;
+        // own ring: slot-major private records (coalesced across the warp); pooled rings are per-cell arrays
+        const RingOwn *ro = a.ro + s;
+        const RingSelf *self = a.self + s;
+        const RingShared *prs = nullptr;
+        size_t ros = a.stride;
         if (E == RING_IN_POOL) {
             const int pi = a.ovf_index[s];
-            E = a.ovf_len[pi]; rs = a.ovf_rs + (size_t)pi * RS_SLOW; ro = a.ovf_ro + (size_t)pi * RS_SLOW;
+            E = a.ovf_len[pi]; prs = a.ovf_rs + (size_t)pi * RS_SLOW; ro = a.ovf_ro + (size_t)pi * RS_SLOW; ros = 1;
         }
+        auto own_rec = [&](int e) {
+            RingShared q;
+            if (prs) q = prs[e];
+            else { const RingSelf f = self[e * ros]; q.nbr = f.nbr; q.type = f.type; q.gx = f.gx; q.gy = f.gy; q.w = f.w; }
+            return q;
+        };
         int misses = 0;
         // contribution of the last edge's neighbour to vertex 0
-        RingShared prev = rs[E - 1];
-        RingOwn prev_o = ro[E - 1];
-        NbrRec pend = {0.0, 0.0, 0.0}, tmp;
+        RingShared prev = own_rec(E - 1);
+        RingOwn prev_o = ro[(E - 1) * ros];
+        NbrRec pend = {0.0, 0.0, nullptr}, tmp;
         if (prev.type == 1) misses += !lookup_edge(a, prev.nbr, s, tmp, pend);
         for (int e = 0; e < E; ++e) {
-            const RingShared cur = rs[e];
-            const RingOwn own = ro[e];
-            NbrRec cs = {0.0, 0.0, 0.0}, ce = {0.0, 0.0, 0.0};
+            const RingShared cur = own_rec(e);
+            const RingOwn own = ro[e * ros];
+            NbrRec cs = {0.0, 0.0, nullptr}, ce = {0.0, 0.0, nullptr};
             if (cur.type == 1) misses += !lookup_edge(a, cur.nbr, s, cs, ce);
             const double Gx = cur.gx + pend.gx + cs.gx, Gy = cur.gy + pend.gy + cs.gy;
             const double hx = own.hx, hy = own.hy;
@@ -218,7 +234,8 @@ __global__ void __launch_bounds__(128, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
                 // outer vertex on the bisector with j (finite_voronoi.py:653-746)
                 const bool entry = (cur.type == 1);
                 const double pjx = entry ? own.px : prev_o.px, pjy = entry ? own.py : prev_o.py;
-                const double Wj = entry ? cs.w : pend.w, Wi = cur.w;
+                const double *pwj = entry ? cs.pw : pend.pw;
+                const double Wj = pwj ? *pwj : 0.0, Wi = cur.w;
                 const double rho2 = pjx * pjx + pjy * pjy, rho = sqrt(rho2);
                 const double root = sqrt(fmax(4.0 * r2 - rho2, 0.0));
                 const double cr = pjx * hy - pjy * hx;
@@ -307,10 +324,11 @@ struct RingView {
     const int *ovf_index, *ovf_len;
     const RingShared *ovf_rs;
     const RingOwn *ovf_ro;
-    __device__ __forceinline__ int get(int s, const RingShared *&prs, const RingOwn *&pro) const {
+    size_t stride;   // RingOwn is slot-major outside the pool
+    __device__ __forceinline__ int get(int s, const RingShared *&prs, const RingOwn *&pro, size_t &ros) const {
         int E = ring_len[s];
-        prs = rs + (size_t)s * RS; pro = ro + (size_t)s * RS;
-        if (E == RING_IN_POOL) { const int pi = ovf_index[s]; E = ovf_len[pi]; prs = ovf_rs + (size_t)pi * RS_SLOW; pro = ovf_ro + (size_t)pi * RS_SLOW; }
+        prs = rs + (size_t)s * RS; pro = ro + s; ros = stride;
+        if (E == RING_IN_POOL) { const int pi = ovf_index[s]; E = ovf_len[pi]; prs = ovf_rs + (size_t)pi * RS_SLOW; pro = ovf_ro + (size_t)pi * RS_SLOW; ros = 1; }
         return E;
     }
 };
@@ -321,11 +339,11 @@ __global__ void k_conn_count(RingView rv, const int64_t *__restrict__ gid, const
     if (s >= n) return;
     int c = 0;
     if (owned[s]) {
-        const RingShared *rs; const RingOwn *ro;
-        const int E = rv.get(s, rs, ro);
+        const RingShared *rs; const RingOwn *ro; size_t ros;
+        const int E = rv.get(s, rs, ro, ros);
         const int64_t gi = gid[s];
         for (int e = 0; e < E; ++e) {
-            const int2 q = *reinterpret_cast<const int2 *>(&rs[e]);
+            const int2 q = *reinterpret_cast<const int2 *>(&rs[e].nbr);
             if (q.y == 1 && gi < gid[q.x]) ++c;
         }
     }
@@ -335,12 +353,12 @@ __global__ void k_conn_emit(RingView rv, const int64_t *__restrict__ gid, const 
                             const int *__restrict__ off, int64_t *__restrict__ pairs) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n || !owned[s]) return;
-    const RingShared *rs; const RingOwn *ro;
-    const int E = rv.get(s, rs, ro);
+    const RingShared *rs; const RingOwn *ro; size_t ros;
+    const int E = rv.get(s, rs, ro, ros);
     const int64_t gi = gid[s];
     int o = off[s];
     for (int e = 0; e < E; ++e) {
-        const int2 q = *reinterpret_cast<const int2 *>(&rs[e]);
+        const int2 q = *reinterpret_cast<const int2 *>(&rs[e].nbr);
         if (q.y == 1) {
             const int64_t gj = gid[q.x];
             if (gi < gj) { pairs[2 * (size_t)o] = gi; pairs[2 * (size_t)o + 1] = gj; ++o; }
@@ -352,20 +370,20 @@ __global__ void k_conn_emit(RingView rv, const int64_t *__restrict__ gid, const 
 __global__ void k_ring_len_by_gid(RingView rv, const int64_t *__restrict__ gid, int n, int *__restrict__ len_out) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const RingShared *rs; const RingOwn *ro;
-    len_out[gid[s]] = rv.get(s, rs, ro);
+    const RingShared *rs; const RingOwn *ro; size_t ros;
+    len_out[gid[s]] = rv.get(s, rs, ro, ros);
 }
 __global__ void k_ring_emit(RingView rv, const int64_t *__restrict__ gid, const double2 *__restrict__ xy, int n,
                             const int *__restrict__ off_by_gid, signed char *__restrict__ types, double *__restrict__ vxy) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const RingShared *rs; const RingOwn *ro;
-    const int E = rv.get(s, rs, ro);
+    const RingShared *rs; const RingOwn *ro; size_t ros;
+    const int E = rv.get(s, rs, ro, ros);
     const int o = off_by_gid[gid[s]];
     const double xi = xy[s].x, yi = xy[s].y;
     for (int e = 0; e < E; ++e) {
         types[o + e] = (signed char)rs[e].type;
-        const RingOwn q = ro[e];
+        const RingOwn q = ro[e * ros];
         vxy[2 * (size_t)(o + e)] = xi + q.hx; vxy[2 * (size_t)(o + e) + 1] = yi + q.hy;
     }
 }
