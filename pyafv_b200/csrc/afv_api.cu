@@ -58,7 +58,6 @@ struct AfvContext {
     unsigned char *ring_len = nullptr;
     int *ring_key = nullptr, *hull_slot = nullptr;
     unsigned char *hull_len = nullptr;
-    RingShared *rs = nullptr;
     RingOwn *ro = nullptr;
     RingSelf *self = nullptr;
     int *flags = nullptr;         // device: [0] slow-path cells, [1] lookup misses, [2] max ring length, [3] hard overflows
@@ -133,13 +132,13 @@ void free_all(AfvHandle h) {
     }
     cudaFree(h->keys); cudaFree(h->keys_sorted); cudaFree(h->iota); cudaFree(h->perm); cudaFree(h->bin_start);
     cudaFree(h->cub_tmp); cudaFree(h->fx); cudaFree(h->fy); cudaFree(h->area); cudaFree(h->perim); cudaFree(h->arcl);
-    cudaFree(h->coord); cudaFree(h->ring_len); cudaFree(h->rs); cudaFree(h->ro); cudaFree(h->self); h->self = nullptr; cudaFree(h->cnt); cudaFree(h->off);
+    cudaFree(h->coord); cudaFree(h->ring_len); cudaFree(h->ro); cudaFree(h->self); h->self = nullptr; cudaFree(h->cnt); cudaFree(h->off);
     cudaFree(h->ovf_index); h->ovf_index = nullptr;
     cudaFree(h->ring_key); h->ring_key = nullptr;
     cudaFree(h->hull_slot); h->hull_slot = nullptr; cudaFree(h->hull_len); h->hull_len = nullptr;
     h->keys = h->keys_sorted = nullptr; h->iota = h->perm = h->bin_start = nullptr; h->cub_tmp = nullptr;
     h->fx = h->fy = h->area = h->perim = h->arcl = nullptr; h->coord = nullptr; h->ring_len = nullptr;
-    h->rs = nullptr; h->ro = nullptr; h->cnt = h->off = nullptr;
+    h->ro = nullptr; h->cnt = h->off = nullptr;
     h->cap = 0;
 }
 
@@ -195,7 +194,6 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     if ((rc = dev_alloc(h, &h->ring_key, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->hull_slot, (size_t)cap * KHULL_STRIDE))) return rc;
     if ((rc = dev_alloc(h, &h->hull_len, cap))) return rc;
-    if ((rc = dev_alloc(h, &h->rs, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->ro, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->self, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->ovf_index, cap))) return rc;
@@ -251,7 +249,7 @@ void collect_spans(AfvHandle h) {
     h->spans.clear();
 }
 
-RingView ring_view(AfvHandle h) { return RingView{h->rs, h->ro, h->ring_len, h->ovf_index, h->ovf_len, h->ovf_rs, h->ovf_ro, (size_t)h->cap}; }
+RingView ring_view(AfvHandle h) { return RingView{h->self, h->ro, h->ring_len, h->ovf_index, h->ovf_len, h->ovf_rs, h->ovf_ro, (size_t)h->cap}; }
 
 PhysDev phys_dev(const AfvParams &p) { return PhysDev{p.r, p.P0, p.KA, p.KP, p.Lambda, p.delta}; }
 
@@ -315,7 +313,7 @@ int stage_geometry(AfvHandle h) {
     const int c = h->cur;
     GeomArgs a;
     a.xy = h->xy[c]; a.a0 = h->a0[c]; a.keys = h->keys_sorted; a.bin_start = h->bin_start; a.grid = h->d_grid;
-    a.n = n; a.ph = phys_dev(h->prm); a.rs = h->rs; a.ro = h->ro; a.self = h->self; a.stride = (size_t)h->cap; a.ring_len = h->ring_len; a.ring_key = h->ring_key; a.hull_slot = h->hull_slot; a.hull_len = h->hull_len;
+    a.n = n; a.ph = phys_dev(h->prm); a.ro = h->ro; a.self = h->self; a.stride = (size_t)h->cap; a.ring_len = h->ring_len; a.ring_key = h->ring_key; a.hull_slot = h->hull_slot; a.hull_len = h->hull_len;
     a.area = h->area; a.perim = h->perim; a.arcl = h->arcl; a.coord = h->coord; a.flags = h->flags;
     a.ovf_cells = h->ovf_cells; a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
     // candidate-list capacity per cell (shared memory scales with it): for a periodic box the mean number of cells
@@ -349,7 +347,7 @@ int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, doub
     const int n = (int)h->n;
     const int c = h->cur;
     ForceArgs a;
-    a.rs = h->rs; a.ro = h->ro; a.self = h->self; a.stride = (size_t)h->cap; a.ring_len = h->ring_len; a.ring_key = h->ring_key; a.owned = h->owned[c]; a.gid = h->gid[c]; a.n = n;
+    a.ro = h->ro; a.self = h->self; a.stride = (size_t)h->cap; a.ring_len = h->ring_len; a.ring_key = h->ring_key; a.owned = h->owned[c]; a.gid = h->gid[c]; a.n = n;
     a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
     a.ph = phys_dev(h->prm); a.fx = h->fx; a.fy = h->fy; a.flags = h->flags;
     a.do_step = do_step ? 1 : 0; a.xy = h->xy[c]; a.theta = h->th[c];

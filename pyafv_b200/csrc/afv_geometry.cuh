@@ -23,9 +23,8 @@ struct GeomArgs {
     const GridDesc *grid;
     int n;
     PhysDev ph;
-    RingShared *rs;            // [n * RS] per cell: what neighbours gather
     RingOwn *ro;               // slot-major, stride `stride`
-    RingSelf *self;            // slot-major, stride `stride`
+    RingSelf *self;            // slot-major, stride `stride`: gradient records, gathered by the neighbours in k_force
     size_t stride;             // allocated cells
     unsigned char *ring_len;
     int *hull_slot;            // [KHULL_STRIDE * stride], slot-major: polygon edges found by k_hull (neighbour slot, or -2 - v for virtual neighbour v)
@@ -159,7 +158,7 @@ __device__ __forceinline__ void finish_cell(const GeomArgs &a, const int s, cons
     }
     P += Larc;
 
-    RingShared *rs = a.rs + (size_t)s * RS;
+    RingShared *rs = nullptr;       // only pooled rings have per-cell records
     RingOwn *ro = a.ro + s;
     size_t ros = a.stride;          // RingOwn / RingSelf element stride (slot-major), 1 inside the overflow pool
     bool pooled = false;
@@ -190,11 +189,10 @@ __device__ __forceinline__ void finish_cell(const GeomArgs &a, const int s, cons
                 w = cA * 0.5 * (r2 - (hx[e] * hx[e2] + hy[e] * hy[e2])) + cL * r;
             else if (typ[e0] == 0)  // an arc ends here
                 w = -(cA * 0.5 * (r2 - (hx[e0] * hx[e] + hy[e0] * hy[e])) + cL * r);
-            RingShared o; o.nbr = nbr[e]; o.type = typ[e]; o.gx = gx; o.gy = gy; o.w = w;
-            rs[e] = o;
             RingOwn q; q.hx = hx[e]; q.hy = hy[e]; q.px = qx[e]; q.py = qy[e];
             ro[e * ros] = q;
-            if (!pooled) { RingSelf f; f.gx = gx; f.gy = gy; f.w = w; f.nbr = nbr[e]; f.type = typ[e]; a.self[e * a.stride + s] = f; }
+            if (pooled) { RingShared o; o.nbr = nbr[e]; o.type = typ[e]; o.gx = gx; o.gy = gy; o.w = w; rs[e] = o; }
+            else { RingSelf f; f.gx = gx; f.gy = gy; f.w = w; f.nbr = nbr[e]; f.type = typ[e]; a.self[e * a.stride + s] = f; }
         }
     }
     if (ringed && E <= RS) {   // the compact key row that k_force scans (entries beyond ring_len are stale)
@@ -431,7 +429,6 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     //      kernel keeps no per-thread arrays at all. ----
     const double r2 = r * r;
     const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
-    RingShared *const rs = a.rs + (size_t)s * RS;
     RingOwn *const ro = a.ro + s;                 // slot-major: entry e at ro[e * ros]
     RingSelf *const self = a.self + s;
     const size_t ros = a.stride;
@@ -586,10 +583,7 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
                     w = cA * 0.5 * (r2 - (hcx * hnx + hcy * hny)) + cL * r;
                 else if (arc_p)  // an arc ends here
                     w = -(cA * 0.5 * (r2 - (hpx * hcx + hpy * hcy)) + cL * r);
-                // final records: the neighbour-visible one (per cell) and the owner's slot-major copy
-                const int2 nt = *reinterpret_cast<const int2 *>(&self[e * ros].nbr);
-                RingShared o; o.nbr = nt.x; o.type = nt.y; o.gx = gx; o.gy = gy; o.w = w;
-                rs[e] = o;
+                // final record (nbr / type were written when the entry was closed)
                 double *dst = reinterpret_cast<double *>(&self[e * ros]);
                 dst[0] = gx; dst[1] = gy; dst[2] = w;
                 hpx = hcx; hpy = hcy; hcx = hnx; hcy = hny; hnx = hqx; hny = hqy; ilp = ilc; ilc = iln; iln = ilq;

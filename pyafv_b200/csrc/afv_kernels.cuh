@@ -117,9 +117,8 @@ __global__ void k_bin_start(const unsigned *__restrict__ keys_sorted, int n, con
 // neighbour's two records at the ends of the shared edge.  No atomics; summation order is the ring order.
 // ------------------------------------------------------------------------------------------------------
 struct ForceArgs {
-    const RingShared *rs;
     const RingOwn *ro;             // slot-major
-    const RingSelf *self;          // slot-major
+    const RingSelf *self;          // slot-major; also what the neighbours gather
     size_t stride;
     const unsigned char *ring_len;
     const int *ring_key;
@@ -153,7 +152,6 @@ __device__ __forceinline__ bool lookup_edge(const ForceArgs &a, int j, int self,
     const int4 *kj = reinterpret_cast<const int4 *>(a.ring_key + (size_t)j * RS);
     int Ej = a.ring_len[j];                       // independent of the key loads: all are in flight together
     const int4 k0 = kj[0], k1 = kj[1];
-    const RingShared *rj = a.rs + (size_t)j * RS;
     int t = -1;
     if (Ej != RING_IN_POOL) {
         unsigned match = (k0.x == self ? 1u : 0u) | (k0.y == self ? 2u : 0u) | (k0.z == self ? 4u : 0u) | (k0.w == self ? 8u : 0u) |
@@ -165,20 +163,29 @@ __device__ __forceinline__ bool lookup_edge(const ForceArgs &a, int j, int self,
         }
         match &= (1u << Ej) - 1u;                 // slots beyond the ring hold stale keys
         t = __ffs(match) - 1;
-    } else {   // pooled ring: generic scan
+        if (t >= 0) {
+            const int t1 = (t + 1 == Ej) ? 0 : t + 1;
+            const RingSelf *re = a.self + (size_t)t * a.stride + j, *rb = a.self + (size_t)t1 * a.stride + j;
+            const double2 ge = *reinterpret_cast<const double2 *>(re), gs = *reinterpret_cast<const double2 *>(rb);
+            at_end.gx = ge.x; at_end.gy = ge.y; at_end.pw = &re->w;
+            at_start.gx = gs.x; at_start.gy = gs.y; at_start.pw = &rb->w;
+            return true;
+        }
+    } else {   // pooled ring: generic scan over its per-cell records
         const int pi = a.ovf_index[j];
-        Ej = a.ovf_len[pi]; rj = a.ovf_rs + (size_t)pi * RS_SLOW;
+        Ej = a.ovf_len[pi];
+        const RingShared *rj = a.ovf_rs + (size_t)pi * RS_SLOW;
         for (int q = 0; q < Ej; ++q) {
             const int2 kt = *reinterpret_cast<const int2 *>(&rj[q].nbr);
             if (kt.x == self && kt.y == 1) { t = q; break; }
         }
-    }
-    if (t >= 0) {
-        const int t1 = (t + 1 == Ej) ? 0 : t + 1;
-        const double2 ge = *reinterpret_cast<const double2 *>(&rj[t]), gs = *reinterpret_cast<const double2 *>(&rj[t1]);
-        at_end.gx = ge.x; at_end.gy = ge.y; at_end.pw = &rj[t].w;
-        at_start.gx = gs.x; at_start.gy = gs.y; at_start.pw = &rj[t1].w;
-        return true;
+        if (t >= 0) {
+            const int t1 = (t + 1 == Ej) ? 0 : t + 1;
+            const double2 ge = *reinterpret_cast<const double2 *>(&rj[t]), gs = *reinterpret_cast<const double2 *>(&rj[t1]);
+            at_end.gx = ge.x; at_end.gy = ge.y; at_end.pw = &rj[t].w;
+            at_start.gx = gs.x; at_start.gy = gs.y; at_start.pw = &rj[t1].w;
+            return true;
+        }
     }
     at_start.gx = at_start.gy = 0.0; at_start.pw = nullptr;
     at_end.gx = at_end.gy = 0.0; at_end.pw = nullptr;
@@ -318,18 +325,22 @@ __global__ void k_gather_by_gid(const double *__restrict__ src, const int64_t *_
 
 // read-only view of all rings (regular fixed-stride storage + overflow pool)
 struct RingView {
-    const RingShared *rs;
+    const RingSelf *self;
     const RingOwn *ro;
     const unsigned char *ring_len;
     const int *ovf_index, *ovf_len;
     const RingShared *ovf_rs;
     const RingOwn *ovf_ro;
     size_t stride;   // RingOwn is slot-major outside the pool
+    // prs != nullptr: pooled ring with per-cell records; else entry e's nbr/type live in self[e * stride + s]
     __device__ __forceinline__ int get(int s, const RingShared *&prs, const RingOwn *&pro, size_t &ros) const {
         int E = ring_len[s];
-        prs = rs + (size_t)s * RS; pro = ro + s; ros = stride;
+        prs = nullptr; pro = ro + s; ros = stride;
         if (E == RING_IN_POOL) { const int pi = ovf_index[s]; E = ovf_len[pi]; prs = ovf_rs + (size_t)pi * RS_SLOW; pro = ovf_ro + (size_t)pi * RS_SLOW; ros = 1; }
         return E;
+    }
+    __device__ __forceinline__ int2 nbr_type(int s, int e, const RingShared *prs) const {
+        return prs ? *reinterpret_cast<const int2 *>(&prs[e].nbr) : *reinterpret_cast<const int2 *>(&self[(size_t)e * stride + s].nbr);
     }
 };
 
@@ -343,7 +354,7 @@ __global__ void k_conn_count(RingView rv, const int64_t *__restrict__ gid, const
         const int E = rv.get(s, rs, ro, ros);
         const int64_t gi = gid[s];
         for (int e = 0; e < E; ++e) {
-            const int2 q = *reinterpret_cast<const int2 *>(&rs[e].nbr);
+            const int2 q = rv.nbr_type(s, e, rs);
             if (q.y == 1 && gi < gid[q.x]) ++c;
         }
     }
@@ -358,7 +369,7 @@ __global__ void k_conn_emit(RingView rv, const int64_t *__restrict__ gid, const 
     const int64_t gi = gid[s];
     int o = off[s];
     for (int e = 0; e < E; ++e) {
-        const int2 q = *reinterpret_cast<const int2 *>(&rs[e].nbr);
+        const int2 q = rv.nbr_type(s, e, rs);
         if (q.y == 1) {
             const int64_t gj = gid[q.x];
             if (gi < gj) { pairs[2 * (size_t)o] = gi; pairs[2 * (size_t)o + 1] = gj; ++o; }
@@ -382,7 +393,7 @@ __global__ void k_ring_emit(RingView rv, const int64_t *__restrict__ gid, const 
     const int o = off_by_gid[gid[s]];
     const double xi = xy[s].x, yi = xy[s].y;
     for (int e = 0; e < E; ++e) {
-        types[o + e] = (signed char)rs[e].type;
+        types[o + e] = (signed char)rv.nbr_type(s, e, rs).y;
         const RingOwn q = ro[e * ros];
         vxy[2 * (size_t)(o + e)] = xi + q.hx; vxy[2 * (size_t)(o + e) + 1] = yi + q.hy;
     }
