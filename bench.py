@@ -192,10 +192,14 @@ def run_ours(args) -> dict:
     roofline = {"kernel": stage_names[dom], "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_cell_step": ALG_BYTES_PER_CELL_STEP, "kernel_ms": dom_ms,
+                "whole_step": {"achieved": ALG_BYTES_PER_CELL_STEP * total_cells / world / (ms / args.steps * 1e-3) / 1e9,
+                               "frac": ALG_BYTES_PER_CELL_STEP * total_cells / world / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                 "stage_ms_per_step": {nm: float(ms4[i] / max(args.steps, 1)) for i, nm in enumerate(stage_names)}}
     roofline_fp64 = {"kernel": stage_names[dom], "bound": "fp64", "achieved": ach_tf, "peak": float(fp64.value),
                      "unit": "TFLOP/s", "frac": ach_tf / float(fp64.value) if fp64.value else None,
-                     "alg_flop_per_cell_step": ALG_FLOP_PER_CELL_STEP, "peak_source": "DFMA micro-benchmark, this run"}
+                     "alg_flop_per_cell_step": ALG_FLOP_PER_CELL_STEP, "peak_source": "DFMA micro-benchmark, this run",
+                     "whole_step": {"achieved": ALG_FLOP_PER_CELL_STEP * total_cells / world / (ms / args.steps * 1e-3) / 1e12,
+                                    "frac": (ALG_FLOP_PER_CELL_STEP * total_cells / world / (ms / args.steps * 1e-3) / 1e12 / float(fp64.value)) if fp64.value else None}}
     traffic_file = ROOT / "profiles" / "dominant_kernel_traffic.json"
     if traffic_file.exists():
         try:
