@@ -27,7 +27,7 @@ struct GeomArgs {
     RingSelf *self;            // slot-major, stride `stride`: gradient records, gathered by the neighbours in k_force
     size_t stride;             // allocated cells
     unsigned char *ring_len;
-    int *hull_slot;            // [KHULL_STRIDE * stride], slot-major: polygon edges found by k_hull (neighbour slot, or -2 - v for virtual neighbour v)
+    int *hull_slot;            // [KHULL_STRIDE * stride], slot-major: polygon edges found by k_hull (neighbour slot, or -2 for the edge at infinity)
     unsigned char *hull_len;   // [n] number of polygon edges; HULL_QUEUED when the cell went to the slow path
     int *ring_key;             // [n * RS] neighbour slot of every ring entry (ARC for arcs; stale beyond ring_len): what k_force scans
     double *area, *perim, *arcl;
@@ -300,20 +300,23 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_hull(GeomArgs a, 
             }
         }
     }
-    // displacement of list entry c (c >= n: virtual neighbour c - n)
+    // displacement of list entry c.  Entry n is the ORIGIN of the dual plane, homogeneous (p, k) = ((0,0), 1): the
+    // "half-plane at infinity".  It becomes a hull vertex exactly when the neighbours do not surround the cell, i.e.
+    // when the Voronoi polygon is unbounded; the two polygon edges next to it then run off to infinity.
     auto disp = [&](int c, double &dx, double &dy) {
+        dx = 0.0; dy = 0.0;
         if (c < n) {
             const double2 pc = a.xy[s_idx[c * HULL_TPB + tid]];
             dx = pc.x - xi; dy = pc.y - yi;
             if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
             if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
-        } else virtual_nbr(c - n, B4, dx, dy);
+        }
     };
 
     // ---- gift wrapping in the dual plane.  Candidate c <-> homogeneous dual point (p_c, k_c), k_c = |p_c|^2 / 2.
     //      orient(a, b, c) = sign((p_b k_a - p_a k_b) x (p_c k_a - p_a k_c));  the nearest neighbour is on the hull.
     //      Two independent running-best chains (even / odd list entries) halve the dependent latency. ----
-    unsigned long long hull_lo = 0ull, hull_hi = 0ull;   // 16 x 8-bit list indices (n..n+3 = virtual)
+    unsigned long long hull_lo = 0ull, hull_hi = 0ull;   // 16 x 8-bit list indices (n = the origin)
     int m = 0;
     const bool wrap = live && ok && n > 0;
     const int npair_max = (__reduce_max_sync(FULL_MASK, wrap ? n : 0) + 1) >> 1;
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_hull(GeomArgs a, 
             if (m < 8) hull_lo |= (unsigned long long)cur << (8 * m); else hull_hi |= (unsigned long long)cur << (8 * (m - 8));
             ++m;
             disp(cur, pax, pay);
-            ka = 0.5 * (pax * pax + pay * pay);
+            ka = (cur < n) ? 0.5 * (pax * pax + pay * pay) : 1.0;
         }
         int best0 = -1, best1 = -1;
         double u0x = 0.0, u0y = 0.0, u1x = 0.0, u1y = 0.0;
@@ -344,21 +347,29 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_hull(GeomArgs a, 
                 if (best1 < 0 || u1x * wy - u1y * wx < 0.0) { best1 = cb; u1x = wx; u1y = wy; }
             }
         }
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {     // the four virtual neighbours, two per chain
-            if (!done && n + v != cur) {
-                double qx_, qy_;
-                virtual_nbr(v, B4, qx_, qy_);
-                const double kc = 0.5 * B4 * B4;
-                const double wx = qx_ * ka - pax * kc, wy = qy_ * ka - pay * kc;
-                if (v & 1) { if (best1 < 0 || u1x * wy - u1y * wx < 0.0) { best1 = n + v; u1x = wx; u1y = wy; } }
-                else       { if (best0 < 0 || u0x * wy - u0y * wx < 0.0) { best0 = n + v; u0x = wx; u0y = wy; } }
-            }
-        }
         if (!done) {
             // merge the chains: the overall next hull vertex is the one with every other point on its left
             int best = best0;
-            if (best0 < 0 || (best1 >= 0 && u0x * u1y - u0y * u1x < 0.0)) best = best1;
+            double ux = u0x, uy = u0y;
+            if (best0 < 0 || (best1 >= 0 && u0x * u1y - u0y * u1x < 0.0)) { best = best1; ux = u1x; uy = u1y; }
+            // the origin (p, k) = ((0,0), 1): w = 0 * k_a - p_a * 1.  An exact tie means q_a, the origin and the best
+            // neighbour are collinear (e.g. collinear cells): the farther point wins, as in any gift wrapping;
+            // |q_c - q_a| = |w_c| / (k_a k_c).
+            if (cur != n) {
+                const double wx = -pax, wy = -pay;
+                bool take = best < 0;
+                if (!take) {
+                    const double cr = ux * wy - uy * wx;
+                    if (cr < 0.0) take = true;
+                    else if (cr == 0.0) {
+                        double bx_, by_;
+                        disp(best, bx_, by_);
+                        const double kb = 0.5 * (bx_ * bx_ + by_ * by_);
+                        take = (wx * wx + wy * wy) * kb * kb > (ux * ux + uy * uy);
+                    }
+                }
+                if (take) best = n;
+            }
             cur = best;
             if (cur == imin) done = true;
             else if (m >= KHULL) { ok = false; done = true; }
@@ -377,7 +388,7 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_hull(GeomArgs a, 
             int *hs = a.hull_slot + s;                       // slot-major: edge k at hs[k * stride]
             for (int k = 0; k < mm; ++k) {
                 const int h = (int)(((k < 8) ? (hull_lo >> (8 * k)) : (hull_hi >> (8 * (k - 8)))) & 0xffull);
-                hs[k * a.stride] = (h < n) ? s_idx[h * HULL_TPB + tid] : -2 - (h - n);
+                hs[k * a.stride] = (h < n) ? s_idx[h * HULL_TPB + tid] : -2;   // -2: the edge at infinity
             }
         }
     }
@@ -419,7 +430,7 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
             dx = pc.x - xi; dy = pc.y - yi;
             if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
             if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
-        } else virtual_nbr(-2 - slot, B4, dx, dy);
+        } else { dx = 0.0; dy = 0.0; }
     };
 
     // ---- ring, streamed.  The polygon edges are the hull vertices h_0..h_{m-1} (counter-clockwise); the ring is
@@ -435,11 +446,22 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     int *const key = a.ring_key + (size_t)s * RS;
     const int mm = m;
     const int mloop = __reduce_max_sync(FULL_MASK, mm);
-    auto isect = [](double ax, double ay, double bx_, double by_, double &x, double &y) {
-        const double ca = 0.5 * (ax * ax + ay * ay), cb = 0.5 * (bx_ * bx_ + by_ * by_);
-        const double idet = __drcp_rn(ax * by_ - ay * bx_);
-        x = (ca * by_ - cb * ay) * idet;
-        y = (ax * cb - bx_ * ca) * idet;
+    // Junction between the counter-clockwise consecutive polygon edges A (slot ja, displacement a) and B (jb, b):
+    // the END of A and the START of B.  Normally one point, the intersection of the two bisectors (a proper left
+    // turn, a x b > 0).  Next to the edge at infinity -- or for a degenerate turn -- the bisector runs off to
+    // infinity instead: a point 4r along it stands in (it only has to lie outside the disk).
+    auto junction = [&](int ja, double ax, double ay, int jb, double bx_, double by_, double &eax, double &eay, double &sbx, double &sby) {
+        const double det = ax * by_ - ay * bx_;
+        if (ja >= 0 && jb >= 0 && det > 0.0) {
+            const double ca = 0.5 * (ax * ax + ay * ay), cb = 0.5 * (bx_ * bx_ + by_ * by_);
+            const double idet = __drcp_rn(det);
+            eax = sbx = (ca * by_ - cb * ay) * idet;
+            eay = sby = (ax * cb - bx_ * ca) * idet;
+        } else {
+            eax = eay = sbx = sby = 0.0;
+            if (ja >= 0) { const double f = B4 * rsqrt(ax * ax + ay * ay); eax = 0.5 * ax - f * ay; eay = 0.5 * ay + f * ax; }      // C_A + 4r ccw(A)
+            if (jb >= 0) { const double f = B4 * rsqrt(bx_ * bx_ + by_ * by_); sbx = 0.5 * bx_ + f * by_; sby = 0.5 * by_ - f * bx_; } // C_B - 4r ccw(B)
+        }
     };
     int E = 0, z = 0;
     unsigned arcmask = 0u;                       // bit e set: ring entry e starts an arc
@@ -479,19 +501,20 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     }
     {
         double pcx = 0.0, pcy = 0.0, pnx = 0.0, pny = 0.0, V1x = 0.0, V1y = 0.0;
-        int jc = -2, jtmp;
+        int jc = -2, jn = -2;
         if (mm > 0) {
+            double tx, ty;
             disp(mm - 1, pcx, pcy, jc);
-            disp(0, pnx, pny, jtmp);
-            isect(pcx, pcy, pnx, pny, V1x, V1y);           // vertex m = vertex 0 = edge(m-1) ^ edge(0)
+            disp(0, pnx, pny, jn);
+            junction(jc, pcx, pcy, jn, pnx, pny, V1x, V1y, tx, ty);   // end of edge m-1 (junction with edge 0)
         }
         for (int kk = 0; kk < mloop; ++kk) {
             if (kk < mm) {
                 const int k = mm - 1 - kk;
-                double ppx, ppy, V2x, V2y;
+                double ppx, ppy, V2x, V2y, Enx, Eny;
                 int jp;
                 disp(k == 0 ? mm - 1 : k - 1, ppx, ppy, jp);
-                isect(ppx, ppy, pcx, pcy, V2x, V2y);       // vertex k = edge(k-1) ^ edge(k)
+                junction(jp, ppx, ppy, jc, pcx, pcy, Enx, Eny, V2x, V2y);   // end of edge k-1, start of edge k
                 if (jc >= 0 && ok) {                       // a real neighbour (virtual edges emit nothing)
                     const int j = jc;
                     if (V1x * V1x + V1y * V1y <= r2) emit(V1x, V1y, pcx, pcy, j);      // inner start vertex, d1 <= r
@@ -505,7 +528,7 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
                         if (tr < t2 && tr > t1) emit(0.5 * pcx + tr * ux, 0.5 * pcy + tr * uy, pcx, pcy, ARC);  // exit point
                     }
                 }
-                pcx = ppx; pcy = ppy; jc = jp; V1x = V2x; V1y = V2y;
+                pcx = ppx; pcy = ppy; jc = jp; V1x = Enx; V1y = Eny;
             }
         }
     }
