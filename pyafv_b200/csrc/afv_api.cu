@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -450,6 +451,7 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
     }
     cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream);
     cudaFuncSetAttribute(k_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(int));
+
     *out = h;
     return AFV_OK;
 }
