@@ -137,6 +137,10 @@ int afv_measure_fp64_peak(AfvHandle h, double *tflops_out);
 void *afv_device_ptr(AfvHandle h, int field);
 void *afv_stream(AfvHandle h);
 int afv_synchronize(AfvHandle h);
+/* Deferred checks (sharded time loops): afv_step returns without synchronising with the host; capacity errors of the
+ * steps issued since are reported by the next afv_finish_exchange or afv_synchronize, which synchronise anyway.  Not
+ * used when afv_step borrows a host noise array. */
+int afv_set_deferred_checks(AfvHandle h, int enabled);
 /* Turn a periodic handle (box_L > 0) into one x-slab of that box: the bin grid covers x in [grid_x0, grid_x1)
  * without wrap (the caller supplies halo cells with x already shifted by +-L where the slab touches the box
  * face), y stays periodic, and afv_step no longer wraps x (cells leaving the slab are migrated by the caller). */

@@ -20,7 +20,7 @@ SYMBOLS = [
     "afv_get_positions", "afv_get_theta", "afv_get_forces", "afv_get_areas", "afv_get_perimeters", "afv_get_arclens",
     "afv_get_coord_nums", "afv_get_num_connections", "afv_get_connections", "afv_get_num_ring_entries", "afv_get_rings",
     "afv_get_diagnostics", "afv_set_profiling", "afv_get_stage_times", "afv_launch_count", "afv_host_alloc",
-    "afv_host_free", "afv_measure_fp64_peak", "afv_device_ptr", "afv_stream", "afv_synchronize",
+    "afv_host_free", "afv_measure_fp64_peak", "afv_device_ptr", "afv_stream", "afv_synchronize", "afv_set_deferred_checks",
     "afv_set_slab", "afv_set_cells_device", "afv_extract_slab", "afv_drop_halo", "afv_append_cells", "afv_num_owned", "afv_pack_owned", "afv_pack_pair", "afv_finish_pair", "afv_pack_exchange", "afv_finish_exchange",
 ]
 
@@ -83,6 +83,7 @@ def load() -> C.CDLL:
         "afv_device_ptr": (P, [H, C.c_int]),
         "afv_stream": (P, [H]),
         "afv_synchronize": (C.c_int, [H]),
+        "afv_set_deferred_checks": (C.c_int, [H, C.c_int]),
         "afv_set_slab": (C.c_int, [H, D, D]),
         "afv_set_cells_device": (C.c_int, [H, P, I64, I64]),
         "afv_extract_slab": (C.c_int, [H, D, D, D, C.c_int, P, I64, C.POINTER(I64)]),

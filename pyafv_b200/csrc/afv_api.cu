@@ -72,6 +72,7 @@ struct AfvContext {
     int64_t n_conn = -1, n_ring = -1;
     bool built = false;
     int cmax_hint = 32;
+    bool defer_checks = false;  // afv_step returns without synchronising; the flags are read at the next exchange / synchronize
     // pair exchange state (afv_pack_pair -> afv_finish_pair)
     int *pair_cnt = nullptr;       // device [2]
     double *pair_host = nullptr;   // pinned [4]
@@ -445,8 +446,8 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
         cudaMalloc((void **)&h->ovf_ro, (size_t)OVF_MAX * RS_SLOW * sizeof(RingOwn)) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
-    if (cudaMalloc((void **)&h->pair_cnt, 4 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 8 * sizeof(double)) != cudaSuccess ||
-        cudaHostAlloc((void **)&h->pair_host, 8 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaMalloc((void **)&h->pair_cnt, 4 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 12 * sizeof(double)) != cudaSuccess ||
+        cudaHostAlloc((void **)&h->pair_host, 12 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
     cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream);
@@ -604,13 +605,15 @@ int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t s
         CK(cudaMemcpyAsync(h->noise_buf.p, noise_host, bytes, cudaMemcpyHostToDevice, h->stream));
         noise_dev = (const double *)h->noise_buf.p;
     }
-    CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
+    const bool deferred = h->defer_checks && !noise_host;
+    if (!deferred) CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
     for (int s = 0; s < n_steps; ++s) {
+        if (deferred) CK(cudaMemsetAsync(h->flags, 0, sizeof(int), h->stream));   // the slow-path queue restarts every step
         if ((rc = stage_sort(h))) return rc;
         if ((rc = stage_geometry(h))) return rc;
         if ((rc = stage_force(h, true, dt, mu, v0, Dr, seed, step0 + s, noise_dev ? noise_dev + (size_t)s * h->n : nullptr))) return rc;
     }
-    if ((rc = check_flags(h))) return rc;   // also synchronises: noise_host is borrowed for the call only
+    if (!deferred && (rc = check_flags(h))) return rc;   // also synchronises: noise_host is borrowed for the call only
     h->built = true;
     h->n_conn = -1; h->n_ring = -1;
     return AFV_OK;
@@ -792,7 +795,14 @@ void *afv_stream(AfvHandle h) { return h ? (void *)h->stream : nullptr; }
 
 int afv_synchronize(AfvHandle h) {
     CHECK_H(h);
+    if (h->defer_checks) return check_flags(h);   // synchronises and reports deferred capacity errors
     CK(cudaStreamSynchronize(h->stream));
+    return AFV_OK;
+}
+
+int afv_set_deferred_checks(AfvHandle h, int enabled) {
+    CHECK_H(h);
+    h->defer_checks = enabled != 0;
     return AFV_OK;
 }
 

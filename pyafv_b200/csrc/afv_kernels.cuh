@@ -457,9 +457,10 @@ __global__ void k_disown_outside(const double2 *__restrict__ xy, unsigned char *
     if (owned[i] && (xv < lo || xv >= hi)) owned[i] = 0;
 }
 __global__ void k_gather_counts8(const int *__restrict__ c, const double *__restrict__ in0, const double *__restrict__ in1,
-                                 double *__restrict__ out) {
+                                 const int *__restrict__ flags, double *__restrict__ out) {
     out[0] = (double)c[0]; out[1] = (double)c[1]; out[2] = (double)c[2]; out[3] = (double)c[3];
     out[4] = in0 ? in0[0] : 0.0; out[5] = in0 ? in0[1] : 0.0; out[6] = in1 ? in1[0] : 0.0; out[7] = in1 ? in1[1] : 0.0;
+    out[8] = (double)flags[0]; out[9] = (double)flags[1]; out[10] = (double)flags[2]; out[11] = (double)flags[3];
 }
 // keep = !(owned && x in either range)
 __global__ void k_flag_keep2(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, double lo0, double hi0,

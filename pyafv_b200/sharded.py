@@ -240,6 +240,7 @@ class SlabShardedSimulator:
         self._h = _lib.Handle(_as_params(phys), self.L, device=device, stream=stream)
         if world > 1:
             self._h.call("afv_set_slab", self.geo.grid_x0, self.geo.grid_x1)
+            self._h.call("afv_set_deferred_checks", 1)    # one host synchronisation per step (at the exchange), not two
         self.store = GpuCellStore(self._h, self.device)
         self.comm = comm if comm is not None else (TorchDistComm(rank, world) if world > 1 else None)
         pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
