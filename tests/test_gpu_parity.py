@@ -220,3 +220,88 @@ def test_parallel_simulator_equals_serial():
     assert set(d["diag_plot"][0]) == {"vertices", "edges_type", "regions"}
     d2 = afv.ParallelFiniteVoronoiSimulator(g["pts"], phys).build()
     assert d2["connections"].shape == (0, 2) and d2["plot_mode"] is False
+
+
+def test_c_abi_error_paths():
+    """Negative return codes + afv_last_error instead of exceptions across the ABI; state checks."""
+    import ctypes as C
+    import pyafv_b200 as afv
+    from pyafv_b200 import _lib
+    from pyafv_b200._lib import AfvError
+    lib = _lib.load()
+    h = C.c_void_p()
+    p = _lib.AfvParams(1.0, np.pi, 4.8, 1.0, 1.0, 0.2, 0.45)
+    assert lib.afv_create(0, C.byref(p), 3.0, None, C.byref(h)) == _lib.AFV_ERR_ARG          # periodic box < 4 r
+    assert b"4 r" in lib.afv_last_error(None)
+    assert lib.afv_create(99, C.byref(p), 0.0, None, C.byref(h)) == _lib.AFV_ERR_ARG         # no such device
+    bad = _lib.AfvParams(-1.0, np.pi, 4.8, 1.0, 1.0, 0.2, 0.45)
+    assert lib.afv_create(0, C.byref(bad), 0.0, None, C.byref(h)) == _lib.AFV_ERR_ARG
+    sim = afv.FiniteVoronoiSimulator(np.random.default_rng(0).random((50, 2)) * 5, afv.PhysicalParams())
+    out = np.zeros((50, 2))
+    assert lib.afv_get_forces(sim._h._h, out.ctypes.data) == _lib.AFV_ERR_STATE              # getter before build
+    assert b"afv_build" in lib.afv_last_error(sim._h._h)
+    k = C.c_int64()
+    sim.build(connect=False, rings=False)
+    assert lib.afv_get_num_connections(sim._h._h, C.byref(k)) == _lib.AFV_ERR_STATE           # connect was not requested
+    with pytest.raises(ValueError, match=r"A0 must be scalar or have shape \(50,\)"):
+        sim.update_preferred_areas(np.ones(49))
+    with pytest.raises(ValueError, match="noise must have shape"):
+        sim.step(0.01, noise=np.zeros((3, 7)), n_steps=3)
+    with pytest.raises(AfvError):
+        afv.FiniteVoronoiSimulator(np.zeros((3, 2)), afv.PhysicalParams(r=2.0), periodic=5.0)
+    sim.close()
+
+
+def test_update_semantics_follow_the_reference():
+    """finite_voronoi.py:1153-1240: N change resets A0; update_params resets A0; update_positions snapshots its input."""
+    import pyafv_b200 as afv
+    from afv_oracle import oracle_build
+    rng = np.random.default_rng(3)
+    pts = rng.random((300, 2)) * 14
+    A0 = np.pi * (1 + 0.3 * rng.random(300))
+    sim = afv.FiniteVoronoiSimulator(pts, afv.PhysicalParams())
+    sim.update_preferred_areas(A0)
+    d1 = sim.build()
+    _close(d1["forces"], oracle_build(pts, A0=A0)["forces"], "forces with A0")
+    work = pts.copy()
+    sim.update_positions(work)
+    work += 100.0                                  # the caller mutates its array after the call (examples/relaxation.py:44-45)
+    _close(sim.build()["forces"], d1["forces"], "snapshot at update_positions")
+    assert np.array_equal(sim.preferred_areas, A0) and sim.preferred_areas is not sim._preferred_areas
+    sim.update_params(sim.phys.replace(KA=2.0))    # resets every A0 to phys.A0
+    assert np.allclose(sim.preferred_areas, np.pi)
+    _close(sim.build()["forces"], oracle_build(pts, KA=2.0)["forces"], "after update_params")
+    sim.update_positions(pts[:120])                # N changes: A0 back to default, results sized to the new N
+    d3 = sim.build()
+    assert d3["forces"].shape == (120, 2) and len(d3["regions"]) == 120
+    _close(d3["forces"], oracle_build(pts[:120], KA=2.0)["forces"], "after N change")
+    sim.update_positions(pts, A0)                  # N changes again, A0 given
+    _close(sim.build()["forces"], oracle_build(pts, A0=A0, KA=2.0)["forces"], "A0 passed with new N")
+    sim.close()
+
+
+def test_step_matches_host_euler_with_philox_noise():
+    """step() == build + host Euler update with the same (host-evaluated) Philox noise, 5 steps, theta included."""
+    import ctypes as C
+    import pyafv_b200 as afv
+    from pyafv_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    N, L = 500, 30.0
+    pts = rng.random((N, 2)) * L
+    theta = 2 * np.pi * rng.random(N) - np.pi
+    phys = afv.PhysicalParams(seed=11)
+    a = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
+    a.step(0.002, 1.0, 1.5, 0.4, theta=theta, n_steps=5)          # seed from phys.seed
+    b = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
+    p, th = pts.copy(), theta.copy()
+    for s in range(5):
+        b.update_positions(p)
+        F = b.build(connect=False, rings=False)["forces"]
+        xi = np.array([lib.afv_philox_normal(C.c_uint64(11), C.c_int64(i), C.c_int64(s)) for i in range(N)])
+        p = np.mod(p + (1.0 * F + 1.5 * np.column_stack((np.cos(th), np.sin(th)))) * 0.002, L)
+        th = th + np.sqrt(2 * 0.4 * 0.002) * xi
+    d = a.pts - p
+    d -= L * np.round(d / L)
+    assert np.abs(d).max() < 1e-10 and np.abs(a.theta - th).max() < 1e-12
+    a.close(); b.close()
