@@ -244,7 +244,7 @@ __device__ __forceinline__ int cell_rows(const GridDesc &g, int by, int (&rows)[
 // ------------------------------------------------------------------------------------------------------
 constexpr int HULL_TPB = 128;
 constexpr int KHULL = 16;        // hull vertices (= polygon edges) on the fast path
-constexpr int CMAX_HARD = 64;    // upper bound of the per-cell candidate list (the launch picks cmax <= this)
+constexpr int CMAX_HARD = 128;   // upper bound of the per-cell candidate list (the launch picks cmax <= this); < 255 (8-bit hull indices)
 
 __device__ __forceinline__ void virtual_nbr(int v, double B4, double &x, double &y) {
     // four virtual neighbours at distance 4r whose bisectors are the sides of the bounding square of half side 2r

@@ -305,3 +305,42 @@ def test_step_matches_host_euler_with_philox_noise():
     d -= L * np.round(d / L)
     assert np.abs(d).max() < 1e-10 and np.abs(a.theta - th).max() < 1e-12
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("N,L,periodic", [(0, 10.0, False), (1, 10.0, True), (2, 10.0, True), (30, 4.5, True), (60, 5.9, True),
+                                          (200, 8.1, True), (3, 50.0, False)])
+def test_tiny_and_small_box_cases(N, L, periodic):
+    """Degenerate sizes and periodic boxes with only 2-4 bins per side (minimum-image candidate search)."""
+    import pyafv_b200 as afv
+    from afv_oracle import oracle_build
+    rng = np.random.default_rng(100 + N)
+    pts = rng.random((N, 2)) * L
+    sim = afv.FiniteVoronoiSimulator(pts, afv.PhysicalParams(), periodic=L if periodic else None)
+    d = sim.build()
+    assert d["forces"].shape == (N, 2) and d["coord_nums"].shape == (N,) and len(d["regions"]) == N
+    if N:
+        o = oracle_build(pts, periodic=L if periodic else None)
+        for k in ("areas", "perimeters", "arclens", "forces"):
+            _close(d[k], o[k], k)
+        assert np.array_equal(d["coord_nums"], o["coord_nums"]) and np.array_equal(d["connections"], o["connections"])
+    sim.step(0.01, 1.0, 1.0, 0.1, n_steps=2)
+    assert sim.pts.shape == (N, 2)
+    sim.close()
+
+
+@pytest.mark.parametrize("dens", [2.5, 4.0])
+def test_high_density_uses_longer_candidate_lists(dens):
+    """Compressed tissue: 30-50 cells within 2 l of every cell; the candidate-list capacity adapts, nothing is dropped."""
+    import pyafv_b200 as afv
+    from afv_oracle import oracle_build
+    N = 20000
+    L = float(np.sqrt(N / dens))
+    pts = np.random.default_rng(17).random((N, 2)) * L
+    sim = afv.FiniteVoronoiSimulator(pts, afv.PhysicalParams(), periodic=L)
+    d = sim.build(rings=False)
+    o = oracle_build(pts, periodic=L)
+    for k in ("areas", "perimeters", "arclens", "forces"):
+        _close(d[k], o[k], k)
+    assert np.array_equal(d["coord_nums"], o["coord_nums"]) and np.array_equal(d["connections"], o["connections"])
+    assert sim.diagnostics()["slow_path_cells"] < N // 100 and sim.diagnostics()["lookup_misses"] == 0
+    sim.close()
