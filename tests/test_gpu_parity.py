@@ -344,3 +344,44 @@ def test_high_density_uses_longer_candidate_lists(dens):
     assert np.array_equal(d["coord_nums"], o["coord_nums"]) and np.array_equal(d["connections"], o["connections"])
     assert sim.diagnostics()["slow_path_cells"] < N // 100 and sim.diagnostics()["lookup_misses"] == 0
     sim.close()
+
+
+def test_long_runs_of_the_baseline_configs_stay_consistent():
+    """BASELINE configs [1] and [2] in miniature: an open active blob (free medium interface) and a periodic jammed
+    hex sheet with per-cell A0, thousands of fused steps: finite state, no unmatched ring look-ups, net force ~ 0, and
+    the relaxation lowers the force scale; the final state still agrees with the CPU oracle."""
+    import pyafv_b200 as afv
+    from afv_oracle import oracle_build
+    rng = np.random.default_rng(42)
+    phys = afv.PhysicalParams()
+    # config [1]: examples/active_FV.py with N = 1000 (blob of density ~1.8), 200 relaxation + 2000 active steps
+    pts = (rng.random((1000, 2)) * 0.3 + 0.35) * 25.0 * np.sqrt(10.0)
+    sim = afv.FiniteVoronoiSimulator(pts, phys)
+    sim.step(0.01, 1.0, 0.0, 0.0, n_steps=200)
+    sim.step(0.01, 1.0, 2.4, 0.3, theta=2 * np.pi * rng.random(1000) - np.pi, seed=42, n_steps=2000)
+    p = sim.pts
+    assert np.isfinite(p).all() and np.isfinite(sim.theta).all()
+    d = sim.build()
+    o = oracle_build(p)
+    _close(d["forces"], o["forces"], "forces after 2200 steps")
+    assert np.array_equal(d["coord_nums"], o["coord_nums"]) and sim.diagnostics()["lookup_misses"] == 0
+    assert np.abs(d["forces"].sum(axis=0)).max() < 1e-9 * max(1.0, np.abs(d["forces"]).sum())
+    sim.close()
+    # config [2]: periodic hex sheet 97 x 112 (N = 10864), a = 1.5197, jitter 0.05, A0 = 2 (1 + 0.1 N(0,1)) >= 0.4
+    ncol, nrow, a = 97, 112, 1.5197
+    L = ncol * a
+    ii, jj = np.meshgrid(np.arange(ncol), np.arange(nrow), indexing="ij")
+    pts = np.stack([((ii + 0.5 * (jj % 2)) * a).ravel(), (jj * (L / nrow)).ravel()], axis=1)
+    pts = np.mod(pts + 0.05 * np.random.default_rng(3).standard_normal(pts.shape), L)
+    A0 = np.maximum(2.0 * (1 + 0.1 * np.random.default_rng(4).standard_normal(len(pts))), 0.4)
+    sim = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
+    sim.update_preferred_areas(A0)
+    f0 = np.abs(sim.build(connect=False, rings=False)["forces"]).max()
+    sim.step(0.01, 1.0, 0.0, 0.0, n_steps=1500)
+    d = sim.build(connect=False, rings=False)
+    assert np.abs(d["forces"]).max() < 0.2 * f0 and sim.diagnostics()["lookup_misses"] == 0
+    o = oracle_build(sim.pts, A0=A0, periodic=L)
+    _close(d["forces"], o["forces"], "forces after relaxation")
+    _close(d["areas"], o["areas"], "areas after relaxation")
+    assert np.array_equal(d["coord_nums"], o["coord_nums"])
+    sim.close()
