@@ -404,7 +404,7 @@ extern "C" {
 
 const char *afv_build_info(void) {
     static char buf[160];
-    snprintf(buf, sizeof buf, "afv_b200 sm_100a; ring_stride=%d; polygon_capacity=%d; cuda_runtime=%d", RS, KPOLY, CUDART_VERSION);
+    snprintf(buf, sizeof buf, "afv_b200 sm_100a; ring_stride=%d; hull_capacity=%d; slow_path=%d/%d; cuda_runtime=%d", RS, KHULL, KPOLY_SLOW, RS_SLOW, CUDART_VERSION);
     return buf;
 }
 

@@ -6,7 +6,6 @@
 namespace afv {
 
 constexpr int RS = 16;      // ring stride: ring entries stored per cell on the fast path
-constexpr int KPOLY = 20;   // clip-polygon capacity per cell on the fast path
 constexpr int ARC = -1;     // neighbour label of an arc edge
 constexpr int RS_SLOW = 96;       // ring capacity of the slow path (pooled rings)
 constexpr int KPOLY_SLOW = 96;    // clip-polygon capacity of the slow path

@@ -246,12 +246,6 @@ constexpr int HULL_TPB = 128;
 constexpr int KHULL = 16;        // hull vertices (= polygon edges) on the fast path
 constexpr int CMAX_HARD = 128;   // upper bound of the per-cell candidate list (the launch picks cmax <= this); < 255 (8-bit hull indices)
 
-__device__ __forceinline__ void virtual_nbr(int v, double B4, double &x, double &y) {
-    // four virtual neighbours at distance 4r whose bisectors are the sides of the bounding square of half side 2r
-    x = (v == 1) ? B4 : ((v == 3) ? -B4 : 0.0);
-    y = (v == 0) ? -B4 : ((v == 2) ? B4 : 0.0);
-}
-
 #ifndef HULL_MIN_BLOCKS
 #define HULL_MIN_BLOCKS 10
 #endif
@@ -260,7 +254,7 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_hull(GeomArgs a, 
     const int tid = threadIdx.x;
     const int s = blockIdx.x * HULL_TPB + tid;
     const bool live = s < a.n;
-    const double r = a.ph.r, cut2 = 4.0 * r * r, B4 = 4.0 * r;
+    const double r = a.ph.r, cut2 = 4.0 * r * r;
     const GridDesc g = *a.grid;
     int n = 0, imin = 0;
     bool ok = true;

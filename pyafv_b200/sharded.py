@@ -19,7 +19,6 @@ exercised without GPUs: a *cell store* (``GpuCellStore`` over the C-ABI handle; 
 from __future__ import annotations
 
 import ctypes as C
-import math
 
 import numpy as np
 import torch
@@ -74,16 +73,6 @@ class GpuCellStore:
     def drop_halo(self) -> None:
         self.h.call("afv_drop_halo")
 
-    def pack_pair(self, r0, r1, cap: int, key: str):
-        """Two messages (cap+1, ROW) with a device-written header row; no host synchronisation."""
-        m0, m1 = self._msg(key + "0", cap), self._msg(key + "1", cap)
-        self.h.call("afv_pack_pair", float(r0[0]), float(r0[1]), float(r0[2]), float(r1[0]), float(r1[1]), float(r1[2]),
-                    m0.data_ptr(), m1.data_ptr(), int(cap))
-        return m0, m1
-
-    def finish_pair(self, in0: torch.Tensor, in1: torch.Tensor, cap: int, is_halo: bool, remove_packed: bool) -> None:
-        self.h.call("afv_finish_pair", in0.data_ptr(), in1.data_ptr(), int(cap), 1 if is_halo else 0, 1 if remove_packed else 0)
-
     def pack_exchange(self, geo, cap: int):
         """(to_left, to_right) messages carrying ownership transfers + halo rows; no host synchronisation."""
         ml, mr = self._msg("xl", cap), self._msg("xr", cap)
@@ -117,36 +106,6 @@ class TorchDistComm:
     def __init__(self, rank: int, world: int):
         self.rank, self.world = rank, world
         self.left, self.right = (rank - 1) % world, (rank + 1) % world
-
-    def exchange(self, to_left: torch.Tensor, to_right: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-        """Send ``to_left`` / ``to_right`` (k,W) to the two neighbours; return what they sent us."""
-        import torch.distributed as dist
-        dev, width = to_left.device, to_left.shape[1]
-        cnt_out = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=dev)
-        cnt_in = torch.zeros(2, dtype=torch.int64, device=dev)   # [from_left, from_right]
-        # a message to the left arrives as the right neighbour's "from right" ... on 2 ranks both neighbours
-        # coincide, so the two directions are separated by tags / order within one batch
-        ops = [dist.P2POp(dist.isend, cnt_out[0:1], self.left, tag=1), dist.P2POp(dist.isend, cnt_out[1:2], self.right, tag=2),
-               dist.P2POp(dist.irecv, cnt_in[1:2], self.right, tag=1), dist.P2POp(dist.irecv, cnt_in[0:1], self.left, tag=2)]
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        n_l, n_r = (int(v) for v in cnt_in.tolist())
-        from_left = torch.empty((n_l, width), dtype=to_left.dtype, device=dev)
-        from_right = torch.empty((n_r, width), dtype=to_left.dtype, device=dev)
-        ops = []
-        if to_left.shape[0]:
-            ops.append(dist.P2POp(dist.isend, to_left.contiguous(), self.left, tag=3))
-        if to_right.shape[0]:
-            ops.append(dist.P2POp(dist.isend, to_right.contiguous(), self.right, tag=4))
-        if n_r:
-            ops.append(dist.P2POp(dist.irecv, from_right, self.right, tag=3))
-        if n_l:
-            ops.append(dist.P2POp(dist.irecv, from_left, self.left, tag=4))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        return from_left, from_right
-
 
     def exchange_fixed(self, to_left: torch.Tensor, to_right: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         """Fixed-capacity messages (header row carries the count): one batch of two sends and two receives."""
@@ -190,24 +149,9 @@ class SlabGeometry:
         self.grid_x0, self.grid_x1 = self.lo - self.halo - pad, self.hi + self.halo + pad
 
 
-def halo_ranges(geo: SlabGeometry):
-    """(lo, hi, shift) of the owned cells each neighbour needs as halo: [left message, right message].  The ranges
-    are open towards the outside so that a cell that drifted past the face before migrating is still sent."""
-    return (-math.inf, geo.lo + geo.halo, geo.shift_to_left), (geo.hi - geo.halo, math.inf, geo.shift_to_right)
-
-
-def migrant_ranges(geo: SlabGeometry):
-    """(lo, hi, shift) of the owned cells that left the slab."""
-    return (-math.inf, geo.lo, geo.shift_to_left), (geo.hi, math.inf, geo.shift_to_right)
-
-
 def halo_capacity(n_owned: int, geo: SlabGeometry) -> int:
     """Rows per message: 2.5 x the uniform-density expectation of the halo (+ transfers); checked on arrival."""
     return max(1024, int(2.5 * n_owned * geo.halo / geo.W) + 256)
-
-
-def migrant_capacity(n_owned: int, geo: SlabGeometry) -> int:
-    return max(1024, int(0.25 * n_owned * geo.halo / geo.W) + 256)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -272,7 +216,7 @@ class SlabShardedSimulator:
                 t = torch.tensor([n], device=self.device, dtype=torch.int64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 n = int(t.item())
-            self._cap = (halo_capacity(n, self.geo), migrant_capacity(n, self.geo))
+            self._cap = (halo_capacity(n, self.geo),)
         return self._cap
 
     def exchange_out(self):
