@@ -47,7 +47,7 @@ def measured_peaks() -> tuple[dict, str]:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the warm-up and the timed region run."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
@@ -146,6 +146,9 @@ def run_ours(args) -> dict:
         def one_step(i):
             sim.step(STEP["dt"], STEP["mu"], STEP["v0"], STEP["Dr"], seed=7, n_steps=1)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         one_step(i)
     # ---- device-timed region ----
@@ -153,9 +156,6 @@ def run_ours(args) -> dict:
     ms4, l4 = np.zeros(6), np.zeros(6, dtype=np.int64)
     h.call("afv_get_stage_times", ms4.ctypes.data, l4.ctypes.data, 1)
     launches0 = int(h.lib.afv_launch_count(h._h))
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)

@@ -235,6 +235,39 @@ class FiniteVoronoiSimulator:
         return self._preferred_areas.copy()
 
     # ------------------------------------------------------------------------------------------------
+    def plot_2d(self, ax=None, show: bool = False, **kw):
+        """Draw the finite Voronoi cells (straight contact edges and medium arcs) of the current positions.
+
+        A light-weight counterpart of the reference's ``plot_2d`` (``finite_voronoi.py:948-1107``): it consumes the
+        same ``build()`` dictionary (``vertices`` / ``regions`` / ``edges_type``), so the reference's own
+        ``visualize_2d(pts, diag, r)`` works on this backend's output as well.  Needs matplotlib.
+        """
+        import matplotlib.pyplot as plt   # imported lazily, like the reference does
+        ax = ax if ax is not None else plt.gca()
+        diag, pts, r = self.build(connect=False), self.pts, self.phys.r
+        V = diag["vertices"]
+        for i, (reg, types) in enumerate(zip(diag["regions"], diag["edges_type"])):
+            if len(reg) < 2:
+                ax.add_patch(plt.Circle(pts[i], r, fill=False, lw=kw.get("line_width", 1.0), color=kw.get("line_colors", "k")))
+                continue
+            for k, t in enumerate(types):
+                a, b = V[reg[k]], V[reg[(k + 1) % len(reg)]]
+                if t == 1:
+                    ax.plot([a[0], b[0]], [a[1], b[1]], "-", color=kw.get("line_colors", "k"), lw=kw.get("line_width", 1.0))
+                else:   # clockwise arc from a to b about the cell centre
+                    t0, t1 = np.arctan2(*(a - pts[i])[::-1]), np.arctan2(*(b - pts[i])[::-1])
+                    if t1 > t0:
+                        t1 -= 2 * np.pi
+                    th = np.linspace(t0, t1, max(int(abs(t1 - t0) / 0.05), 2))
+                    ax.plot(pts[i, 0] + r * np.cos(th), pts[i, 1] + r * np.sin(th), "-", color=kw.get("line_colors", "k"), lw=kw.get("line_width", 1.0))
+        if kw.get("show_points", True):
+            ax.plot(pts[:, 0], pts[:, 1], ".", ms=kw.get("point_size", 2))
+        ax.set_aspect("equal")
+        if show:
+            plt.show()
+        return ax
+
+    # ------------------------------------------------------------------------------------------------
     def diagnostics(self) -> dict[str, int]:
         """Counters of the last build: slow-path cells, unmatched ring look-ups, max ring length, bins."""
         out = np.zeros(4, dtype=np.int64)
