@@ -258,9 +258,13 @@ PhysDev phys_dev(const AfvParams &p) { return PhysDev{p.r, p.P0, p.KA, p.KP, p.L
 // grid of a periodic box (or of an x-slab of it): returns the bin counts
 void periodic_grid(AfvHandle h, GridDesc &g) {
     const double cut = 2.0 * h->prm.r;
-    int nby = std::max(1, (int)std::floor(h->L / cut));
     const double wx = h->slab ? (h->slab_x1 - h->slab_x0) : h->L;
-    int nbx = std::max(1, (int)std::floor(wx / cut));
+    double fy = std::max(1.0, std::floor(h->L / cut)), fx = std::max(1.0, std::floor(wx / cut));
+    if (fx * fy > (double)h->nbins_cap) {   // very dilute system: coarser bins (still >= 2r) so that the grid fits
+        const double sc = std::sqrt((double)h->nbins_cap / (fx * fy));
+        fx = std::max(1.0, std::floor(fx * sc)); fy = std::max(1.0, std::floor(fy * sc));
+    }
+    int nbx = (int)fx, nby = (int)fy;
     while ((int64_t)nbx * nby > h->nbins_cap) { if (nbx >= nby) --nbx; else --nby; }
     g.x0 = h->slab ? h->slab_x0 : 0.0; g.y0 = 0.0;
     g.inv_bx = (double)nbx / wx; g.inv_by = (double)nby / h->L;
@@ -375,6 +379,23 @@ int check_flags(AfvHandle h) {
         return AFV_ERR_CAPACITY;
     }
     return AFV_OK;
+}
+
+// Geometry stage with a synchronous capacity check: when more cells were queued for the slow path than it can take
+// (the candidate lists were too short for the local density), double the list capacity and run the stage again.
+// Used where a host round trip per build is acceptable: afv_build, and every step of an open-boundary run (whose
+// density is not known in advance).
+int geometry_checked(AfvHandle h) {
+    for (;;) {
+        int rc = stage_geometry(h);
+        if (rc) return rc;
+        int f[4];
+        CK(cudaMemcpyAsync(f, h->flags, sizeof f, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (f[3] == 0 || h->cmax_hint >= CMAX_HARD) return AFV_OK;      // fine, or nothing left to grow: check_flags reports it
+        h->cmax_hint = std::min(CMAX_HARD, 2 * h->cmax_hint);
+        CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
+    }
 }
 
 int require_built(AfvHandle h) {
@@ -549,7 +570,7 @@ int afv_build(AfvHandle h, unsigned flags) {
     int rc;
     CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
     if ((rc = stage_sort(h))) return rc;
-    if ((rc = stage_geometry(h))) return rc;
+    if ((rc = geometry_checked(h))) return rc;
     if ((rc = stage_force(h, false, 0, 0, 0, 0, 0, 0, nullptr))) return rc;
     if ((rc = check_flags(h))) return rc;
     h->built = true;
@@ -610,7 +631,8 @@ int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t s
     for (int s = 0; s < n_steps; ++s) {
         if (deferred) CK(cudaMemsetAsync(h->flags, 0, sizeof(int), h->stream));   // the slow-path queue restarts every step
         if ((rc = stage_sort(h))) return rc;
-        if ((rc = stage_geometry(h))) return rc;
+        // open boundaries: the local density is unknown, so the capacity is checked (and grown) before the positions move
+        if ((rc = (h->L > 0.0 ? stage_geometry(h) : geometry_checked(h)))) return rc;
         if ((rc = stage_force(h, true, dt, mu, v0, Dr, seed, step0 + s, noise_dev ? noise_dev + (size_t)s * h->n : nullptr))) return rc;
     }
     if (!deferred && (rc = check_flags(h))) return rc;   // also synchronises: noise_host is borrowed for the call only

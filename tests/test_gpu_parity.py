@@ -385,3 +385,22 @@ def test_long_runs_of_the_baseline_configs_stay_consistent():
     _close(d["areas"], o["areas"], "areas after relaxation")
     assert np.array_equal(d["coord_nums"], o["coord_nums"])
     sim.close()
+
+
+def test_dense_open_blob_grows_candidate_lists():
+    """Open boundaries give no density in advance: a blob with ~45 cells within 2 l of each cell overflows the
+    initial candidate lists of far more cells than the slow path can queue; the build must grow them and succeed."""
+    import pyafv_b200 as afv
+    from afv_oracle import oracle_build
+    rng = np.random.default_rng(23)
+    N = 60000
+    pts = rng.random((N, 2)) * np.sqrt(N / 3.5) + 1000.0
+    sim = afv.FiniteVoronoiSimulator(pts, afv.PhysicalParams())
+    d = sim.build(rings=False)
+    o = oracle_build(pts)
+    for k in ("areas", "perimeters", "arclens", "forces"):
+        _close(d[k], o[k], k)
+    assert np.array_equal(d["coord_nums"], o["coord_nums"])
+    sim.step(1e-4, 1.0, 0.0, 0.0, n_steps=3)
+    assert np.isfinite(sim.pts).all()
+    sim.close()
