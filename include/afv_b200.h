@@ -114,7 +114,8 @@ int afv_get_num_ring_entries(AfvHandle h, int64_t *T);
 int afv_get_rings(AfvHandle h, int64_t *region_off, int8_t *edge_types, double *vertices_xy);
 
 /* diagnostics of the last build: [0] cells that needed the large-capacity path, [1] ring look-ups that found
- * no partner (inconsistent near-cocircular topology), [2] max ring length, [3] number of bins */
+ * no partner (inconsistent near-cocircular topology), [2] longest ring when it exceeds 12 entries (else 0), [3] number
+ * of bins (periodic handles) */
 int afv_get_diagnostics(AfvHandle h, int64_t out[4]);
 
 /* ---- measurement --------------------------------------------------------------------------------- */
