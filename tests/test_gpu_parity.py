@@ -404,3 +404,25 @@ def test_dense_open_blob_grows_candidate_lists():
     sim.step(1e-4, 1.0, 0.0, 0.0, n_steps=3)
     assert np.isfinite(sim.pts).all()
     sim.close()
+
+
+def test_full_size_parity_with_oracle_1e6():
+    """BASELINE config [3] at full size: N = 10^6 periodic dense, heterogeneous A0 -- topology exact, FP64 quantities to
+    1e-9, against the CPU oracle (which finishes 10^6 cells in a few seconds)."""
+    import pyafv_b200 as afv
+    from afv_oracle import oracle_build
+    N = 1_000_000
+    L = float(np.sqrt(N))
+    rng = np.random.default_rng(42)
+    pts = rng.random((N, 2)) * L
+    A0 = np.pi * (1 + 0.1 * rng.standard_normal(N))
+    sim = afv.FiniteVoronoiSimulator(pts, afv.PhysicalParams(), periodic=L)
+    sim.update_preferred_areas(A0)
+    d = sim.build(connect=True, rings=False)
+    o = oracle_build(pts, A0=A0, periodic=L)
+    for k in ("areas", "perimeters", "arclens", "forces"):
+        _close(d[k], o[k], k)
+    assert np.array_equal(d["coord_nums"], o["coord_nums"])
+    assert np.array_equal(d["connections"], o["connections"])
+    assert sim.diagnostics()["lookup_misses"] == 0
+    sim.close()
