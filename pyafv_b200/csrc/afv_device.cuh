@@ -1,6 +1,7 @@
 // Device-side building blocks of the AFV hot path (sm_100a).  See DESIGN.md for the data layout.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace afv {

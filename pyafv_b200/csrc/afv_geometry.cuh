@@ -294,81 +294,84 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_hull(GeomArgs a, 
             }
         }
     }
-    // displacement of list entry c.  Entry n is the ORIGIN of the dual plane, homogeneous (p, k) = ((0,0), 1): the
-    // "half-plane at infinity".  It becomes a hull vertex exactly when the neighbours do not surround the cell, i.e.
-    // when the Voronoi polygon is unbounded; the two polygon edges next to it then run off to infinity.
-    auto disp = [&](int c, double &dx, double &dy) {
-        dx = 0.0; dy = 0.0;
-        if (c < n) {
-            const double2 pc = a.xy[s_idx[c * HULL_TPB + tid]];
-            dx = pc.x - xi; dy = pc.y - yi;
-            if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
-            if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
-        }
-    };
-
-    // ---- gift wrapping in the dual plane.  Candidate c <-> homogeneous dual point (p_c, k_c), k_c = |p_c|^2 / 2.
+    // ---- gift wrapping in the dual plane.  List entry c <-> homogeneous dual point (p_c, k_c) with k_c = |p_c|^2
+    //      (twice the true k; the factor cancels in every sign).  Entry n is the ORIGIN of the dual plane, (p, k) =
+    //      ((0,0), 2): the "half-plane at infinity".  It becomes a hull vertex exactly when the neighbours do not
+    //      surround the cell, i.e. when the Voronoi polygon is unbounded; the two polygon edges next to it then run
+    //      off to infinity.
     //      orient(a, b, c) = sign((p_b k_a - p_a k_b) x (p_c k_a - p_a k_c));  the nearest neighbour is on the hull.
-    //      Two independent running-best chains (even / odd list entries) halve the dependent latency. ----
+    //      Two independent running-best chains (even / odd list entries) halve the dependent latency.  The loop is
+    //      compiled twice: warps none of whose cells touches a periodic face skip the minimum-image code. ----
     unsigned long long hull_lo = 0ull, hull_hi = 0ull;   // 16 x 8-bit list indices (n = the origin)
     int m = 0;
     const bool wrap = live && ok && n > 0;
     const int npair_max = (__reduce_max_sync(FULL_MASK, wrap ? n : 0) + 1) >> 1;
-    bool done = !wrap;
-    int cur = imin;
-    while (__any_sync(FULL_MASK, !done)) {
-        double pax = 0.0, pay = 0.0, ka = 1.0;
-        if (!done) {
-            if (m < 8) hull_lo |= (unsigned long long)cur << (8 * m); else hull_hi |= (unsigned long long)cur << (8 * (m - 8));
-            ++m;
-            disp(cur, pax, pay);
-            ka = (cur < n) ? 0.5 * (pax * pax + pay * pay) : 1.0;
-        }
-        int best0 = -1, best1 = -1;
-        double u0x = 0.0, u0y = 0.0, u1x = 0.0, u1y = 0.0;
-        for (int cp = 0; cp < npair_max; ++cp) {
-            const int ca = 2 * cp, cb = 2 * cp + 1;
-            if (!done && ca < n && ca != cur) {
-                double qx_, qy_; disp(ca, qx_, qy_);
-                const double kc = 0.5 * (qx_ * qx_ + qy_ * qy_);
-                const double wx = qx_ * ka - pax * kc, wy = qy_ * ka - pay * kc;
-                if (best0 < 0 || u0x * wy - u0y * wx < 0.0) { best0 = ca; u0x = wx; u0y = wy; }
+    auto hull_steps = [&](auto wrap_tag) {
+        constexpr bool W = decltype(wrap_tag)::value;
+        auto disp = [&](int c, double &dx, double &dy) {       // displacement of list entry c (< n)
+            const double2 pc = a.xy[s_idx[c * HULL_TPB + tid]];
+            dx = pc.x - xi; dy = pc.y - yi;
+            if (W) {
+                if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
+                if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
             }
-            if (!done && cb < n && cb != cur) {
-                double qx_, qy_; disp(cb, qx_, qy_);
-                const double kc = 0.5 * (qx_ * qx_ + qy_ * qy_);
-                const double wx = qx_ * ka - pax * kc, wy = qy_ * ka - pay * kc;
-                if (best1 < 0 || u1x * wy - u1y * wx < 0.0) { best1 = cb; u1x = wx; u1y = wy; }
+        };
+        bool done = !wrap;
+        int cur = imin;
+        while (__any_sync(FULL_MASK, !done)) {
+            double pax = 0.0, pay = 0.0, ka = 2.0;
+            if (!done) {
+                if (m < 8) hull_lo |= (unsigned long long)cur << (8 * m); else hull_hi |= (unsigned long long)cur << (8 * (m - 8));
+                ++m;
+                if (cur < n) { disp(cur, pax, pay); ka = pax * pax + pay * pay; }
             }
-        }
-        if (!done) {
-            // merge the chains: the overall next hull vertex is the one with every other point on its left
-            int best = best0;
-            double ux = u0x, uy = u0y;
-            if (best0 < 0 || (best1 >= 0 && u0x * u1y - u0y * u1x < 0.0)) { best = best1; ux = u1x; uy = u1y; }
-            // the origin (p, k) = ((0,0), 1): w = 0 * k_a - p_a * 1.  An exact tie means q_a, the origin and the best
-            // neighbour are collinear (e.g. collinear cells): the farther point wins, as in any gift wrapping;
-            // |q_c - q_a| = |w_c| / (k_a k_c).
-            if (cur != n) {
-                const double wx = -pax, wy = -pay;
-                bool take = best < 0;
-                if (!take) {
-                    const double cr = ux * wy - uy * wx;
-                    if (cr < 0.0) take = true;
-                    else if (cr == 0.0) {
-                        double bx_, by_;
-                        disp(best, bx_, by_);
-                        const double kb = 0.5 * (bx_ * bx_ + by_ * by_);
-                        take = (wx * wx + wy * wy) * kb * kb > (ux * ux + uy * uy);
-                    }
+            int best0 = -1, best1 = -1;
+            double u0x = 0.0, u0y = 0.0, u1x = 0.0, u1y = 0.0;
+            for (int cp = 0; cp < npair_max; ++cp) {
+                const int ca = 2 * cp, cb = 2 * cp + 1;
+                if (!done && ca < n && ca != cur) {
+                    double qx_, qy_; disp(ca, qx_, qy_);
+                    const double kc = qx_ * qx_ + qy_ * qy_;
+                    const double wx = qx_ * ka - pax * kc, wy = qy_ * ka - pay * kc;
+                    if (best0 < 0 || u0x * wy - u0y * wx < 0.0) { best0 = ca; u0x = wx; u0y = wy; }
                 }
-                if (take) best = n;
+                if (!done && cb < n && cb != cur) {
+                    double qx_, qy_; disp(cb, qx_, qy_);
+                    const double kc = qx_ * qx_ + qy_ * qy_;
+                    const double wx = qx_ * ka - pax * kc, wy = qy_ * ka - pay * kc;
+                    if (best1 < 0 || u1x * wy - u1y * wx < 0.0) { best1 = cb; u1x = wx; u1y = wy; }
+                }
             }
-            cur = best;
-            if (cur == imin) done = true;
-            else if (m >= KHULL) { ok = false; done = true; }
+            if (!done) {
+                // merge the chains: the overall next hull vertex is the one with every other point on its left
+                int best = best0;
+                double ux = u0x, uy = u0y;
+                if (best0 < 0 || (best1 >= 0 && u0x * u1y - u0y * u1x < 0.0)) { best = best1; ux = u1x; uy = u1y; }
+                // the origin: w = 0 * k_a - p_a * k_O, direction -p_a.  An exact tie means q_a, the origin and the best
+                // neighbour are collinear (e.g. collinear cells): the farther point wins, as in any gift wrapping;
+                // |q_c - q_a| is proportional to |w_c| / k_c.
+                if (cur != n) {
+                    const double wx = -pax, wy = -pay;
+                    bool take = best < 0;
+                    if (!take) {
+                        const double cr = ux * wy - uy * wx;
+                        if (cr < 0.0) take = true;
+                        else if (cr == 0.0) {
+                            double bx_, by_;
+                            disp(best, bx_, by_);
+                            const double kb = bx_ * bx_ + by_ * by_;
+                            take = (wx * wx + wy * wy) * kb * kb > (ux * ux + uy * uy);
+                        }
+                    }
+                    if (take) best = n;
+                }
+                cur = best;
+                if (cur == imin) done = true;
+                else if (m >= KHULL) { ok = false; done = true; }
+            }
         }
-    }
+    };
+    if (__any_sync(FULL_MASK, wrapx || wrapy)) hull_steps(std::true_type{}); else hull_steps(std::false_type{});
 
     // ---- hand the polygon to k_ring ----
     if (live) {
