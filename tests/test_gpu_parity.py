@@ -426,3 +426,31 @@ def test_full_size_parity_with_oracle_1e6():
     assert np.array_equal(d["connections"], o["connections"])
     assert sim.diagnostics()["lookup_misses"] == 0
     sim.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_random_parameter_sets_match_oracle(seed):
+    """Random physical parameters (radius, stiffnesses, tensions of either sign, delta from 0 to r), random densities,
+    open and periodic, per-cell A0: every term of the force (area, perimeter, arc tension, delta cut-off) is exercised."""
+    import pyafv_b200 as afv
+    from afv_oracle import oracle_build
+    rng = np.random.default_rng(1000 + seed)
+    r = float(rng.uniform(0.5, 2.0))
+    kw = dict(r=r, A0=float(rng.uniform(0.3, 1.5) * np.pi * r * r), P0=float(rng.uniform(2.0, 7.0) * r), KA=float(rng.uniform(0.0, 3.0)),
+              KP=float(rng.uniform(0.0, 3.0)), Lambda=float(rng.uniform(-0.5, 0.8)), delta=float(rng.uniform(0.0, 1.0) * r))
+    N = 8000
+    dens = float(rng.choice([0.15, 0.4, 1.0, 1.6])) / (r * r)
+    L = float(np.sqrt(N / dens))
+    periodic = bool(seed % 2)
+    pts = rng.random((N, 2)) * L + (0.0 if periodic else -0.5 * L)
+    A0 = kw["A0"] * (1 + 0.3 * rng.random(N))
+    sim = afv.FiniteVoronoiSimulator(pts, afv.PhysicalParams(**kw), periodic=L if periodic else None)
+    sim.update_preferred_areas(A0)
+    d = sim.build()
+    okw = dict(kw); okw["A0"] = A0
+    o = oracle_build(pts, periodic=L if periodic else None, **okw)
+    for k in ("areas", "perimeters", "arclens", "forces"):
+        _close(d[k], o[k], k)
+    assert np.array_equal(d["coord_nums"], o["coord_nums"]) and np.array_equal(d["connections"], o["connections"])
+    assert sim.diagnostics()["lookup_misses"] == 0
+    sim.close()
