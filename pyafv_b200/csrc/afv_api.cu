@@ -38,6 +38,9 @@ struct AfvContext {
     bool slab = false;          // x-slab of a periodic box: grid open in x over [slab_x0, slab_x1), periodic in y
     double slab_x0 = 0.0, slab_x1 = 0.0;
     int64_t n = 0, n_owned = 0, cap = 0;
+    GridDesc grid_host{};        // last grid description uploaded to d_grid (periodic / slab mode)
+    bool grid_uploaded = false;
+    int64_t n_dead = 0;          // cells marked CELL_DEAD (counted in n) that the next sort drops
     bool gid_is_perm = true;  // gid is a permutation of 0..n-1 (single-GPU use); false after set_cells_device
     // SoA state, double-buffered for the reorder
     double2 *xy[2] = {nullptr, nullptr};
@@ -180,7 +183,7 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     int bits = 6;
     while (((int64_t)1 << bits) < 2 * cap && bits < 31) ++bits;
     h->key_bits = bits;
-    h->nbins_cap = (int)std::min<int64_t>((int64_t)1 << bits, ((int64_t)1 << 31) - 2);
+    h->nbins_cap = (int)std::min<int64_t>(((int64_t)1 << bits) - 1, ((int64_t)1 << 31) - 2);   // the all-ones key marks dead cells
     if ((rc = dev_alloc(h, &h->keys, cap))) return rc;
     if ((rc = dev_alloc(h, &h->keys_sorted, cap))) return rc;
     if ((rc = dev_alloc(h, &h->iota, cap))) return rc;
@@ -275,40 +278,51 @@ void periodic_grid(AfvHandle h, GridDesc &g) {
 int upload_grid_periodic(AfvHandle h) {
     GridDesc g{};
     periodic_grid(h, g);
-    CK(cudaMemcpyAsync(h->d_grid, &g, sizeof g, cudaMemcpyHostToDevice, h->stream));
+    if (h->grid_uploaded && std::memcmp(&g, &h->grid_host, sizeof g) == 0) return AFV_OK;   // unchanged since the last step
+    h->grid_host = g;
+    CK(cudaMemcpyAsync(h->d_grid, &h->grid_host, sizeof g, cudaMemcpyHostToDevice, h->stream));
+    h->grid_uploaded = true;
     return AFV_OK;
 }
 
-// bin + sort + reorder + bin starts
+// bin + sort + reorder + bin starts.  Cells marked dead by the exchange sort behind the live ones and are dropped here.
 int stage_sort(AfvHandle h) {
     StageTimer t(h, 0);
-    const int n = (int)h->n;
+    const int n_all = (int)h->n;
+    const int n = (int)(h->n - h->n_dead);
     const int c = h->cur, o = 1 - c;
     if (h->L > 0.0) {
         int rc = upload_grid_periodic(h);
         if (rc) return rc;
     } else {
-        int nb = std::min(nblk(n, 256), 1024);
-        k_bbox_partial<<<nb, 256, 0, h->stream>>>(h->xy[c], n, h->bbox_part);
+        int nb = std::min(nblk(n_all, 256), 1024);
+        k_bbox_partial<<<nb, 256, 0, h->stream>>>(h->xy[c], n_all, h->bbox_part);
         k_bbox_final<<<1, 32, 0, h->stream>>>(h->bbox_part, nb, h->prm.r, h->nbins_cap, h->d_grid);
         h->launches += 2;
     }
-    k_bin_keys<<<nblk(n, 256), 256, 0, h->stream>>>(h->xy[c], n, h->d_grid, h->keys);
+    // sort width: the bins actually in use when the host knows them (periodic box / slab), else the capacity; dead
+    // cells carry the first key behind the bins
+    int sort_bits = h->key_bits;
+    unsigned dead_key = (1u << h->key_bits) - 1u;
+    if (h->L > 0.0) {
+        dead_key = (unsigned)(h->grid_host.nbx * h->grid_host.nby);
+        sort_bits = 1;
+        while ((1u << sort_bits) <= dead_key) ++sort_bits;
+    }
+    k_bin_keys<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->xy[c], h->owned[c], n_all, h->d_grid, dead_key, h->keys);
     size_t tmp = h->cub_tmp_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->keys, h->keys_sorted, h->iota, h->perm, n, 0, h->key_bits, h->stream));
-    k_reorder<<<nblk(n, 256), 256, 0, h->stream>>>(h->perm, n, h->xy[c], h->th[c], h->a0[c], h->gid[c], h->owned[c],
-                                                    h->xy[o], h->th[o], h->a0[o], h->gid[o], h->owned[o]);
+    CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->keys, h->keys_sorted, h->iota, h->perm, n_all, 0, sort_bits, h->stream));
+    if (n > 0)
+        k_reorder<<<nblk(n, 256), 256, 0, h->stream>>>(h->perm, n, h->xy[c], h->th[c], h->a0[c], h->gid[c], h->owned[c],
+                                                        h->xy[o], h->th[o], h->a0[o], h->gid[o], h->owned[o]);
     h->cur = o;
-    // the number of bins is a device-side quantity in the open case: launch for the capacity, threads beyond
-    // nbx*nby exit immediately
-    int64_t nb_launch = (h->L > 0.0) ? 0 : (int64_t)h->nbins_cap + 1;
+    h->n = n; h->n_dead = 0;
     if (h->L > 0.0) {
         GridDesc g{};
         periodic_grid(h, g);
-        nb_launch = (int64_t)g.nbx * g.nby + 1;
         h->h_flags[3] = g.nbx * g.nby;
     }
-    k_bin_start<<<nblk(nb_launch, 256), 256, 0, h->stream>>>(h->keys_sorted, n, h->d_grid, h->bin_start);
+    k_bin_start<<<nblk(n + 1, 256), 256, 0, h->stream>>>(h->keys_sorted, n, h->d_grid, h->bin_start);
     h->launches += 4;  // keys, sort (counted once), reorder, bin_start
     CK(cudaGetLastError());
     return AFV_OK;
@@ -502,7 +516,7 @@ int afv_set_params(AfvHandle h, const AfvParams *p) {
     return AFV_OK;
 }
 
-int64_t afv_num_cells(AfvHandle h) { return h ? h->n : 0; }
+int64_t afv_num_cells(AfvHandle h) { return h ? h->n - h->n_dead : 0; }
 int64_t afv_num_owned(AfvHandle h) { return h ? h->n_owned : 0; }
 
 int afv_set_positions(AfvHandle h, const double *xy_host, int64_t N) {
@@ -532,7 +546,7 @@ int afv_set_positions(AfvHandle h, const double *xy_host, int64_t N) {
         k_init_cells<<<nblk(n, 256), 256, 0, h->stream>>>(n, h->gid[h->cur], h->owned[h->cur]);
         h->launches += 1;
     }
-    h->n = N; h->n_owned = N; h->gid_is_perm = true; h->built = false;
+    h->n = N; h->n_owned = N; h->n_dead = 0; h->gid_is_perm = true; h->built = false;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));  // xy_host is borrowed for the call only
     return AFV_OK;
@@ -566,6 +580,7 @@ int afv_set_theta(AfvHandle h, const double *theta_host, int64_t N) {
 int afv_build(AfvHandle h, unsigned flags) {
     CHECK_H(h);
     h->n_conn = -1; h->n_ring = -1;
+    if (h->n == h->n_dead) { h->n = h->n_dead = 0; }   // only stale halo copies left
     if (h->n == 0) { h->built = true; h->n_conn = 0; h->n_ring = 0; return AFV_OK; }
     int rc;
     CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
@@ -616,6 +631,7 @@ int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t s
              const double *noise_host) {
     CHECK_H(h);
     if (n_steps < 0 || Dr < 0.0 || !(dt >= 0.0)) { h->err = "invalid step arguments"; return AFV_ERR_ARG; }
+    if (h->n == h->n_dead) { h->n = h->n_dead = 0; }
     if (h->n == 0 || n_steps == 0) return AFV_OK;
     int rc;
     const double *noise_dev = nullptr;

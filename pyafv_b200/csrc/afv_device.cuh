@@ -12,6 +12,9 @@ constexpr int RS_SLOW = 96;       // ring capacity of the slow path (pooled ring
 constexpr int KPOLY_SLOW = 96;    // clip-polygon capacity of the slow path
 constexpr int OVF_MAX = 8192;     // cells per build that may take the slow path
 constexpr int RING_IN_POOL = 255; // ring_len sentinel: the ring lives in the overflow pool
+// ownership mark of a cell (slab sharding): owned by this rank / halo copy of a neighbour rank's cell / stale halo copy
+// waiting to be dropped by the next sort
+constexpr unsigned char CELL_HALO = 0, CELL_OWNED = 1, CELL_DEAD = 2;
 
 // Uniform cell list description.  Lives in device memory so that the open-boundary path can refresh it on the
 // device (bounding box -> grid) without a host round trip.

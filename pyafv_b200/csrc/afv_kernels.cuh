@@ -72,9 +72,13 @@ __global__ void k_bbox_final(const double *__restrict__ part, int nblocks, doubl
 // ------------------------------------------------------------------------------------------------------
 // K1a: bin hash.  key = by * nbx + bx  (row-major so that the 3 bins of a row are contiguous after the sort)
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_bin_keys(const double2 *__restrict__ xy, int n, const GridDesc *__restrict__ gp, unsigned *__restrict__ keys) {
+// Cells marked CELL_DEAD (stale halo copies, see k_exchange_pack) get `dead_key`, larger than every bin key: the
+// sort moves them behind the live cells, where the reorder drops them.
+__global__ void k_bin_keys(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, const GridDesc *__restrict__ gp,
+                           unsigned dead_key, unsigned *__restrict__ keys) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (owned[i] == CELL_DEAD) { keys[i] = dead_key; return; }
     const GridDesc g = *gp;
     const double2 q = xy[i];
     int bx = (int)floor((q.x - g.x0) * g.inv_bx), by = (int)floor((q.y - g.y0) * g.inv_by);
@@ -95,18 +99,16 @@ __global__ void k_reorder(const int *__restrict__ perm, int n, const double2 *__
     xy1[s] = xy0[p]; t1[s] = t0[p]; a1[s] = a0[p]; g1[s] = g0[p]; o1[s] = o0[p];
 }
 
-// K1c: first sorted slot of every bin (lower bound), bin_start[nbins] = n
+// K1c: first sorted slot of every bin (lower bound), bin_start[nbins] = n.  One thread per sorted slot s in [0, n]:
+// the bins in (key[s-1], key[s]] start at s (every bin is written exactly once; runs of empty bins are short).
 __global__ void k_bin_start(const unsigned *__restrict__ keys_sorted, int n, const GridDesc *__restrict__ gp,
                             int *__restrict__ bin_start) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    int nb = gp->nbx * gp->nby;
-    if (b > nb) return;
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (keys_sorted[mid] < (unsigned)b) lo = mid + 1; else hi = mid;
-    }
-    bin_start[b] = lo;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n) return;
+    const int nb = gp->nbx * gp->nby;
+    const int first = (s > 0) ? (int)keys_sorted[s - 1] + 1 : 0;
+    const int last = (s < n) ? (int)keys_sorted[s] : nb;
+    for (int b = first; b <= last; ++b) bin_start[b] = s;
 }
 
 #include "afv_geometry.cuh"
@@ -449,12 +451,131 @@ __global__ void k_pack_exchange(const int *__restrict__ idxA, const int *__restr
     double *q = msg + 5 * (size_t)(i + 1);
     q[0] = xy[s].x + x_shift; q[1] = xy[s].y; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
 }
+// ---- the per-step exchange, three launches, no atomics (message order = slot order, reproducible) ----------------
+// Owned cells fall into up to four lists: q = 0 transfers to the left rank (x < lo), 1 halo rows for the left rank
+// (lo <= x < lo + halo), 2 transfers to the right rank (x >= hi), 3 halo rows for the right rank (hi - halo <= x < hi).
+constexpr int XCH_TPB = 256;
+__device__ __forceinline__ unsigned xch_lists(double x, unsigned char own, double lo, double hi, double halo) {
+    if (own != CELL_OWNED) return 0u;
+    return (x < lo ? 1u : 0u) | ((x >= lo && x < lo + halo) ? 2u : 0u) | (x >= hi ? 4u : 0u) | ((x >= hi - halo && x < hi) ? 8u : 0u);
+}
+// pass 1: members of every list per block
+__global__ void __launch_bounds__(XCH_TPB) k_exchange_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n,
+                                                            double lo, double hi, double halo, int *__restrict__ blk_cnt) {
+    const int i = blockIdx.x * XCH_TPB + threadIdx.x;
+    const unsigned m = (i < n) ? xch_lists(xy[i].x, owned[i], lo, hi, halo) : 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = __syncthreads_count((m >> q) & 1u);
+        if (threadIdx.x == 0) blk_cnt[4 * blockIdx.x + q] = c;
+    }
+}
+// pass 2 (one block): exclusive scan of the block counts of every list, list totals, message headers
+__global__ void __launch_bounds__(1024) k_exchange_scan(const int *__restrict__ blk_cnt, int nblocks, int *__restrict__ blk_off,
+                                                        int *__restrict__ totals, double *__restrict__ msg_left, double *__restrict__ msg_right) {
+    __shared__ int warp_sum[32][4];
+    __shared__ int carry[4];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t < 4) carry[t] = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int b = base + t;
+        int v[4], inc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            v[q] = (b < nblocks) ? blk_cnt[4 * b + q] : 0;
+            int x = v[q];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL_MASK, x, d); if (lane >= d) x += y; }
+            inc[q] = x;
+            if (lane == 31) warp_sum[w][q] = x;
+        }
+        __syncthreads();
+        if (w == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int x = warp_sum[lane][q];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL_MASK, x, d); if (lane >= d) x += y; }
+                warp_sum[lane][q] = x;       // inclusive over warps
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int before = carry[q] + (w ? warp_sum[w - 1][q] : 0) + inc[q] - v[q];
+            if (b < nblocks) blk_off[4 * b + q] = before;
+        }
+        __syncthreads();
+        if (t < 4) carry[t] += warp_sum[31][t];
+        __syncthreads();
+    }
+    if (t < 4) totals[t] = carry[t];
+    if (t == 0) {
+        msg_left[0] = (double)carry[0]; msg_left[1] = (double)carry[1]; msg_left[2] = msg_left[3] = msg_left[4] = 0.0;
+        msg_right[0] = (double)carry[2]; msg_right[1] = (double)carry[3]; msg_right[2] = msg_right[3] = msg_right[4] = 0.0;
+    }
+}
+// pass 3: write the rows ([header][transfers][halo rows]; rows beyond `cap` are dropped, the header keeps the true
+// counts so that both ends see the overflow) and update the ownership marks: halo copies of the previous step
+// become CELL_DEAD (the next sort drops them), cells that left the slab stay as halo copies of their new owner's cell.
+__global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__restrict__ xy, const double *__restrict__ th,
+                                                           const double *__restrict__ a0, const int64_t *__restrict__ gid,
+                                                           unsigned char *__restrict__ owned, int n, double lo, double hi, double halo,
+                                                           double shift_left, double shift_right, const int *__restrict__ blk_off,
+                                                           const int *__restrict__ totals, int cap, double *__restrict__ msg_left,
+                                                           double *__restrict__ msg_right) {
+    __shared__ int warp_cnt[XCH_TPB / 32][4];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int i = blockIdx.x * XCH_TPB + t;
+    double2 p = make_double2(0.0, 0.0);
+    unsigned char own = CELL_DEAD;
+    if (i < n) { p = xy[i]; own = owned[i]; }
+    const unsigned m = xch_lists(p.x, own, lo, hi, halo);
+    int rank_in_warp[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const unsigned bal = __ballot_sync(FULL_MASK, (m >> q) & 1u);
+        rank_in_warp[q] = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) warp_cnt[w][q] = __popc(bal);
+    }
+    __syncthreads();
+    if (i < n) {
+        if (own == CELL_HALO) owned[i] = CELL_DEAD;
+        else if (m & 5u) owned[i] = CELL_HALO;
+    }
+    if (!m) return;
+    const double tv = th[i], av = a0[i], gv = (double)gid[i];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (!((m >> q) & 1u)) continue;
+        int r = blk_off[4 * blockIdx.x + q] + rank_in_warp[q];
+        for (int k = 0; k < w; ++k) r += warp_cnt[k][q];
+        if (q & 1) r += totals[q - 1];                       // halo rows follow the transfers
+        if (r >= cap) continue;
+        double *row = ((q < 2) ? msg_left : msg_right) + 5 * (size_t)(r + 1);
+        row[0] = p.x + ((q < 2) ? shift_left : shift_right); row[1] = p.y; row[2] = tv; row[3] = av; row[4] = gv;
+    }
+}
+// received messages -> cells appended behind slot `base`: [left transfers][left halo][right transfers][right halo]
+__global__ void k_exchange_append(const double *__restrict__ in_left, const double *__restrict__ in_right, int nl_own, int nl, int nr_own,
+                                  int nr, int base, double2 *__restrict__ xy, double *__restrict__ th, double *__restrict__ a0,
+                                  int64_t *__restrict__ gid, unsigned char *__restrict__ owned) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nl + nr) return;
+    const bool left = i < nl;
+    const int k = left ? i : i - nl;
+    const double *q = (left ? in_left : in_right) + 5 * (size_t)(k + 1);
+    const int d = base + i;
+    xy[d] = make_double2(q[0], q[1]); th[d] = q[2]; a0[d] = q[3]; gid[d] = (int64_t)q[4];
+    owned[d] = (k < (left ? nl_own : nr_own)) ? CELL_OWNED : CELL_HALO;
+}
 // owned cells outside [lo, hi) stay as halo copies of cells that now belong to a neighbour
 __global__ void k_disown_outside(const double2 *__restrict__ xy, unsigned char *__restrict__ owned, int n, double lo, double hi) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double xv = xy[i].x;
-    if (owned[i] && (xv < lo || xv >= hi)) owned[i] = 0;
+    if (owned[i] == CELL_OWNED && (xv < lo || xv >= hi)) owned[i] = CELL_HALO;
 }
 __global__ void k_gather_counts8(const int *__restrict__ c, const double *__restrict__ in0, const double *__restrict__ in1,
                                  const int *__restrict__ flags, double *__restrict__ out) {
@@ -468,7 +589,7 @@ __global__ void k_flag_keep2(const double2 *__restrict__ xy, const unsigned char
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double xv = xy[i].x;
-    const bool sel = owned[i] && ((xv >= lo0 && xv < hi0) || (xv >= lo1 && xv < hi1));
+    const bool sel = owned[i] == CELL_OWNED && ((xv >= lo0 && xv < hi0) || (xv >= lo1 && xv < hi1));
     flag[i] = sel ? 0 : 1;
 }
 __global__ void k_gather_counts(const int *__restrict__ c0, const int *__restrict__ c1, const double *__restrict__ in0,
@@ -493,12 +614,12 @@ __global__ void k_flag_slab(const double2 *__restrict__ xy, const unsigned char 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double xv = xy[i].x;
-    const int sel = (owned[i] && xv >= lo && xv < hi) ? 1 : 0;
+    const int sel = (owned[i] == CELL_OWNED && xv >= lo && xv < hi) ? 1 : 0;
     flag[i] = invert ? 1 - sel : sel;
 }
 __global__ void k_flag_owned(const unsigned char *__restrict__ owned, int n, int *__restrict__ flag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flag[i] = owned[i] ? 1 : 0;
+    if (i < n) flag[i] = (owned[i] == CELL_OWNED) ? 1 : 0;
 }
 
 // DFMA throughput micro-benchmark: 8 independent chains per thread

@@ -74,7 +74,8 @@ class GpuCellStore:
         self.h.call("afv_drop_halo")
 
     def pack_exchange(self, geo, cap: int):
-        """(to_left, to_right) messages carrying ownership transfers + halo rows; no host synchronisation."""
+        """(to_left, to_right) messages carrying ownership transfers + halo rows; no host synchronisation.  Halo copies
+        left from the previous exchange are retired by the same pass."""
         ml, mr = self._msg("xl", cap), self._msg("xr", cap)
         self.h.call("afv_pack_exchange", float(geo.lo), float(geo.hi), float(geo.halo), float(geo.shift_to_left),
                     float(geo.shift_to_right), ml.data_ptr(), mr.data_ptr(), int(cap))
@@ -229,16 +230,14 @@ class SlabShardedSimulator:
     def compute_step(self, dt, mu, v0, Dr, seed, want_results: bool = False):
         self._h.call("afv_step", float(dt), float(mu), float(v0), float(Dr), C.c_uint64(int(seed)), C.c_int64(self._step_index), 1, None)
         self._step_index += 1
-        res = self.store.results() if want_results else None   # rows of the owned cells: updated x, y, theta + F, A, P, L, z
-        self.store.drop_halo()
-        return res
+        # rows of the owned cells: updated x, y, theta + F, A, P, L, z.  The halo copies stay until the next exchange
+        # retires them (pack_exchange), which costs nothing extra; drop_halo() is the explicit form.
+        return self.store.results() if want_results else None
 
     def compute_build(self) -> torch.Tensor:
         from . import _lib
         self._h.call("afv_build", _lib.BUILD_FORCES)
-        res = self.store.results().clone()
-        self.store.drop_halo()
-        return res
+        return self.store.results().clone()
 
     # -- the per-rank drivers (one process per GPU) ---------------------------------------------------------
     def step(self, dt: float, mu: float = 1.0, v0: float = 0.0, Dr: float = 0.0, *, seed: int = 0, n_steps: int = 1) -> None:

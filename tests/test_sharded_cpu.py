@@ -42,6 +42,7 @@ class NumpyCellStore:
 
     # the message format of afv_pack_exchange / afv_finish_exchange: (cap+1, ROW), header [n_transfer, n_halo, 0, 0, 0]
     def pack_exchange(self, geo, cap):
+        self.drop_halo()                              # copies of the previous exchange are retired by the pack pass
         x = self.rows[:, 0]
         self._slab = (geo.lo, geo.hi)
         out = []
@@ -111,7 +112,8 @@ def _worker(rank, world, port, L, N, halo, q):
             for i in got:                                       # nothing but genuine images of other ranks' cells
                 for y in got[i]:
                     assert min(abs(y - (xs[i] + sh)) for sh in (-L, 0.0, L)) < 1e-9 and not (geo.lo <= y < geo.hi)
-            store.drop_halo()
+            if it % 2:                                          # explicit drop and drop-by-the-next-pack both occur
+                store.drop_halo()
             # ---- "dynamics": a deterministic drift that pushes cells across faces (< halo width) ----
             drift = 0.9 * np.sin(np.arange(N) + it)
             ids = store.rows[:, 4].astype(int)
