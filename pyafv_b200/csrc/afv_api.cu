@@ -77,12 +77,10 @@ struct AfvContext {
     int cmax_hint = 32;
     bool defer_checks = false;  // afv_step returns without synchronising; the flags are read at the next exchange / synchronize
     // pair exchange state (afv_pack_pair -> afv_finish_pair)
-    int *pair_cnt = nullptr;       // device [2]
-    double *pair_host = nullptr;   // pinned [4]
-    double *pair_dev = nullptr;    // device [4]
+    int *pair_cnt = nullptr;       // device: list lengths of the last pack (2 for the pair form, 4 for the exchange)
+    double *pair_host = nullptr;   // pinned [12]: counts sent / received (+ the deferred flags)
+    double *pair_dev = nullptr;    // device [12]
     double pair_rng[4] = {0, 0, 0, 0};
-    double xch_lo = 0, xch_hi = 0;  // slab interval of the last afv_pack_exchange
-    int *xch_idx[4] = {nullptr, nullptr, nullptr, nullptr};   // selection lists (views of scratch arrays)
     // profiling
     bool profiling = false;
     struct Span { int stage; cudaEvent_t a, b; };

@@ -437,21 +437,9 @@ __global__ void k_pack_message(const int *__restrict__ idx, const int *__restric
     double *q = msg + 5 * (size_t)(i + 1);
     q[0] = xy[s].x + x_shift; q[1] = xy[s].y; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
 }
-// exchange message = (cap+1, 5) rows: header [nA, nB, 0, 0, 0], then nA "transfer" rows (cells that change owner)
-// followed by nB halo rows.  Counts are read on the device.
-__global__ void k_pack_exchange(const int *__restrict__ idxA, const int *__restrict__ idxB, const int *__restrict__ cntA,
-                                const int *__restrict__ cntB, int cap, double x_shift, const double2 *__restrict__ xy,
-                                const double *__restrict__ th, const double *__restrict__ a0, const int64_t *__restrict__ gid,
-                                double *__restrict__ msg) {
-    const int nA = *cntA, nB = *cntB;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { msg[0] = (double)nA; msg[1] = (double)nB; msg[2] = msg[3] = msg[4] = 0.0; }
-    if (i >= nA + nB || i >= cap) return;
-    const int s = (i < nA) ? idxA[i] : idxB[i - nA];
-    double *q = msg + 5 * (size_t)(i + 1);
-    q[0] = xy[s].x + x_shift; q[1] = xy[s].y; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
-}
 // ---- the per-step exchange, three launches, no atomics (message order = slot order, reproducible) ----------------
+// exchange message = (cap+1, 5) rows: header [n_transfer, n_halo, 0, 0, 0], then the transfer rows (cells that change
+// owner) followed by the halo rows.
 // Owned cells fall into up to four lists: q = 0 transfers to the left rank (x < lo), 1 halo rows for the left rank
 // (lo <= x < lo + halo), 2 transfers to the right rank (x >= hi), 3 halo rows for the right rank (hi - halo <= x < hi).
 constexpr int XCH_TPB = 256;
@@ -569,13 +557,6 @@ __global__ void k_exchange_append(const double *__restrict__ in_left, const doub
     const int d = base + i;
     xy[d] = make_double2(q[0], q[1]); th[d] = q[2]; a0[d] = q[3]; gid[d] = (int64_t)q[4];
     owned[d] = (k < (left ? nl_own : nr_own)) ? CELL_OWNED : CELL_HALO;
-}
-// owned cells outside [lo, hi) stay as halo copies of cells that now belong to a neighbour
-__global__ void k_disown_outside(const double2 *__restrict__ xy, unsigned char *__restrict__ owned, int n, double lo, double hi) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double xv = xy[i].x;
-    if (owned[i] == CELL_OWNED && (xv < lo || xv >= hi)) owned[i] = CELL_HALO;
 }
 __global__ void k_gather_counts8(const int *__restrict__ c, const double *__restrict__ in0, const double *__restrict__ in1,
                                  const int *__restrict__ flags, double *__restrict__ out) {

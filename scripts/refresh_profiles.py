@@ -32,3 +32,12 @@ print("value %.4g ms/step %.4f e2e %.4g stages %s" % (d["value"], d["ms_per_step
 print("roofline", d["roofline"]["frac"], d["roofline"]["traffic"], "fp64", d["roofline_fp64"]["frac"], d["roofline_fp64"]["whole_step"], "clocks", d["clocks"], "cpu", d["cpu_baseline"]["value"])
 r = json.loads(open(f"{P}r1_final_bench_reference.json").read().strip().splitlines()[-1]); print("reference arm", r["value"], r["cpu_baseline"]["cores"])
 print(t)
+# multi-GPU lines of scripts/gpu_scaling.sh, when the tag has them
+import os
+for n in (1, 2, 4, 8):
+    for suffix, dst in (("", f"r1_final_bench_{n}gpu.json"), ("_1e8", f"r1_final_bench_{n}gpu_N1e8.json")):
+        src = f"{G}{tag}_bench{n}{suffix}.json"
+        if os.path.exists(src) and not (n == 1 and suffix == ""):      # the 1-GPU default line is the gpu_final.sh one
+            shutil.copy(src, P + dst)
+            d = json.loads(open(src).read().strip().splitlines()[-1])
+            print(f"{n} GPUs{suffix}: {d['value']:.4g} cell-steps/s  {d['ms_per_step']:.3f} ms/step")
