@@ -120,7 +120,8 @@ def run_ours(args) -> dict:
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner out of the one-JSON-line stdout
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local),
+                                pg_options=dist.ProcessGroupNCCL.Options(is_high_priority_stream=True))
     cells = args.cells_per_gpu
     pts, theta, L = make_slab(rank, world, cells, seed=42)
     phys = afv.PhysicalParams()
@@ -141,7 +142,8 @@ def run_ours(args) -> dict:
             sim.step(STEP["dt"], STEP["mu"], STEP["v0"], STEP["Dr"], seed=7, n_steps=1)
     else:
         from pyafv_b200.sharded import SlabShardedSimulator
-        sim = SlabShardedSimulator(pts, theta, phys, L, rank=rank, world=world, device=local, stream=stream.cuda_stream)
+        sim = SlabShardedSimulator(pts, theta, phys, L, rank=rank, world=world, device=local, stream=stream.cuda_stream,
+                                   overlap=not args.no_overlap)
         h = sim._h
         def one_step(i):
             sim.step(STEP["dt"], STEP["mu"], STEP["v0"], STEP["Dr"], seed=7, n_steps=1)
@@ -156,6 +158,7 @@ def run_ours(args) -> dict:
     ms4, l4 = np.zeros(6), np.zeros(6, dtype=np.int64)
     h.call("afv_get_stage_times", ms4.ctypes.data, l4.ctypes.data, 1)
     launches0 = int(h.lib.afv_launch_count(h._h))
+    ov0 = getattr(sim, "overlapped_steps", 0)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -170,6 +173,10 @@ def run_ours(args) -> dict:
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = int(h.lib.afv_launch_count(h._h)) - launches0
+    ov_steps = getattr(sim, "overlapped_steps", 0) - ov0
+    if world > 1 and rank == 0:
+        print(f"[bench] overlapped steps in the timed region: {ov_steps} of {args.steps}; largest |dx| of the recent steps: "
+              f"{[round(v, 3) for v in sim._dx_hist]}", file=sys.stderr)
     h.call("afv_get_stage_times", ms4.ctypes.data, l4.ctypes.data, 1)
     h.call("afv_set_profiling", 0)
     if world > 1:
@@ -259,7 +266,11 @@ def run_ours(args) -> dict:
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": f"N={total_cells} periodic active AFV, uniform random rho*l^2=1 "
                                       f"(BASELINE config[{3 if world == 1 else 4}] shape), {cells} cells/GPU, x-slabs",
-                          "cells_per_gpu": cells, "box_L": L, **STEP, "l2_policy": "per-step working set (ring records "
+                          "cells_per_gpu": cells, "box_L": L, **STEP,
+                          "exchange": ("none (1 GPU)" if world == 1 else "per step, NCCL point-to-point with both ring neighbours, " +
+                                       ("then step" if args.no_overlap else "overlapped with the interior update of the previous step")),
+                          "exchange_overlapped_steps": ov_steps,
+                          "l2_policy": "per-step working set (ring records "
                           f"{n_local * 1024 / 1e6:.0f} MB + state) exceeds the 126 MB L2; no explicit flush"},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_fp64": roofline_fp64,
                "cpu_baseline": cpu}
@@ -389,6 +400,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--reference-cells", type=int, default=200_000)
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: exchange, then step (default: the exchange for the next step "
+                    "overlaps the interior update)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -47,6 +47,7 @@ struct AfvContext {
     double *th[2] = {nullptr, nullptr}, *a0[2] = {nullptr, nullptr};
     int64_t *gid[2] = {nullptr, nullptr};
     unsigned char *owned[2] = {nullptr, nullptr};
+    unsigned char *marks = nullptr;   // per cell: MARK_DONE | exchange lists, written by the two-phase k_force
     int cur = 0;
     // cell list
     unsigned *keys = nullptr, *keys_sorted = nullptr;
@@ -64,7 +65,8 @@ struct AfvContext {
     unsigned char *hull_len = nullptr;
     RingOwn *ro = nullptr;
     RingSelf *self = nullptr;
-    int *flags = nullptr;         // device: [0] slow-path cells, [1] lookup misses, [2] max ring length, [3] hard overflows
+    int *flags = nullptr;         // device: [0] slow-path cells, [1] lookup misses, [2] max ring length, [3] hard overflows,
+                                  // [4], [5] largest |dx| of a step (float bits; even / odd overlapped steps)
     int *ovf_cells = nullptr, *ovf_index = nullptr, *ovf_len = nullptr;
     RingShared *ovf_rs = nullptr;
     RingOwn *ovf_ro = nullptr;
@@ -78,9 +80,14 @@ struct AfvContext {
     bool defer_checks = false;  // afv_step returns without synchronising; the flags are read at the next exchange / synchronize
     // pair exchange state (afv_pack_pair -> afv_finish_pair)
     int *pair_cnt = nullptr;       // device: list lengths of the last pack (2 for the pair form, 4 for the exchange)
-    double *pair_host = nullptr;   // pinned [12]: counts sent / received (+ the deferred flags)
-    double *pair_dev = nullptr;    // device [12]
+    double *pair_host = nullptr;   // pinned [16]: counts sent / received, the deferred flags, the displacement slots
+    double *pair_dev = nullptr;    // device [16]
     double pair_rng[4] = {0, 0, 0, 0};
+    // overlapped step + exchange: the face strips are done (ev_strip) / the received cells are appended (ev_append)
+    cudaEvent_t ev_strip = nullptr, ev_append = nullptr;
+    int64_t slab_steps = 0;        // deferred slab steps issued (parity selects the displacement slot flags[4 + parity])
+    double last_dx[2] = {-1.0, -1.0};   // largest |dx| of the last two slab steps as read by the last exchange (< 0: unknown)
+    double ov_margin = -1.0;       // adaptive strip margin for the next overlapped step (< 0: not known yet, every owned cell is a strip cell)
     // profiling
     bool profiling = false;
     struct Span { int stage; cudaEvent_t a, b; };
@@ -139,6 +146,7 @@ void free_all(AfvHandle h) {
     cudaFree(h->ovf_index); h->ovf_index = nullptr;
     cudaFree(h->ring_key); h->ring_key = nullptr;
     cudaFree(h->hull_slot); h->hull_slot = nullptr; cudaFree(h->hull_len); h->hull_len = nullptr;
+    cudaFree(h->marks); h->marks = nullptr;
     h->keys = h->keys_sorted = nullptr; h->iota = h->perm = h->bin_start = nullptr; h->cub_tmp = nullptr;
     h->fx = h->fy = h->area = h->perim = h->arcl = nullptr; h->coord = nullptr; h->ring_len = nullptr;
     h->ro = nullptr; h->cnt = h->off = nullptr;
@@ -197,6 +205,7 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     if ((rc = dev_alloc(h, &h->ring_key, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->hull_slot, (size_t)cap * KHULL_STRIDE))) return rc;
     if ((rc = dev_alloc(h, &h->hull_len, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->marks, cap))) return rc;
     if ((rc = dev_alloc(h, &h->ro, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->self, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->ovf_index, cap))) return rc;
@@ -359,8 +368,15 @@ int stage_geometry(AfvHandle h) {
     return AFV_OK;
 }
 
+// Two-phase form of the update (slab sharding with overlap): the cells in the face strips first, then the interior;
+// `after_strips` (optional) runs between the two launches, e.g. to record the event the exchange stream waits for.
+struct StripPhases {
+    double strip_lo, strip_hi;     // strips: x < strip_lo or x >= strip_hi before the update
+    double lo, hi, halo;           // slab interval and halo width (exchange lists of the updated positions)
+};
+
 int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, double Dr, uint64_t seed, int64_t step,
-                const double *noise_row) {
+                const double *noise_row, const StripPhases *phases = nullptr, cudaEvent_t after_strips = nullptr, int disp_slot = -1) {
     StageTimer t(h, 3);
     const int n = (int)h->n;
     const int c = h->cur;
@@ -371,8 +387,21 @@ int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, doub
     a.do_step = do_step ? 1 : 0; a.xy = h->xy[c]; a.theta = h->th[c];
     a.dt = dt; a.mu = mu; a.v0 = v0; a.noise_amp = std::sqrt(2.0 * Dr * dt); a.seed = seed; a.step = step;
     a.noise = noise_row; a.Lx = h->slab ? 0.0 : h->L; a.Ly = h->L;
-    k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
-    h->launches += 1;
+    a.phase = 0; a.strip_lo = a.strip_hi = 0.0; a.xlo = a.xhi = a.xhalo = 0.0; a.marks = h->marks;
+    a.disp_max = disp_slot >= 0 ? reinterpret_cast<unsigned *>(h->flags + disp_slot) : nullptr;
+    if (!phases) {
+        k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
+        h->launches += 1;
+    } else {
+        a.strip_lo = phases->strip_lo; a.strip_hi = phases->strip_hi; a.xlo = phases->lo; a.xhi = phases->hi; a.xhalo = phases->halo;
+        CK(cudaMemsetAsync(h->marks, 0, (size_t)n, h->stream));
+        a.phase = 1;
+        k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
+        if (after_strips) CK(cudaEventRecord(after_strips, h->stream));
+        a.phase = 2;
+        k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
+        h->launches += 2;
+    }
     CK(cudaGetLastError());
     return AFV_OK;
 }
@@ -470,7 +499,7 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
         if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete h; return AFV_ERR_CUDA; }
         h->own_stream = true;
     }
-    if (cudaMalloc((void **)&h->d_grid, sizeof(GridDesc)) != cudaSuccess || cudaMalloc((void **)&h->flags, 4 * sizeof(int)) != cudaSuccess ||
+    if (cudaMalloc((void **)&h->d_grid, sizeof(GridDesc)) != cudaSuccess || cudaMalloc((void **)&h->flags, 8 * sizeof(int)) != cudaSuccess ||
         cudaMalloc((void **)&h->bbox_part, 4 * 1024 * sizeof(double)) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
@@ -479,11 +508,11 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
         cudaMalloc((void **)&h->ovf_ro, (size_t)OVF_MAX * RS_SLOW * sizeof(RingOwn)) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
-    if (cudaMalloc((void **)&h->pair_cnt, 4 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 12 * sizeof(double)) != cudaSuccess ||
-        cudaHostAlloc((void **)&h->pair_host, 12 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaMalloc((void **)&h->pair_cnt, 4 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 16 * sizeof(double)) != cudaSuccess ||
+        cudaHostAlloc((void **)&h->pair_host, 16 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
-    cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream);
+    cudaMemsetAsync(h->flags, 0, 8 * sizeof(int), h->stream);
     cudaFuncSetAttribute(k_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(int));
 
     *out = h;
@@ -498,6 +527,8 @@ void afv_destroy(AfvHandle h) {
     cudaFree(h->d_grid); cudaFree(h->flags); cudaFree(h->bbox_part);
     cudaFree(h->ovf_cells); cudaFree(h->ovf_len); cudaFree(h->ovf_rs); cudaFree(h->ovf_ro);
     cudaFree(h->pair_cnt); cudaFree(h->pair_dev); cudaFreeHost(h->pair_host);
+    if (h->ev_strip) cudaEventDestroy(h->ev_strip);
+    if (h->ev_append) cudaEventDestroy(h->ev_append);
     for (DevBuf *b : {&h->scratch_a, &h->scratch_b, &h->noise_buf, &h->conn_buf, &h->ring_types, &h->ring_xy, &h->ring_off}) cudaFree(b->p);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -643,11 +674,18 @@ int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t s
     const bool deferred = h->defer_checks && !noise_host;
     if (!deferred) CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
     for (int s = 0; s < n_steps; ++s) {
-        if (deferred) CK(cudaMemsetAsync(h->flags, 0, sizeof(int), h->stream));   // the slow-path queue restarts every step
+        int disp_slot = -1;
+        if (deferred) {
+            CK(cudaMemsetAsync(h->flags, 0, sizeof(int), h->stream));   // the slow-path queue restarts every step
+            if (h->slab) {   // largest |dx| of the step, read by the next exchange (drives the overlapped form)
+                disp_slot = 4 + (int)(h->slab_steps++ & 1);
+                CK(cudaMemsetAsync(h->flags + disp_slot, 0, sizeof(int), h->stream));
+            }
+        }
         if ((rc = stage_sort(h))) return rc;
         // open boundaries: the local density is unknown, so the capacity is checked (and grown) before the positions move
         if ((rc = (h->L > 0.0 ? stage_geometry(h) : geometry_checked(h)))) return rc;
-        if ((rc = stage_force(h, true, dt, mu, v0, Dr, seed, step0 + s, noise_dev ? noise_dev + (size_t)s * h->n : nullptr))) return rc;
+        if ((rc = stage_force(h, true, dt, mu, v0, Dr, seed, step0 + s, noise_dev ? noise_dev + (size_t)s * h->n : nullptr, nullptr, nullptr, disp_slot))) return rc;
     }
     if (!deferred && (rc = check_flags(h))) return rc;   // also synchronises: noise_host is borrowed for the call only
     h->built = true;

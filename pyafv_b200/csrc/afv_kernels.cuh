@@ -142,7 +142,22 @@ struct ForceArgs {
     int64_t step;
     const double *noise;           // nullptr -> Philox; else row of this step, indexed by gid
     double Lx, Ly;                 // periodic wrap of the updated positions per direction (0 = none)
+    // two-phase update of a slab (phase != 0): phase 1 handles the cells in the face strips (x < strip_lo or
+    // x >= strip_hi before the update) and writes marks[s] = MARK_DONE | exchange lists of the updated position; phase 2
+    // handles the rest while the exchange of the strip cells is already under way on another stream.
+    int phase;
+    double strip_lo, strip_hi;
+    double xlo, xhi, xhalo;        // slab interval and halo width: the exchange lists of the updated positions
+    unsigned char *marks;
+    unsigned *disp_max;            // largest |dx| of the step as float bits (non-negative floats order like integers)
 };
+constexpr unsigned char MARK_DONE = 0x80;
+
+// exchange lists of an owned cell at x (bit q set = member of list q, see k_exchange_count)
+__device__ __forceinline__ unsigned xch_lists(double x, unsigned char own, double lo, double hi, double halo) {
+    if (own != CELL_OWNED) return 0u;
+    return (x < lo ? 1u : 0u) | ((x >= lo && x < lo + halo) ? 2u : 0u) | (x >= hi ? 4u : 0u) | ((x >= hi - halo && x < hi) ? 8u : 0u);
+}
 
 struct NbrRec { double gx, gy; const double *pw; };   // the arc weight is fetched only at outer vertices
 
@@ -200,7 +215,14 @@ __device__ __forceinline__ bool lookup_edge(const ForceArgs &a, int j, int self,
 __global__ void __launch_bounds__(128, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n) return;
-    if (!a.owned[s]) { a.fx[s] = 0.0; a.fy[s] = 0.0; return; }
+    if (a.phase == 1) {
+        const double x0 = a.xy[s].x;
+        if (!(x0 < a.strip_lo || x0 >= a.strip_hi)) return;
+        a.marks[s] = MARK_DONE;
+    } else if (a.phase == 2) {
+        if (a.marks[s] & MARK_DONE) return;
+    }
+    if (a.owned[s] != CELL_OWNED) { a.fx[s] = 0.0; a.fy[s] = 0.0; return; }
     int E = a.ring_len[s];
     const double r = a.ph.r, r2 = r * r;
     double dEx = 0.0, dEy = 0.0;
@@ -289,6 +311,15 @@ __global__ void __launch_bounds__(128, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
             xi_ = a.noise ? a.noise[id] : philox_normal(a.seed, id, a.step);
         }
         a.xy[s] = make_double2(xn, yn); a.theta[s] = th + a.noise_amp * xi_;
+        if (a.disp_max) {
+            const unsigned db = __float_as_uint(__double2float_ru(fabs(xn - pos.x)));
+            if (db > *reinterpret_cast<volatile unsigned *>(a.disp_max)) atomicMax(a.disp_max, db);
+        }
+        if (a.phase) {
+            const unsigned m = xch_lists(xn, CELL_OWNED, a.xlo, a.xhi, a.xhalo);
+            if (a.phase == 1) a.marks[s] = (unsigned char)(MARK_DONE | m);
+            else if (m) atomicAdd(&a.flags[3], 1);   // moved further than the strip margin in one step: the exchange missed it
+        }
     }
 }
 
@@ -440,18 +471,22 @@ __global__ void k_pack_message(const int *__restrict__ idx, const int *__restric
 // ---- the per-step exchange, three launches, no atomics (message order = slot order, reproducible) ----------------
 // exchange message = (cap+1, 5) rows: header [n_transfer, n_halo, 0, 0, 0], then the transfer rows (cells that change
 // owner) followed by the halo rows.
-// Owned cells fall into up to four lists: q = 0 transfers to the left rank (x < lo), 1 halo rows for the left rank
-// (lo <= x < lo + halo), 2 transfers to the right rank (x >= hi), 3 halo rows for the right rank (hi - halo <= x < hi).
+// Owned cells fall into up to four lists (xch_lists above): q = 0 transfers to the left rank (x < lo), 1 halo rows for
+// the left rank (lo <= x < lo + halo), 2 transfers to the right rank (x >= hi), 3 halo rows for the right rank
+// (hi - halo <= x < hi).  `marks` (optional): list bits already written by a two-phase k_force.
 constexpr int XCH_TPB = 256;
-__device__ __forceinline__ unsigned xch_lists(double x, unsigned char own, double lo, double hi, double halo) {
+__device__ __forceinline__ unsigned xch_lists_of(const double2 *xy, const unsigned char *owned, const unsigned char *marks, int i,
+                                                 double lo, double hi, double halo) {
+    const unsigned char own = owned[i];
     if (own != CELL_OWNED) return 0u;
-    return (x < lo ? 1u : 0u) | ((x >= lo && x < lo + halo) ? 2u : 0u) | (x >= hi ? 4u : 0u) | ((x >= hi - halo && x < hi) ? 8u : 0u);
+    return marks ? (unsigned)(marks[i] & 0x0f) : xch_lists(xy[i].x, own, lo, hi, halo);
 }
 // pass 1: members of every list per block
-__global__ void __launch_bounds__(XCH_TPB) k_exchange_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n,
-                                                            double lo, double hi, double halo, int *__restrict__ blk_cnt) {
+__global__ void __launch_bounds__(XCH_TPB) k_exchange_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned,
+                                                            const unsigned char *__restrict__ marks, int n, double lo, double hi, double halo,
+                                                            int *__restrict__ blk_cnt) {
     const int i = blockIdx.x * XCH_TPB + threadIdx.x;
-    const unsigned m = (i < n) ? xch_lists(xy[i].x, owned[i], lo, hi, halo) : 0u;
+    const unsigned m = (i < n) ? xch_lists_of(xy, owned, marks, i, lo, hi, halo) : 0u;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int c = __syncthreads_count((m >> q) & 1u);
@@ -509,8 +544,9 @@ __global__ void __launch_bounds__(1024) k_exchange_scan(const int *__restrict__ 
 // become CELL_DEAD (the next sort drops them), cells that left the slab stay as halo copies of their new owner's cell.
 __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__restrict__ xy, const double *__restrict__ th,
                                                            const double *__restrict__ a0, const int64_t *__restrict__ gid,
-                                                           unsigned char *__restrict__ owned, int n, double lo, double hi, double halo,
-                                                           double shift_left, double shift_right, const int *__restrict__ blk_off,
+                                                           unsigned char *__restrict__ owned, const unsigned char *__restrict__ marks, int n,
+                                                           double lo, double hi, double halo, double shift_left, double shift_right,
+                                                           const int *__restrict__ blk_off,
                                                            const int *__restrict__ totals, int cap, double *__restrict__ msg_left,
                                                            double *__restrict__ msg_right) {
     __shared__ int warp_cnt[XCH_TPB / 32][4];
@@ -518,8 +554,8 @@ __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__rest
     const int i = blockIdx.x * XCH_TPB + t;
     double2 p = make_double2(0.0, 0.0);
     unsigned char own = CELL_DEAD;
-    if (i < n) { p = xy[i]; own = owned[i]; }
-    const unsigned m = xch_lists(p.x, own, lo, hi, halo);
+    unsigned m = 0u;
+    if (i < n) { p = xy[i]; own = owned[i]; m = xch_lists_of(xy, owned, marks, i, lo, hi, halo); }
     int rank_in_warp[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -563,6 +599,7 @@ __global__ void k_gather_counts8(const int *__restrict__ c, const double *__rest
     out[0] = (double)c[0]; out[1] = (double)c[1]; out[2] = (double)c[2]; out[3] = (double)c[3];
     out[4] = in0 ? in0[0] : 0.0; out[5] = in0 ? in0[1] : 0.0; out[6] = in1 ? in1[0] : 0.0; out[7] = in1 ? in1[1] : 0.0;
     out[8] = (double)flags[0]; out[9] = (double)flags[1]; out[10] = (double)flags[2]; out[11] = (double)flags[3];
+    out[12] = (double)__int_as_float(flags[4]); out[13] = (double)__int_as_float(flags[5]);
 }
 // keep = !(owned && x in either range)
 __global__ void k_flag_keep2(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, double lo0, double hi0,

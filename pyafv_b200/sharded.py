@@ -84,6 +84,18 @@ class GpuCellStore:
     def finish_exchange(self, from_left: torch.Tensor, from_right: torch.Tensor, cap: int) -> None:
         self.h.call("afv_finish_exchange", from_left.data_ptr(), from_right.data_ptr(), int(cap))
 
+    def step_pack_overlapped(self, geo, cap: int, margin: float, exchange_stream: int, dt, mu, v0, Dr, seed, step_index):
+        """One step on the handle's stream with the face strips first; the next exchange's messages are packed on
+        ``exchange_stream`` while the interior is still being updated (``afv_step_pack_overlapped``)."""
+        ml, mr = self._msg("xl", cap), self._msg("xr", cap)
+        self.h.call("afv_step_pack_overlapped", float(dt), float(mu), float(v0), float(Dr), C.c_uint64(int(seed)), C.c_int64(int(step_index)),
+                    float(geo.lo), float(geo.hi), float(geo.halo), float(margin), float(geo.shift_to_left), float(geo.shift_to_right),
+                    ml.data_ptr(), mr.data_ptr(), int(cap), C.c_void_p(int(exchange_stream)))
+        return ml, mr
+
+    def finish_exchange_overlapped(self, from_left: torch.Tensor, from_right: torch.Tensor, cap: int, exchange_stream: int) -> None:
+        self.h.call("afv_finish_exchange_overlapped", from_left.data_ptr(), from_right.data_ptr(), int(cap), C.c_void_p(int(exchange_stream)))
+
     def _msg(self, key: str, cap: int) -> torch.Tensor:
         t = self._buf.get(key)
         if t is None or t.shape[0] != cap + 1:
@@ -171,10 +183,25 @@ class SlabShardedSimulator:
             the Philox noise stream is keyed by them, so results do not depend on the number of GPUs).
         A0: per-cell preferred areas (default ``phys.A0``).
         comm: communicator (default :class:`TorchDistComm`); ``None`` with ``world == 1``.
+        overlap: ``step()`` updates the cells near the slab faces first and runs the exchange for the next step on a
+            second stream while the interior cells are still being updated (default).  ``False``: exchange, then step.
+            The overlapped form needs a bound on how far a cell moves in one step, so it engages only while the
+            dynamics is calm: the largest |dx| of each of the last ``CALM_STEPS`` steps stayed below ``r``.  Violent
+            transients (e.g. the first steps from a random configuration) run as exchange-then-step, which tolerates
+            any displacement.
+        strip_margin: with ``overlap``, the bound on |dx| per step; engages the overlapped form unconditionally
+            (a violation raises at a later exchange).  Default: chosen by the library from the displacements it
+            observes (4 x the largest one + r/2).
+        exchange_stream: ``torch.cuda.Stream`` for the overlapped exchange (default: a new high-priority one).  For
+            the transport to overlap as well, create the NCCL process group with
+            ``pg_options=ProcessGroupNCCL.Options(is_high_priority_stream=True)``.
     """
 
+    CALM_STEPS = 8      # steps in a row with every |dx| < r before the overlapped form engages
+
     def __init__(self, pts, theta, phys, L: float, *, rank: int = 0, world: int = 1, device: int = 0, stream: int | None = None,
-                 gids=None, A0=None, halo_width: float | None = None, comm=None):
+                 gids=None, A0=None, halo_width: float | None = None, comm=None, overlap: bool = True,
+                 strip_margin: float | None = None, exchange_stream=None):
         from . import _lib
         from .finite_voronoi import _as_params
         self.phys, self.L, self.rank, self.world = phys, float(L), rank, world
@@ -200,6 +227,15 @@ class SlabShardedSimulator:
         self.store.set_cells(torch.from_numpy(rows).to(self.device), n)
         self._step_index = 0
         self._cap = None
+        self._halo_fresh = False          # the halo copies on the device belong to the current positions
+        self.overlap = bool(overlap) and world > 1
+        self.strip_margin = 0.0 if strip_margin is None else float(strip_margin)      # <= 0: adaptive
+        self._dx_hist = []                # largest |dx| of the recent steps, newest last
+        self.overlapped_steps = 0         # steps taken in the overlapped form so far
+        self._xs = None
+        if self.overlap:
+            # high priority: its blocks are dispatched ahead of the pending blocks of the interior update
+            self._xs = exchange_stream if exchange_stream is not None else torch.cuda.Stream(self.device, priority=-1)
 
     @property
     def n_owned(self) -> int:
@@ -226,10 +262,46 @@ class SlabShardedSimulator:
 
     def exchange_in(self, from_left, from_right) -> None:
         self.store.finish_exchange(from_left, from_right, self._caps()[0])
+        self._halo_fresh = True
+        self._note_displacement()
+
+    def _note_displacement(self) -> None:
+        dx = C.c_double(-1.0)
+        self._h.call("afv_get_max_displacement", C.byref(dx))
+        if dx.value >= 0.0:
+            self._dx_hist = (self._dx_hist + [dx.value])[-self.CALM_STEPS:]
+
+    def _overlap_engaged(self) -> bool:
+        if not self.overlap:
+            return False
+        if self.strip_margin > 0.0:
+            return True
+        return len(self._dx_hist) == self.CALM_STEPS and max(self._dx_hist) < self.phys.r
+
+    def step_and_pack(self, dt, mu, v0, Dr, seed):
+        """Overlapped phase 1: one step (needs fresh halo copies) + the messages of the next exchange, packed on the
+        exchange stream as soon as the cells near the faces are updated."""
+        msgs = self.store.step_pack_overlapped(self.geo, self._caps()[0], self.strip_margin, self._xs.cuda_stream, dt, mu, v0, Dr, seed,
+                                               self._step_index)
+        self._step_index += 1
+        self.overlapped_steps += 1
+        self._halo_fresh = False
+        return msgs
+
+    def exchange_in_overlapped(self, from_left, from_right) -> None:
+        """Overlapped phase 2 (after the transport on the exchange stream): append what arrived."""
+        self.store.finish_exchange_overlapped(from_left, from_right, self._caps()[0], self._xs.cuda_stream)
+        self._halo_fresh = True
+        self._note_displacement()
+
+    def _refresh_halo(self) -> None:
+        if self.world > 1 and not self._halo_fresh:
+            self.exchange_in(*self.comm.exchange_fixed(*self.exchange_out()))
 
     def compute_step(self, dt, mu, v0, Dr, seed, want_results: bool = False):
         self._h.call("afv_step", float(dt), float(mu), float(v0), float(Dr), C.c_uint64(int(seed)), C.c_int64(self._step_index), 1, None)
         self._step_index += 1
+        self._halo_fresh = False
         # rows of the owned cells: updated x, y, theta + F, A, P, L, z.  The halo copies stay until the next exchange
         # retires them (pack_exchange), which costs nothing extra; drop_halo() is the explicit form.
         return self.store.results() if want_results else None
@@ -242,17 +314,22 @@ class SlabShardedSimulator:
     # -- the per-rank drivers (one process per GPU) ---------------------------------------------------------
     def step(self, dt: float, mu: float = 1.0, v0: float = 0.0, Dr: float = 0.0, *, seed: int = 0, n_steps: int = 1) -> None:
         """``n_steps`` of: one exchange with the ring neighbours (cells that left the slab during the previous update
-        change owner, halo cells are refreshed), then the fused build + force + update."""
+        change owner, halo cells are refreshed), then the fused build + force + update.  With ``overlap`` the exchange
+        for step k+1 runs on the exchange stream while step k is still updating its interior cells."""
         for _ in range(n_steps):
-            if self.world > 1:
-                self.exchange_in(*self.comm.exchange_fixed(*self.exchange_out()))
-            self.compute_step(dt, mu, v0, Dr, seed)
+            self._refresh_halo()          # a no-op after an overlapped step: it leaves fresh halo copies behind
+            if self._overlap_engaged():
+                msgs = self.step_and_pack(dt, mu, v0, Dr, seed)
+                with torch.cuda.stream(self._xs):
+                    inbox = self.comm.exchange_fixed(*msgs)
+                self.exchange_in_overlapped(*inbox)
+            else:
+                self.compute_step(dt, mu, v0, Dr, seed)
 
     def build(self) -> dict[str, np.ndarray]:
         """Forces and geometry of the owned cells (keys of the reference's merged dict, ``parallel_voronoi.py:596-611``,
         plus ``gids`` and ``pts``)."""
-        if self.world > 1:
-            self.exchange_in(*self.comm.exchange_fixed(*self.exchange_out()))
+        self._refresh_halo()
         return results_dict(self.compute_build())
 
     def e2e_measure(self, k: int, step: dict) -> dict:
@@ -275,7 +352,8 @@ class SlabShardedSimulator:
         for _ in range(k):
             dev.copy_(host, non_blocking=True)
             self.store.set_cells(dev, n)
-            self.exchange_in(*self.comm.exchange_fixed(*self.exchange_out()))
+            self._halo_fresh = False
+            self._refresh_halo()
             r = self.compute_step(step["dt"], step["mu"], step["v0"], step["Dr"], 7, want_results=True)
             out[: r.shape[0]].copy_(r, non_blocking=True)
             torch.cuda.synchronize()
@@ -302,7 +380,8 @@ def results_dict(res: torch.Tensor) -> dict[str, np.ndarray]:
 class LoopbackShardedSimulator:
     """``world`` slabs driven from one process on one device; same phases as the distributed run."""
 
-    def __init__(self, pts, theta, phys, L: float, world: int, *, device: int = 0, A0=None, halo_width=None):
+    def __init__(self, pts, theta, phys, L: float, world: int, *, device: int = 0, A0=None, halo_width=None, overlap: bool = False,
+                 strip_margin=None):
         pts = np.asarray(pts, dtype=np.float64)
         N = pts.shape[0]
         theta = np.zeros(N) if theta is None else np.asarray(theta, dtype=np.float64)
@@ -311,25 +390,34 @@ class LoopbackShardedSimulator:
         owner = np.minimum((pts[:, 0] // W).astype(int), world - 1)
         self.ranks = []
         stream = torch.cuda.current_stream(torch.device("cuda", device)).cuda_stream   # one stream for every rank
+        self.overlap = bool(overlap) and world > 1
+        xs = torch.cuda.Stream(torch.device("cuda", device), priority=-1) if self.overlap else None   # and one exchange stream
         for rk in range(world):
             m = owner == rk
             self.ranks.append(SlabShardedSimulator(pts[m], theta[m], phys, L, rank=rk, world=world, device=device,
-                                                   gids=np.flatnonzero(m), A0=A0[m], halo_width=halo_width, comm=False, stream=stream))
+                                                   gids=np.flatnonzero(m), A0=A0[m], halo_width=halo_width, comm=False, stream=stream,
+                                                   overlap=self.overlap, strip_margin=strip_margin, exchange_stream=xs))
         self.world, self.N = world, N
+
+    def _refresh_halo(self) -> None:
+        if self.world > 1 and not all(s._halo_fresh for s in self.ranks):
+            for sim, inbox in zip(self.ranks, loopback_exchange([s.exchange_out() for s in self.ranks])):
+                sim.exchange_in(*inbox)
 
     def step(self, dt, mu=1.0, v0=0.0, Dr=0.0, *, seed=0, n_steps=1) -> None:
         for _ in range(n_steps):
-            if self.world > 1:
-                for sim, inbox in zip(self.ranks, loopback_exchange([s.exchange_out() for s in self.ranks])):
-                    sim.exchange_in(*inbox)
-            for sim in self.ranks:
-                sim.compute_step(dt, mu, v0, Dr, seed)
+            self._refresh_halo()
+            if self.overlap and all(sim._overlap_engaged() for sim in self.ranks):
+                msgs = [sim.step_and_pack(dt, mu, v0, Dr, seed) for sim in self.ranks]
+                for sim, inbox in zip(self.ranks, loopback_exchange(msgs)):
+                    sim.exchange_in_overlapped(*inbox)
+            else:
+                for sim in self.ranks:
+                    sim.compute_step(dt, mu, v0, Dr, seed)
 
     def build(self) -> dict[str, np.ndarray]:
         """Merged dict in global cell order (the reference's ``_merge_results``)."""
-        if self.world > 1:
-            for sim, inbox in zip(self.ranks, loopback_exchange([s.exchange_out() for s in self.ranks])):
-                sim.exchange_in(*inbox)
+        self._refresh_halo()
         parts = [results_dict(sim.compute_build()) for sim in self.ranks]
         out = {}
         gids = np.concatenate([p["gids"] for p in parts])
