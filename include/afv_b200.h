@@ -188,7 +188,7 @@ int afv_finish_exchange(AfvHandle h, const double *in_left_dev, const double *in
  * halo cells fresh (one afv_pack_exchange / afv_finish_exchange before the first call).  margin bounds the distance in
  * x a cell may move in one step (a violation is reported as AFV_ERR_CAPACITY by a later finish); margin <= 0: the
  * handle chooses it -- every owned cell counts as a face cell in the first step, afterwards 4 x the largest |dx| of the
- * previous steps + r/2.  Per-cell results of the step are not kept (use afv_step + afv_pack_owned when they are
+ * previous steps + r/2, at least 8 r.  Per-cell results of the step are not kept (use afv_step + afv_pack_owned when they are
  * needed). */
 int afv_step_pack_overlapped(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t seed, int64_t step, double lo, double hi,
                              double halo, double margin, double shift_left, double shift_right, double *msg_left_dev,

@@ -184,14 +184,14 @@ class SlabShardedSimulator:
         A0: per-cell preferred areas (default ``phys.A0``).
         comm: communicator (default :class:`TorchDistComm`); ``None`` with ``world == 1``.
         overlap: ``step()`` updates the cells near the slab faces first and runs the exchange for the next step on a
-            second stream while the interior cells are still being updated (default).  ``False``: exchange, then step.
-            The overlapped form needs a bound on how far a cell moves in one step, so it engages only while the
+            second stream while the interior cells are still being updated.  ``False`` (default): exchange, then step,
+            which is exact for any displacement.  The overlapped form needs a bound on how far a cell moves in one step, so it engages only while the
             dynamics is calm: the largest |dx| of each of the last ``CALM_STEPS`` steps stayed below ``r``.  Violent
             transients (e.g. the first steps from a random configuration) run as exchange-then-step, which tolerates
             any displacement.
         strip_margin: with ``overlap``, the bound on |dx| per step; engages the overlapped form unconditionally
             (a violation raises at a later exchange).  Default: chosen by the library from the displacements it
-            observes (4 x the largest one + r/2).
+            observes (4 x the largest one + r/2, at least 8 r).
         exchange_stream: ``torch.cuda.Stream`` for the overlapped exchange (default: a new high-priority one).  For
             the transport to overlap as well, create the NCCL process group with
             ``pg_options=ProcessGroupNCCL.Options(is_high_priority_stream=True)``.
@@ -200,7 +200,7 @@ class SlabShardedSimulator:
     CALM_STEPS = 8      # steps in a row with every |dx| < r before the overlapped form engages
 
     def __init__(self, pts, theta, phys, L: float, *, rank: int = 0, world: int = 1, device: int = 0, stream: int | None = None,
-                 gids=None, A0=None, halo_width: float | None = None, comm=None, overlap: bool = True,
+                 gids=None, A0=None, halo_width: float | None = None, comm=None, overlap: bool = False,
                  strip_margin: float | None = None, exchange_stream=None):
         from . import _lib
         from .finite_voronoi import _as_params
