@@ -398,9 +398,12 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_hull(GeomArgs a, 
 #ifndef RING_MIN_BLOCKS
 #define RING_MIN_BLOCKS 6
 #endif
-__global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) {
-    const int s = blockIdx.x * HULL_TPB + threadIdx.x;
-    const bool live = s < a.n;
+// POOL = false: the fast path, every lane of the warp calls it (warp-uniform loop bounds), records slot-major, at most
+// RS entries; a longer ring queues the cell.  POOL = true: one queued cell per thread (k_geometry_slow), records into
+// slot `pool_idx` of the overflow pool, at most RING_POOL_FAST entries; returns false when even that is too short.
+constexpr int RING_POOL_FAST = 32;               // bounded by the 32-bit arc mask
+template <bool POOL>
+__device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const bool live, const int pool_idx) {
     const double r = a.ph.r, B4 = 4.0 * r;
     const GridDesc g = *a.grid;
     double xi = 0.0, yi = 0.0;
@@ -437,12 +440,15 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     //      kernel keeps no per-thread arrays at all. ----
     const double r2 = r * r;
     const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
-    RingOwn *const ro = a.ro + s;                 // slot-major: entry e at ro[e * ros]
-    RingSelf *const self = a.self + s;
-    const size_t ros = a.stride;
-    int *const key = a.ring_key + (size_t)s * RS;
+    // slot-major: entry e at ro[e * ros]; inside the pool the records of a cell are contiguous (RingShared and RingSelf
+    // have the same layout)
+    RingOwn *const ro = POOL ? a.ovf_ro + (size_t)pool_idx * RS_SLOW : a.ro + s;
+    RingSelf *const self = POOL ? reinterpret_cast<RingSelf *>(a.ovf_rs + (size_t)pool_idx * RS_SLOW) : a.self + s;
+    const size_t ros = POOL ? 1 : a.stride;
+    int *const key = a.ring_key + (size_t)s * RS;   // the compact key row k_force scans (fast path only)
+    constexpr int ECAP = POOL ? RING_POOL_FAST : RS;
     const int mm = m;
-    const int mloop = __reduce_max_sync(FULL_MASK, mm);
+    const int mloop = POOL ? mm : __reduce_max_sync(FULL_MASK, mm);
     // Junction between the counter-clockwise consecutive polygon edges A (slot ja, displacement a) and B (jb, b):
     // the END of A and the START of B.  Normally one point, the intersection of the two bisectors (a proper left
     // turn, a x b > 0).  Next to the edge at infinity -- or for a degenerate turn -- the bisector runs off to
@@ -482,10 +488,10 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
             o.gy = xp * x + yp * y;              // v1 . v2
         }
         self[(E - 1) * ros] = o;
-        key[E - 1] = nbr_p;
+        if (!POOL) key[E - 1] = nbr_p;
     };
     auto emit = [&](double x, double y, double ex, double ey, int nb) {
-        if (E >= RS) { ok = false; return; }
+        if (E >= ECAP) { ok = false; return; }
         if (E > 0) close_prev(x, y); else { x0 = x; y0 = y; }
         RingOwn q; q.hx = x; q.hy = y; q.px = ex; q.py = ey;
         ro[E * ros] = q;
@@ -532,7 +538,8 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     const bool ringed = live && ok && !queued && E >= 2;
     if (ringed) close_prev(x0, y0);              // closing edge: last entry -> first entry
 
-    if (live && !ok) {                           // ring longer than the stride: queue the cell for the large-capacity kernel
+    if (POOL && !ok) return false;               // the caller falls back to the clipping path
+    if (!POOL && live && !ok) {                  // ring longer than the stride: queue the cell for the large-capacity kernel
         const int idx = atomicAdd(&a.flags[0], 1);
         if (idx < OVF_MAX) a.ovf_cells[idx] = s; else atomicAdd(&a.flags[3], 1);
         a.ring_len[s] = 0;
@@ -547,7 +554,7 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     double Larc = 0.0;
     {
         unsigned rem = ringed ? arcmask : 0u;
-        const int aloop = __reduce_max_sync(FULL_MASK, __popc(rem));
+        const int aloop = POOL ? __popc(rem) : __reduce_max_sync(FULL_MASK, __popc(rem));
         for (int q = 0; q < aloop; ++q) {
             if (rem) {
                 const int e = __ffs(rem) - 1;
@@ -564,7 +571,8 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     double cA = 0.0, cP = 0.0, cL = 0.0;
     if (ringed) {
         a.area[s] = A; a.perim[s] = P; a.arcl[s] = Larc; a.coord[s] = z;
-        a.ring_len[s] = (unsigned char)E;
+        if (POOL) { a.ring_len[s] = RING_IN_POOL; a.ovf_index[s] = pool_idx; a.ovf_len[pool_idx] = E; }
+        else a.ring_len[s] = (unsigned char)E;
         if (E > 12) atomicMax(&a.flags[2], E);
         cA = 2.0 * a.ph.KA * (A - a.a0[s]);
         cP = 2.0 * a.ph.KP * (P - a.ph.P0);
@@ -574,7 +582,7 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
     // ---- per-vertex gradients of this cell (cell_geom.pyx:478-539), streamed over the ring records ----
     {
         const int EE = ringed ? E : 0;
-        const int Eloop = __reduce_max_sync(FULL_MASK, EE);
+        const int Eloop = POOL ? EE : __reduce_max_sync(FULL_MASK, EE);
         // software pipeline: the record of entry e+2 (vertex position, 1/length scratch) is requested while vertex e is
         // being processed; entry e's scratch is only overwritten after its last use
         double hpx = 0.0, hpy = 0.0, hcx = 0.0, hcy = 0.0, hnx = 0.0, hny = 0.0, ilp = 0.0, ilc = 0.0, iln = 0.0;
@@ -610,6 +618,12 @@ __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) 
             }
         }
     }
+    return true;
+}
+
+__global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) {
+    const int s = blockIdx.x * HULL_TPB + threadIdx.x;
+    ring_cell<false>(a, s, s < a.n, 0);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -655,6 +669,10 @@ __device__ __noinline__ void geom_cell_slow(const GeomArgs &a, const int s, cons
 
 __global__ void __launch_bounds__(64) k_geometry_slow(GeomArgs a) {
     const int cnt = min(a.flags[0], OVF_MAX);
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x)
-        geom_cell_slow(a, a.ovf_cells[idx], idx);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x) {
+        const int s = a.ovf_cells[idx];
+        // queued by k_ring (its polygon is fine, only the ring outgrew the stride): emit the ring again, into the pool;
+        // queued by k_hull, or a ring beyond RING_POOL_FAST: clip from scratch
+        if (a.hull_len[s] == HULL_QUEUED || !ring_cell<true>(a, s, true, idx)) geom_cell_slow(a, s, idx);
+    }
 }

@@ -206,6 +206,38 @@ def test_many_neighbour_cell_uses_overflow_pool(n_ring, radius):
     sim.close()
 
 
+@pytest.mark.parametrize("n_ring", [9, 12, 15])
+def test_long_ring_with_short_polygon_is_emitted_into_the_pool(n_ring):
+    """n_ring <= 16 neighbours whose bisectors each cut the disk separately: the polygon fits the fast path but the ring
+    (entry + exit point per neighbour, arcs in between) has 2 n_ring > 16 entries.  k_ring queues the cell and the slow
+    kernel emits the ring again from the same polygon, into the pool."""
+    import pyafv_b200 as afv
+    from afv_oracle import oracle_build
+    rng = np.random.default_rng(100 + n_ring)
+    ang = 2 * np.pi * (np.arange(n_ring) + 0.05 * rng.random(n_ring)) / n_ring
+    ringpts = (1.97 + 0.01 * rng.random(n_ring))[:, None] * np.column_stack((np.cos(ang), np.sin(ang)))
+    filler = (rng.random((400, 2)) - 0.5) * 30.0
+    filler = filler[np.hypot(filler[:, 0], filler[:, 1]) > 4.2]
+    pts = np.vstack([[0.0, 0.0], ringpts, filler]) + 15.0
+    sim = afv.FiniteVoronoiSimulator(pts, afv.PhysicalParams())
+    d = sim.build()
+    o = oracle_build(pts, rings=True)
+    n_expect = int(o["ring_off"][1] - o["ring_off"][0])
+    assert 16 < n_expect <= 32 and n_expect == 2 * n_ring
+    for k in ("areas", "perimeters", "arclens", "forces"):
+        _close(d[k], o[k], k)
+    assert np.array_equal(d["coord_nums"], o["coord_nums"]) and d["coord_nums"][0] == n_ring
+    assert np.array_equal(d["connections"], o["connections"])
+    assert len(d["regions"][0]) == n_expect
+    diag = sim.diagnostics()
+    assert diag["slow_path_cells"] >= 1 and diag["lookup_misses"] == 0 and diag["max_ring_len"] == n_expect
+    # and the same over a few fused steps (the pooled ring is looked up by its neighbours' force gathers)
+    sim.step(1e-3, 1.0, 0.0, 0.0, n_steps=3)
+    o2 = oracle_build(sim.pts)
+    _close(sim.build(connect=False, rings=False)["forces"], o2["forces"], "forces after 3 steps")
+    sim.close()
+
+
 def test_parallel_simulator_equals_serial():
     """tests/test_parallel.py:112-176 of the reference: the parallel API returns the serial results."""
     import pyafv_b200 as afv
