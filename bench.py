@@ -268,7 +268,7 @@ def run_ours(args) -> dict:
                                       f"(BASELINE config[{3 if world == 1 else 4}] shape), {cells} cells/GPU, x-slabs",
                           "cells_per_gpu": cells, "box_L": L, **STEP,
                           "exchange": ("none (1 GPU)" if world == 1 else "per step, NCCL point-to-point with both ring neighbours, " +
-                                       ("overlapped with the interior update of the previous step while the dynamics is calm" if args.overlap else "then step")),
+                                       ("overlapped with the sort and the interior geometry of the step (late cells)" if args.overlap else "then step")),
                           "exchange_overlapped_steps": ov_steps,
                           "l2_policy": "per-step working set (ring records "
                           f"{n_local * 1024 / 1e6:.0f} MB + state) exceeds the 126 MB L2; no explicit flush"},
@@ -400,8 +400,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--reference-cells", type=int, default=200_000)
-    ap.add_argument("--overlap", action="store_true", help="N > 1: let the exchange for the next step overlap the interior update "
-                    "whenever the dynamics is calm (it never is for this workload: see DESIGN.md section 5); default: exchange, then step")
+    ap.add_argument("--overlap", action="store_true", help="N > 1: the exchange of a step travels while the step sorts its cells and "
+                    "builds its interior geometry (late cells); default: exchange, then step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

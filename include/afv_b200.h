@@ -195,6 +195,29 @@ int afv_step_pack_overlapped(AfvHandle h, double dt, double mu, double v0, doubl
                              double *msg_right_dev, int64_t cap_rows, void *exchange_stream);
 int afv_finish_exchange_overlapped(AfvHandle h, const double *in_left_dev, const double *in_right_dev, int64_t cap_rows,
                                    void *exchange_stream);
+/* Exchange overlapped with the geometry of the interior cells, exact for any displacement ("late cells").  Per step:
+ *   afv_late_step_begin   handle's stream: sort of the cells on the device, geometry of the interior cells;
+ *   afv_late_finish       exchange stream: one synchronisation (of that stream only) for the counts of the messages
+ *                         packed after the previous update, then the received rows are appended behind the sorted
+ *                         cells as "late" cells with a bin table of their own;
+ *   afv_late_step_end     handle's stream: geometry of the cells in the face columns and of the late cells (both
+ *                         tables in view; of every cell when a received transfer landed beyond the face columns, which
+ *                         the sender flags in header slot 2), force gather + update of every owned cell (as afv_step
+ *                         with n_steps = 1 and the built-in generator); then, on the exchange stream, the messages of
+ *                         the next exchange.  The caller moves them on that stream and loops.
+ * Before the first afv_late_step_begin: afv_pack_exchange + transport on the handle's stream.  To leave the loop:
+ * afv_stream_wait(h, exchange_stream), then afv_finish_exchange with the last messages received.  Needs afv_set_slab
+ * and afv_set_deferred_checks(1); cap_rows as for afv_pack_exchange (room for 2 cap_rows cells is reserved). */
+int afv_late_step_begin(AfvHandle h, int64_t cap_rows);
+int afv_late_finish(AfvHandle h, const double *in_left_dev, const double *in_right_dev, int64_t cap_rows, void *exchange_stream);
+int afv_late_step_end(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t seed, int64_t step, double lo, double hi,
+                      double halo, double shift_left, double shift_right, double *msg_left_dev, double *msg_right_dev,
+                      int64_t cap_rows, void *exchange_stream);
+/* [0] steps taken in the late form, [1] of those, steps whose face pass covered every cell (a received transfer had
+ * landed beyond the face columns), [2] late cells of the last step, [3] face columns per side */
+int afv_get_exchange_stats(AfvHandle h, int64_t out[4]);
+/* make the handle's stream wait for everything issued so far on other_stream */
+int afv_stream_wait(AfvHandle h, void *other_stream);
 /* Largest |dx| any owned cell moved in one of the last two slab steps (deferred checks), as read by the last
  * afv_finish_exchange[_overlapped]; -1 before the first such step.  A driver uses it to decide when the overlapped
  * form is safe (calm dynamics) and when to fall back to exchange-then-step, which tolerates any displacement. */

@@ -41,6 +41,16 @@ struct AfvContext {
     GridDesc grid_host{};        // last grid description uploaded to d_grid (periodic / slab mode)
     bool grid_uploaded = false;
     int64_t n_dead = 0;          // cells marked CELL_DEAD (counted in n) that the next sort drops
+    // late cells: appended behind the sorted cells after the sort of the step (overlapped exchange), slots n_main .. n-1
+    int64_t n_main = 0, n_late = 0;
+    int *bin_start_late = nullptr;     // their bin table (entries relative to n_main)
+    bool late_deep = false;            // a received cell lies beyond the face columns: the face pass covers every cell
+    int face_cols = 0;
+    int64_t face_len0 = 0, face_s1 = 0;   // sorted cells in the first face_cols columns / first slot of the last face_cols columns
+    DevBuf late_keys, late_keys_sorted, late_perm, late_tmp;
+    cudaEvent_t ev_sorted = nullptr, ev_late = nullptr, ev_force = nullptr, ev_pack = nullptr;
+    int64_t late_steps = 0, late_deep_steps = 0;   // steps taken in the late form / of those, with the face pass over every cell
+    bool pack_pending = false;         // ev_pack was recorded: the next sort waits for the ownership marks of that pack
     bool gid_is_perm = true;  // gid is a permutation of 0..n-1 (single-GPU use); false after set_cells_device
     // SoA state, double-buffered for the reorder
     double2 *xy[2] = {nullptr, nullptr};
@@ -80,8 +90,8 @@ struct AfvContext {
     bool defer_checks = false;  // afv_step returns without synchronising; the flags are read at the next exchange / synchronize
     // pair exchange state (afv_pack_pair -> afv_finish_pair)
     int *pair_cnt = nullptr;       // device: list lengths of the last pack (2 for the pair form, 4 for the exchange)
-    double *pair_host = nullptr;   // pinned [16]: counts sent / received, the deferred flags, the displacement slots
-    double *pair_dev = nullptr;    // device [16]
+    double *pair_host = nullptr;   // pinned [20]: counts sent / received, the deferred flags, the displacement slots
+    double *pair_dev = nullptr;    // device [20]
     double pair_rng[4] = {0, 0, 0, 0};
     // overlapped step + exchange: the face strips are done (ev_strip) / the received cells are appended (ev_append)
     cudaEvent_t ev_strip = nullptr, ev_append = nullptr;
@@ -147,6 +157,7 @@ void free_all(AfvHandle h) {
     cudaFree(h->ring_key); h->ring_key = nullptr;
     cudaFree(h->hull_slot); h->hull_slot = nullptr; cudaFree(h->hull_len); h->hull_len = nullptr;
     cudaFree(h->marks); h->marks = nullptr;
+    cudaFree(h->bin_start_late); h->bin_start_late = nullptr;
     h->keys = h->keys_sorted = nullptr; h->iota = h->perm = h->bin_start = nullptr; h->cub_tmp = nullptr;
     h->fx = h->fy = h->area = h->perim = h->arcl = nullptr; h->coord = nullptr; h->ring_len = nullptr;
     h->ro = nullptr; h->cnt = h->off = nullptr;
@@ -195,6 +206,7 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     if ((rc = dev_alloc(h, &h->iota, cap))) return rc;
     if ((rc = dev_alloc(h, &h->perm, cap))) return rc;
     if ((rc = dev_alloc(h, &h->bin_start, (size_t)h->nbins_cap + 2))) return rc;
+    if ((rc = dev_alloc(h, &h->bin_start_late, (size_t)h->nbins_cap + 2))) return rc;
     if ((rc = dev_alloc(h, &h->fx, cap))) return rc;
     if ((rc = dev_alloc(h, &h->fy, cap))) return rc;
     if ((rc = dev_alloc(h, &h->area, cap))) return rc;
@@ -228,7 +240,8 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
 struct StageTimer {
     AfvHandle h;
     int idx = -1;
-    StageTimer(AfvHandle h_, int stage) : h(h_) {
+    cudaStream_t st;
+    StageTimer(AfvHandle h_, int stage, cudaStream_t stream = nullptr) : h(h_), st(stream ? stream : h_->stream) {
         if (!h->profiling) return;
         AfvContext::Span sp;
         sp.stage = stage;
@@ -239,12 +252,12 @@ struct StageTimer {
             return e;
         };
         sp.a = get(); sp.b = get();
-        cudaEventRecord(sp.a, h->stream);
+        cudaEventRecord(sp.a, st);
         h->spans.push_back(sp);
         idx = (int)h->spans.size() - 1;
     }
     ~StageTimer() {
-        if (idx >= 0) cudaEventRecord(h->spans[idx].b, h->stream);
+        if (idx >= 0) cudaEventRecord(h->spans[idx].b, st);
     }
 };
 
@@ -280,6 +293,8 @@ void periodic_grid(AfvHandle h, GridDesc &g) {
     g.inv_bx = (double)nbx / wx; g.inv_by = (double)nby / h->L;
     g.Lx = h->L; g.halfLx = 0.5 * h->L; g.Ly = h->L; g.halfLy = 0.5 * h->L;
     g.nbx = nbx; g.nby = nby; g.perx = h->slab ? 0 : 1; g.pery = 1;
+    g.swap = h->slab ? 1 : 0;   // x-slabs: columns contiguous, so that the face columns are the two ends of the sorted order
+    g.pad_ = 0;
 }
 
 int upload_grid_periodic(AfvHandle h) {
@@ -324,6 +339,7 @@ int stage_sort(AfvHandle h) {
                                                         h->xy[o], h->th[o], h->a0[o], h->gid[o], h->owned[o]);
     h->cur = o;
     h->n = n; h->n_dead = 0;
+    h->n_main = n; h->n_late = 0; h->late_deep = false;
     if (h->L > 0.0) {
         GridDesc g{};
         periodic_grid(h, g);
@@ -335,14 +351,29 @@ int stage_sort(AfvHandle h) {
     return AFV_OK;
 }
 
-int stage_geometry(AfvHandle h) {
-    const int n = (int)h->n;
+// which cells a geometry launch covers (slab sharding with the exchange overlapped; the default is every cell)
+struct GeomPass {
+    int filter = 0;        // 0 every cell, 1 interior cells only (placed by the sort, away from the face columns), 2 the others
+    bool late = false;     // look at the late cells' bin table as well
+    bool slow = true;      // run the queue of the slow path afterwards (once per step, after the last pass)
+    bool fast = true;      // run k_hull / k_ring (false: only the slow-path queue)
+    cudaStream_t stream = nullptr;   // nullptr: the handle's stream
+};
+
+int stage_geometry(AfvHandle h, GeomPass gp = GeomPass()) {
+    // threads with work: every cell; the sorted cells (interior pass: the face columns drop out per thread); or, dense, the
+    // cells of the face columns + the late cells
+    const int64_t face_len1 = h->n_main - h->face_s1;
+    const int n = (int)(gp.filter == 1 ? h->n_main : (gp.filter == 2 ? h->face_len0 + face_len1 + h->n_late : h->n));
     const int c = h->cur;
     GeomArgs a;
+    a.face_len0 = (int)h->face_len0; a.face_len1 = (int)face_len1; a.face_s1 = (int)h->face_s1;
     a.xy = h->xy[c]; a.a0 = h->a0[c]; a.keys = h->keys_sorted; a.bin_start = h->bin_start; a.grid = h->d_grid;
     a.n = n; a.ph = phys_dev(h->prm); a.ro = h->ro; a.self = h->self; a.stride = (size_t)h->cap; a.ring_len = h->ring_len; a.ring_key = h->ring_key; a.hull_slot = h->hull_slot; a.hull_len = h->hull_len;
     a.area = h->area; a.perim = h->perim; a.arcl = h->arcl; a.coord = h->coord; a.flags = h->flags;
     a.ovf_cells = h->ovf_cells; a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
+    a.n_main = (int)h->n_main; a.bin_start_late = (gp.late && h->n_late > 0) ? h->bin_start_late : nullptr;
+    a.filter = gp.filter; a.face_cols = h->face_cols;
     // candidate-list capacity per cell (shared memory scales with it): for a periodic box the mean number of cells
     // within 2r is known, 4 pi r^2 N / L^2; otherwise start at 32 and grow when the slow path gets busy
     if (h->L > 0.0) {
@@ -352,18 +383,27 @@ int stage_geometry(AfvHandle h) {
     }
     int cmax = h->cmax_hint;
     const size_t smem = (size_t)cmax * HULL_TPB * sizeof(int);
-    {
-        StageTimer t(h, 1);
-        k_hull<<<nblk(n, HULL_TPB), HULL_TPB, smem, h->stream>>>(a, cmax);
+    cudaStream_t st = gp.stream ? gp.stream : h->stream;
+    if (n > 0 && gp.fast) {
+        {
+            StageTimer t(h, 1, st);
+            if (h->slab) k_hull<true><<<nblk(n, HULL_TPB), HULL_TPB, smem, st>>>(a, cmax);
+            else k_hull<false><<<nblk(n, HULL_TPB), HULL_TPB, smem, st>>>(a, cmax);
+        }
+        {
+            StageTimer t(h, 2, st);
+            if (h->slab) k_ring<true><<<nblk(n, HULL_TPB), HULL_TPB, 0, st>>>(a);
+            else k_ring<false><<<nblk(n, HULL_TPB), HULL_TPB, 0, st>>>(a);
+        }
+        h->launches += 2;
     }
-    {
-        StageTimer t(h, 2);
-        k_ring<<<nblk(n, HULL_TPB), HULL_TPB, 0, h->stream>>>(a);
+    if (gp.slow) {
+        StageTimer t(h, 5, st);
+        // cells queued by the fast kernels (usually none): large-capacity path, reads the queue length on the device
+        a.filter = 0;
+        k_geometry_slow<<<16, 64, 0, st>>>(a);
+        h->launches += 1;
     }
-    StageTimer t(h, 5);
-    // cells queued by the fast kernel (usually none): large-capacity path, reads the queue length on the device
-    k_geometry_slow<<<16, 64, 0, h->stream>>>(a);
-    h->launches += 3;
     CK(cudaGetLastError());
     return AFV_OK;
 }
@@ -508,12 +548,13 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
         cudaMalloc((void **)&h->ovf_ro, (size_t)OVF_MAX * RS_SLOW * sizeof(RingOwn)) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
-    if (cudaMalloc((void **)&h->pair_cnt, 4 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 16 * sizeof(double)) != cudaSuccess ||
-        cudaHostAlloc((void **)&h->pair_host, 16 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaMalloc((void **)&h->pair_cnt, 4 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 20 * sizeof(double)) != cudaSuccess ||
+        cudaHostAlloc((void **)&h->pair_host, 20 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
     }
     cudaMemsetAsync(h->flags, 0, 8 * sizeof(int), h->stream);
-    cudaFuncSetAttribute(k_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(int));
+    cudaFuncSetAttribute(k_hull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(int));
+    cudaFuncSetAttribute(k_hull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(int));
 
     *out = h;
     return AFV_OK;
@@ -527,6 +568,8 @@ void afv_destroy(AfvHandle h) {
     cudaFree(h->d_grid); cudaFree(h->flags); cudaFree(h->bbox_part);
     cudaFree(h->ovf_cells); cudaFree(h->ovf_len); cudaFree(h->ovf_rs); cudaFree(h->ovf_ro);
     cudaFree(h->pair_cnt); cudaFree(h->pair_dev); cudaFreeHost(h->pair_host);
+    for (cudaEvent_t e : {h->ev_sorted, h->ev_late, h->ev_force, h->ev_pack}) if (e) cudaEventDestroy(e);
+    for (DevBuf *b : {&h->late_keys, &h->late_keys_sorted, &h->late_perm, &h->late_tmp}) cudaFree(b->p);
     if (h->ev_strip) cudaEventDestroy(h->ev_strip);
     if (h->ev_append) cudaEventDestroy(h->ev_append);
     for (DevBuf *b : {&h->scratch_a, &h->scratch_b, &h->noise_buf, &h->conn_buf, &h->ring_types, &h->ring_xy, &h->ring_off}) cudaFree(b->p);

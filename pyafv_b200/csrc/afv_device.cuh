@@ -25,7 +25,20 @@ struct GridDesc {
     double Ly, halfLy;    // periodic period in y (used when pery)
     int nbx, nby;
     int perx, pery;       // periodic wrap of the bin grid / minimum image per direction
+    int swap;             // 0: key = by * nbx + bx (rows contiguous); 1: key = bx * nby + by (columns contiguous: x-slabs, whose face
+                          // columns then are the two ends of the sorted order)
+    int pad_;
 };
+
+__device__ __forceinline__ unsigned bin_key(const GridDesc &g, int bx, int by) {
+    return g.swap ? (unsigned)(bx * g.nby + by) : (unsigned)(by * g.nbx + bx);
+}
+// key -> (position along the line, line); bin column / row: see bin_xy
+__device__ __forceinline__ void bin_xy(const GridDesc &g, unsigned key, int &bx, int &by) {
+    const unsigned w = (unsigned)(g.swap ? g.nby : g.nbx);
+    const int line = (int)(key / w), pos = (int)(key - (unsigned)line * w);
+    bx = g.swap ? line : pos; by = g.swap ? pos : line;
+}
 
 // Shared part of a ring entry: what OTHER cells read during the force gather.  32 B = one DRAM sector.
 struct __align__(16) RingShared {

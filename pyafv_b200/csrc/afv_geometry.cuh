@@ -39,7 +39,33 @@ struct GeomArgs {
     int *ovf_len;              // [OVF_MAX] ring length of pooled rings
     RingShared *ovf_rs;        // [OVF_MAX * RS_SLOW]
     RingOwn *ovf_ro;
+    // late cells (slab sharding with the exchange overlapped): cells appended behind the sorted ones AFTER the sort,
+    // slots n_main .. n-1, with a bin table of their own (entries relative to n_main)
+    int n_main;
+    const int *bin_start_late; // nullptr: no late cells to look at
+    int filter;                // 0 every cell; 1 interior cells only; 2 the others (face columns and late cells)
+    int face_cols;             // bin columns at either end of the slab grid whose cells can see a late cell
+    // filter == 2: the launch is dense over the face cells -- thread t handles slot t (t < face_len0: the first face_cols
+    // columns), face_s1 + (t - face_len0) (the last face_cols columns, face_len1 cells), or a late cell
+    int face_len0, face_len1, face_s1;
 };
+
+// sorted slot handled by thread t of a geometry launch (n = number of threads with work)
+__device__ __forceinline__ int slot_of_thread(const GeomArgs &a, int t) {
+    if (a.filter != 2) return t;
+    if (t < a.face_len0) return t;
+    t -= a.face_len0;
+    if (t < a.face_len1) return a.face_s1 + t;
+    return a.n_main + (t - a.face_len1);
+}
+
+// the launch handles cell s (bin column bx)?  Interior cells: placed by the sort, at least face_cols columns from both
+// ends of the grid, so that no late cell lies in their 3 x 3 bin neighbourhood.
+__device__ __forceinline__ bool pass_selects(const GeomArgs &a, const GridDesc &g, int s, int bx) {
+    if (a.filter == 0) return true;
+    const bool interior = s < a.n_main && bx >= a.face_cols && bx < g.nbx - a.face_cols;
+    return (a.filter == 1) == interior;
+}
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr int KHULL_STRIDE = 16;
@@ -202,40 +228,41 @@ __device__ __forceinline__ void finish_cell(const GeomArgs &a, const int s, cons
 }
 
 // ------------------------------------------------------------------------------------------------------
-// candidate runs of one bin row: columns bx-1..bx+1 as (up to) two contiguous runs of sorted slots
+// candidate runs of one line of bins (a row; a column when the grid is swapped): positions pos-1..pos+1 of the line as
+// (up to) two contiguous runs of sorted slots.  npos bins per line, periodic along the line or not.
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int row_runs(const GridDesc &g, const int *__restrict__ bin_start, int row, int bx, int (&c0)[2], int (&c1)[2]) {
-    const int base = row * g.nbx;
-    if (!g.perx || g.nbx < 3) {
-        const int lo = g.perx ? 0 : max(bx - 1, 0), hi = g.perx ? g.nbx - 1 : min(bx + 1, g.nbx - 1);
+__device__ __forceinline__ int row_runs(const int npos, const bool per, const int *__restrict__ bin_start, int line, int pos, int (&c0)[2], int (&c1)[2]) {
+    const int base = line * npos;
+    if (!per || npos < 3) {
+        const int lo = per ? 0 : max(pos - 1, 0), hi = per ? npos - 1 : min(pos + 1, npos - 1);
         c0[0] = bin_start[base + lo]; c1[0] = bin_start[base + hi + 1];
         return 1;
     }
-    if (bx == 0) {
+    if (pos == 0) {
         c0[0] = bin_start[base]; c1[0] = bin_start[base + 2];
-        c0[1] = bin_start[base + g.nbx - 1]; c1[1] = bin_start[base + g.nbx];
+        c0[1] = bin_start[base + npos - 1]; c1[1] = bin_start[base + npos];
         return 2;
     }
-    if (bx == g.nbx - 1) {
-        c0[0] = bin_start[base + bx - 1]; c1[0] = bin_start[base + bx + 1];
+    if (pos == npos - 1) {
+        c0[0] = bin_start[base + pos - 1]; c1[0] = bin_start[base + pos + 1];
         c0[1] = bin_start[base]; c1[1] = bin_start[base + 1];
         return 2;
     }
-    c0[0] = bin_start[base + bx - 1]; c1[0] = bin_start[base + bx + 2];
+    c0[0] = bin_start[base + pos - 1]; c1[0] = bin_start[base + pos + 2];
     return 1;
 }
 
-// rows to visit for a cell in bin row `by`: returns the count, fills rows[]
-__device__ __forceinline__ int cell_rows(const GridDesc &g, int by, int (&rows)[3]) {
-    if (g.pery) {
-        if (g.nby < 3) { for (int i = 0; i < g.nby; ++i) rows[i] = i; return g.nby; }
-        rows[0] = (by == 0) ? g.nby - 1 : by - 1; rows[1] = by; rows[2] = (by == g.nby - 1) ? 0 : by + 1;
+// lines to visit for a cell in line `line` (of nline, periodic or not): returns the count, fills rows[]
+__device__ __forceinline__ int cell_rows(const int nline, const bool per, int line, int (&rows)[3]) {
+    if (per) {
+        if (nline < 3) { for (int i = 0; i < nline; ++i) rows[i] = i; return nline; }
+        rows[0] = (line == 0) ? nline - 1 : line - 1; rows[1] = line; rows[2] = (line == nline - 1) ? 0 : line + 1;
         return 3;
     }
     int n = 0;
-    if (by > 0) rows[n++] = by - 1;
-    rows[n++] = by;
-    if (by < g.nby - 1) rows[n++] = by + 1;
+    if (line > 0) rows[n++] = line - 1;
+    rows[n++] = line;
+    if (line < nline - 1) rows[n++] = line + 1;
     return n;
 }
 
@@ -249,46 +276,62 @@ constexpr int CMAX_HARD = 128;   // upper bound of the per-cell candidate list (
 #ifndef HULL_MIN_BLOCKS
 #define HULL_MIN_BLOCKS 10
 #endif
+// SLAB = false: one box, every cell, rows of bins contiguous (the single-GPU path, nothing of the slab machinery is
+// compiled in).  SLAB = true: an x-slab -- columns contiguous, pass filters, the late cells' bin table.
+template <bool SLAB>
 __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_hull(GeomArgs a, const int cmax) {
     extern __shared__ int s_idx[];               // [cmax][HULL_TPB]: sorted slots of the in-range neighbours of each lane's cell
     const int tid = threadIdx.x;
-    const int s = blockIdx.x * HULL_TPB + tid;
-    const bool live = s < a.n;
+    const int t_ = blockIdx.x * HULL_TPB + tid;
+    bool live = t_ < a.n;
+    const int s = SLAB ? slot_of_thread(a, t_) : t_;
     const double r = a.ph.r, cut2 = 4.0 * r * r;
-    const GridDesc g = *a.grid;
+    GridDesc g = *a.grid;
+    if (!SLAB) g.swap = 0;
     int n = 0, imin = 0;
     bool ok = true;
     double xi = 0.0, yi = 0.0;
     bool wrapx = false, wrapy = false;            // only cells in the outermost bins can see a periodic image
+    int bx = 0, by = 0;
+    if (live) {
+        bin_xy(g, a.keys[s], bx, by);
+        if (SLAB) live = pass_selects(a, g, s, bx);
+    }
 
-    // ---- gather the neighbours within 2r ----
+    // ---- gather the neighbours within 2r: the sorted cells, then (face pass of a slab) the late cells ----
     if (live) {
         const double2 pi_ = a.xy[s];
         xi = pi_.x; yi = pi_.y;
-        const unsigned key = a.keys[s];
-        const int by = (int)(key / (unsigned)g.nbx), bx = (int)(key - (unsigned)by * (unsigned)g.nbx);
         wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);
         wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
+        // lines of bins: rows, or columns in a swapped (slab) grid
+        const int npos = g.swap ? g.nby : g.nbx, nline = g.swap ? g.nbx : g.nby, pos = g.swap ? by : bx;
+        const bool per_pos = g.swap ? g.pery : g.perx, per_line = g.swap ? g.perx : g.pery;
         int rows[3];
-        const int nrow = cell_rows(g, by, rows);
+        const int nrow = cell_rows(nline, per_line, g.swap ? bx : by, rows);
         double dmin = 1e300;
-        for (int ir = 0; ir < nrow; ++ir) {
-            int c0[2], c1[2];
-            const int nrun = row_runs(g, a.bin_start, rows[ir], bx, c0, c1);
-            for (int q = 0; q < nrun; ++q) {
+        for (int tab = 0; tab < (SLAB ? 2 : 1); ++tab) {
+            const int *const bin_start = tab ? a.bin_start_late : a.bin_start;
+            if (!bin_start) break;
+            const int first = tab ? a.n_main : 0;
+            for (int ir = 0; ir < nrow; ++ir) {
+                int c0[2], c1[2];
+                const int nrun = row_runs(npos, per_pos, bin_start, rows[ir], pos, c0, c1);
+                for (int q = 0; q < nrun; ++q) {
 #pragma unroll 4
-                for (int c = c0[q]; c < c1[q]; ++c) {
-                    const double2 pc = a.xy[c];
-                    double dx = pc.x - xi, dy = pc.y - yi;
-                    if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
-                    if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
-                    const double d2 = dx * dx + dy * dy;
-                    if (d2 < cut2 && c != s && d2 > 0.0) {
-                        if (n < cmax) {
-                            s_idx[n * HULL_TPB + tid] = c;
-                            if (d2 < dmin) { dmin = d2; imin = n; }
-                            ++n;
-                        } else ok = false;
+                    for (int c = first + c0[q]; c < first + c1[q]; ++c) {
+                        const double2 pc = a.xy[c];
+                        double dx = pc.x - xi, dy = pc.y - yi;
+                        if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
+                        if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
+                        const double d2 = dx * dx + dy * dy;
+                        if (d2 < cut2 && c != s && d2 > 0.0) {
+                            if (n < cmax) {
+                                s_idx[n * HULL_TPB + tid] = c;
+                                if (d2 < dmin) { dmin = d2; imin = n; }
+                                ++n;
+                            } else ok = false;
+                        }
                     }
                 }
             }
@@ -402,23 +445,28 @@ __global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_hull(GeomArgs a, 
 // RS entries; a longer ring queues the cell.  POOL = true: one queued cell per thread (k_geometry_slow), records into
 // slot `pool_idx` of the overflow pool, at most RING_POOL_FAST entries; returns false when even that is too short.
 constexpr int RING_POOL_FAST = 32;               // bounded by the 32-bit arc mask
-template <bool POOL>
-__device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const bool live, const int pool_idx) {
+template <bool POOL, bool SLAB>
+__device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const bool live_in, const int pool_idx) {
+    bool live = live_in;
     const double r = a.ph.r, B4 = 4.0 * r;
-    const GridDesc g = *a.grid;
+    GridDesc g = *a.grid;
+    if (!SLAB) g.swap = 0;
     double xi = 0.0, yi = 0.0;
     bool wrapx = false, wrapy = false;
     int m = 0;
     bool ok = true;
     const int *hs = a.hull_slot + (live ? s : 0);      // slot-major: edge k at hs[k * a.stride]
     if (live) {
-        const double2 pi_ = a.xy[s];
-        xi = pi_.x; yi = pi_.y;
-        const unsigned key_ = a.keys[s];
-        const int by = (int)(key_ / (unsigned)g.nbx), bx = (int)(key_ - (unsigned)by * (unsigned)g.nbx);
-        wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);
-        wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
-        m = a.hull_len[s];
+        int bx, by;
+        bin_xy(g, a.keys[s], bx, by);
+        if (!POOL && SLAB) live = pass_selects(a, g, s, bx);
+        if (live) {
+            const double2 pi_ = a.xy[s];
+            xi = pi_.x; yi = pi_.y;
+            wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);
+            wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
+            m = a.hull_len[s];
+        }
     }
     const bool queued = (m == HULL_QUEUED);
     if (queued) m = 0;
@@ -621,9 +669,10 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
     return true;
 }
 
+template <bool SLAB>
 __global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) {
-    const int s = blockIdx.x * HULL_TPB + threadIdx.x;
-    ring_cell<false>(a, s, s < a.n, 0);
+    const int t = blockIdx.x * HULL_TPB + threadIdx.x;
+    ring_cell<false, SLAB>(a, SLAB ? slot_of_thread(a, t) : t, t < a.n, 0);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -634,8 +683,10 @@ __device__ __noinline__ void geom_cell_slow(const GeomArgs &a, const int s, cons
     const double r = a.ph.r, cut2 = 4.0 * r * r;
     const double xi = a.xy[s].x, yi = a.xy[s].y;
     const GridDesc g = *a.grid;
-    const unsigned key = a.keys[s];
-    const int by = (int)(key / (unsigned)g.nbx), bx = (int)(key - (unsigned)by * (unsigned)g.nbx);
+    int bx, by;
+    bin_xy(g, a.keys[s], bx, by);
+    const int npos = g.swap ? g.nby : g.nbx, nline = g.swap ? g.nbx : g.nby, pos = g.swap ? by : bx;
+    const bool per_pos = g.swap ? g.pery : g.perx, per_line = g.swap ? g.perx : g.pery;
     // bounding square of half side B = 2r as four virtual bisectors (virtual neighbours at distance 4r)
     double vx[K], vy[K], px[K], py[K];
     int lab[K];
@@ -647,20 +698,25 @@ __device__ __noinline__ void geom_cell_slow(const GeomArgs &a, const int s, cons
     int m = 4;
     bool ok = true;
     int rows[3];
-    const int nrow = cell_rows(g, by, rows);
-    for (int ir = 0; ir < nrow; ++ir) {
-        int c0[2], c1[2];
-        const int nrun = row_runs(g, a.bin_start, rows[ir], bx, c0, c1);
-        for (int q = 0; q < nrun; ++q) {
-            for (int c = c0[q]; c < c1[q]; ++c) {
-                if (c == s) continue;
-                const double2 pc = a.xy[c];
-                double dx = pc.x - xi, dy = pc.y - yi;
-                if (g.perx) dx = min_image(dx, g.Lx, g.halfLx);
-                if (g.pery) dy = min_image(dy, g.Ly, g.halfLy);
-                const double d2 = dx * dx + dy * dy;
-                if (d2 >= cut2 || d2 == 0.0) continue;
-                ok = ok && clip_polygon<K>(vx, vy, px, py, lab, m, dx, dy, 0.5 * d2, c);
+    const int nrow = cell_rows(nline, per_line, g.swap ? bx : by, rows);
+    for (int tab = 0; tab < 2; ++tab) {
+        const int *const bin_start = tab ? a.bin_start_late : a.bin_start;
+        if (!bin_start) break;
+        const int first = tab ? a.n_main : 0;
+        for (int ir = 0; ir < nrow; ++ir) {
+            int c0[2], c1[2];
+            const int nrun = row_runs(npos, per_pos, bin_start, rows[ir], pos, c0, c1);
+            for (int q = 0; q < nrun; ++q) {
+                for (int c = first + c0[q]; c < first + c1[q]; ++c) {
+                    if (c == s) continue;
+                    const double2 pc = a.xy[c];
+                    double dx = pc.x - xi, dy = pc.y - yi;
+                    if (g.perx) dx = min_image(dx, g.Lx, g.halfLx);
+                    if (g.pery) dy = min_image(dy, g.Ly, g.halfLy);
+                    const double d2 = dx * dx + dy * dy;
+                    if (d2 >= cut2 || d2 == 0.0) continue;
+                    ok = ok && clip_polygon<K>(vx, vy, px, py, lab, m, dx, dy, 0.5 * d2, c);
+                }
             }
         }
     }
@@ -673,6 +729,6 @@ __global__ void __launch_bounds__(64) k_geometry_slow(GeomArgs a) {
         const int s = a.ovf_cells[idx];
         // queued by k_ring (its polygon is fine, only the ring outgrew the stride): emit the ring again, into the pool;
         // queued by k_hull, or a ring beyond RING_POOL_FAST: clip from scratch
-        if (a.hull_len[s] == HULL_QUEUED || !ring_cell<true>(a, s, true, idx)) geom_cell_slow(a, s, idx);
+        if (a.hull_len[s] == HULL_QUEUED || !ring_cell<true, true>(a, s, true, idx)) geom_cell_slow(a, s, idx);
     }
 }

@@ -65,7 +65,7 @@ __global__ void k_bbox_final(const double *__restrict__ part, int nblocks, doubl
         int nbx = (int)fx, nby = (int)fy;
         double bsx = fmax(cut, sx / (double)nbx), bsy = fmax(cut, sy / (double)nby);
         g->x0 = xmin; g->y0 = ymin; g->inv_bx = 1.0 / bsx; g->inv_by = 1.0 / bsy;
-        g->Lx = g->Ly = 0.0; g->halfLx = g->halfLy = 0.0; g->nbx = nbx; g->nby = nby; g->perx = 0; g->pery = 0;
+        g->Lx = g->Ly = 0.0; g->halfLx = g->halfLy = 0.0; g->nbx = nbx; g->nby = nby; g->perx = 0; g->pery = 0; g->swap = 0; g->pad_ = 0;
     }
 }
 
@@ -84,7 +84,7 @@ __global__ void k_bin_keys(const double2 *__restrict__ xy, const unsigned char *
     int bx = (int)floor((q.x - g.x0) * g.inv_bx), by = (int)floor((q.y - g.y0) * g.inv_by);
     bx = min(max(bx, 0), g.nbx - 1);
     by = min(max(by, 0), g.nby - 1);
-    keys[i] = (unsigned)(by * g.nbx + bx);
+    keys[i] = bin_key(g, bx, by);
 }
 
 // K1b: gather the SoA state into sorted order
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__rest
                                                            const double *__restrict__ a0, const int64_t *__restrict__ gid,
                                                            unsigned char *__restrict__ owned, const unsigned char *__restrict__ marks, int n,
                                                            double lo, double hi, double halo, double shift_left, double shift_right,
-                                                           const int *__restrict__ blk_off,
+                                                           double deep_lo, double deep_hi, const int *__restrict__ blk_off,
                                                            const int *__restrict__ totals, int cap, double *__restrict__ msg_left,
                                                            double *__restrict__ msg_right) {
     __shared__ int warp_cnt[XCH_TPB / 32][4];
@@ -569,6 +569,9 @@ __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__rest
         else if (m & 5u) owned[i] = CELL_HALO;
     }
     if (!m) return;
+    // transfers that land beyond the receiver's face columns (header slot 2): its face pass then covers every cell
+    if ((m & 1u) && p.x < deep_lo) atomicAdd(&msg_left[2], 1.0);
+    if ((m & 4u) && p.x >= deep_hi) atomicAdd(&msg_right[2], 1.0);
     const double tv = th[i], av = a0[i], gv = (double)gid[i];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -581,25 +584,54 @@ __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__rest
         row[0] = p.x + ((q < 2) ? shift_left : shift_right); row[1] = p.y; row[2] = tv; row[3] = av; row[4] = gv;
     }
 }
-// received messages -> cells appended behind slot `base`: [left transfers][left halo][right transfers][right halo]
+// received messages -> cells appended behind slot `base`: [left transfers][left halo][right transfers][right halo];
+// with `perm` (late cells, sorted by bin among themselves) row perm[i] of that sequence goes to slot base + i
 __global__ void k_exchange_append(const double *__restrict__ in_left, const double *__restrict__ in_right, int nl_own, int nl, int nr_own,
-                                  int nr, int base, double2 *__restrict__ xy, double *__restrict__ th, double *__restrict__ a0,
-                                  int64_t *__restrict__ gid, unsigned char *__restrict__ owned) {
+                                  int nr, int base, const int *__restrict__ perm, double2 *__restrict__ xy, double *__restrict__ th,
+                                  double *__restrict__ a0, int64_t *__restrict__ gid, unsigned char *__restrict__ owned) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nl + nr) return;
-    const bool left = i < nl;
-    const int k = left ? i : i - nl;
+    const int src = perm ? perm[i] : i;
+    const bool left = src < nl;
+    const int k = left ? src : src - nl;
     const double *q = (left ? in_left : in_right) + 5 * (size_t)(k + 1);
     const int d = base + i;
     xy[d] = make_double2(q[0], q[1]); th[d] = q[2]; a0[d] = q[3]; gid[d] = (int64_t)q[4];
     owned[d] = (k < (left ? nl_own : nr_own)) ? CELL_OWNED : CELL_HALO;
 }
+// bin table of the (few, clustered) late cells: one thread per bin, lower bound by bisection -- the boundary walk of
+// k_bin_start would leave the whole interior of the grid to a single thread
+__global__ void k_bin_start_search(const unsigned *__restrict__ keys_sorted, int n, const GridDesc *__restrict__ gp, int *__restrict__ bin_start) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > gp->nbx * gp->nby) return;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (keys_sorted[mid] < (unsigned)b) lo = mid + 1; else hi = mid;
+    }
+    bin_start[b] = lo;
+}
+// bin keys of the received rows, in the order of k_exchange_append's unpermuted sequence
+__global__ void k_late_keys(const double *__restrict__ in_left, const double *__restrict__ in_right, int nl, int nr,
+                            const GridDesc *__restrict__ gp, unsigned *__restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nl + nr) return;
+    const double *q = (i < nl ? in_left + 5 * (size_t)(i + 1) : in_right + 5 * (size_t)(i - nl + 1));
+    const GridDesc g = *gp;
+    int bx = (int)floor((q[0] - g.x0) * g.inv_bx), by = (int)floor((q[1] - g.y0) * g.inv_by);
+    bx = min(max(bx, 0), g.nbx - 1);
+    by = min(max(by, 0), g.nby - 1);
+    keys[i] = bin_key(g, bx, by);
+}
 __global__ void k_gather_counts8(const int *__restrict__ c, const double *__restrict__ in0, const double *__restrict__ in1,
-                                 const int *__restrict__ flags, double *__restrict__ out) {
+                                 const int *__restrict__ flags, const int *__restrict__ bin_start, int bin_a, int bin_b,
+                                 double *__restrict__ out) {
     out[0] = (double)c[0]; out[1] = (double)c[1]; out[2] = (double)c[2]; out[3] = (double)c[3];
     out[4] = in0 ? in0[0] : 0.0; out[5] = in0 ? in0[1] : 0.0; out[6] = in1 ? in1[0] : 0.0; out[7] = in1 ? in1[1] : 0.0;
     out[8] = (double)flags[0]; out[9] = (double)flags[1]; out[10] = (double)flags[2]; out[11] = (double)flags[3];
     out[12] = (double)__int_as_float(flags[4]); out[13] = (double)__int_as_float(flags[5]);
+    out[14] = in0 ? in0[2] : 0.0; out[15] = in1 ? in1[2] : 0.0;
+    out[16] = bin_start ? (double)bin_start[bin_a] : 0.0; out[17] = bin_start ? (double)bin_start[bin_b] : 0.0;   // ends of the face columns
 }
 // keep = !(owned && x in either range)
 __global__ void k_flag_keep2(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, double lo0, double hi0,

@@ -62,6 +62,91 @@ def test_sharded_trajectory_equals_single():
     ref.close(); sh.close()
 
 
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_late_cell_exchange_equals_plain(world):
+    """Exchange overlapped with the interior geometry (late cells, afv_late_*): the same trajectory as exchange-then-step,
+    from an UNRELAXED random start (single cells jump many radii per step, so received transfers land beyond the face
+    columns now and then and the full-pass fallback runs too); mixed with plain steps and builds in between."""
+    import pyafv_b200 as afv
+    from pyafv_b200.sharded import LoopbackShardedSimulator
+    pts, theta, A0, L = _setup(12000, 1.0, 31)
+    phys = afv.PhysicalParams()
+    out = []
+    for overlap in (False, True):
+        sh = LoopbackShardedSimulator(pts, theta, phys, L, world, A0=A0, overlap=overlap)
+        sh.step(0.01, 1.0, 2.4, 0.3, seed=9, n_steps=25)
+        mid = sh.build()                                        # leaves the late loop (pending messages are consumed)
+        assert sum(s.n_owned for s in sh.ranks) == len(pts)
+        sh.step(0.01, 1.0, 2.4, 0.3, seed=9, n_steps=15)       # and re-enters it
+        assert all(s.overlapped_steps == (40 if overlap else 0) for s in sh.ranks)
+        if overlap:
+            stats = [s.exchange_stats() for s in sh.ranks]
+            assert all(st["late_steps"] == 40 and st["late_cells"] > 0 for st in stats)
+        out.append((mid, sh.build()))
+        sh.close()
+    # the two runs order the cells of a bin differently, so near-degenerate orientation tests may fall the other way
+    # (edges of length ~1e-16) and this violent dynamics amplifies that: most cells stay bit-identical, the rest
+    # agrees to ~1e-8; a missed halo cell or transfer would show up as an O(1) difference
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a["gids"], b["gids"])
+        d = a["pts"] - b["pts"]
+        d -= L * np.round(d / L)
+        assert np.abs(d).max() <= 1e-7
+        for k in ("theta", "forces", "areas", "perimeters", "arclens"):
+            scale = max(1.0, np.abs(a[k]).max())
+            assert np.abs(a[k] - b[k]).max() <= 1e-6 * scale, k
+            assert np.mean(a[k] == b[k]) > 0.9, k
+        assert np.mean(a["coord_nums"] == b["coord_nums"]) > 0.999
+
+
+def test_late_cells_beyond_the_face_columns_trigger_the_full_face_pass():
+    """Every cell drifts 5.5 radii in +x per step: the transfers that started next to the face land beyond the receiver's
+    face columns (4.8 radii here), the sender flags them and the receiver's face pass covers every cell.  A rigid
+    translation leaves the geometry unchanged."""
+    import pyafv_b200 as afv
+    from pyafv_b200.sharded import LoopbackShardedSimulator
+    pts, theta, A0, L = _setup(12000, 1.0, 5)
+    phys = afv.PhysicalParams()
+    ref = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
+    ref.update_preferred_areas(A0)
+    a = ref.build(connect=False, rings=False)
+    sh = LoopbackShardedSimulator(pts, np.zeros(len(pts)), phys, L, 3, A0=A0, overlap="late")
+    sh.step(1.0, 0.0, 5.5, 0.0, seed=1, n_steps=4)              # mu = 0: pure drift
+    stats = [s.exchange_stats() for s in sh.ranks]
+    assert all(st["full_face_passes"] >= 3 for st in stats), stats
+    b = sh.build()
+    d = b["pts"] - (pts + [22.0, 0.0])
+    d -= L * np.round(d / L)
+    assert np.abs(d).max() <= 1e-9
+    for k in ("forces", "areas", "perimeters", "arclens"):
+        scale = max(1.0, np.abs(a[k]).max())
+        assert np.abs(a[k] - b[k]).max() <= 1e-9 * scale, k
+    assert np.array_equal(a["coord_nums"], b["coord_nums"])
+    ref.close(); sh.close()
+
+
+def test_late_cell_exchange_follows_single_gpu():
+    import pyafv_b200 as afv
+    from pyafv_b200.sharded import LoopbackShardedSimulator
+    pts, theta, A0, L = _setup(6000, 0.4, 12)
+    phys = afv.PhysicalParams()
+    ref = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
+    ref.step(0.01, 1.0, 0.0, 0.0, n_steps=200)
+    pts = ref.pts.copy()
+    ref.step(0.01, 1.0, 2.4, 0.3, theta=theta, seed=5, n_steps=30)
+    sh = LoopbackShardedSimulator(pts, theta, phys, L, 4, overlap="late")
+    for s in sh.ranks:
+        s._step_index = 200
+    sh.step(0.01, 1.0, 2.4, 0.3, seed=5, n_steps=30)
+    assert all(s.overlapped_steps == 30 for s in sh.ranks)
+    b = sh.build()
+    d = b["pts"] - ref.pts
+    d -= L * np.round(d / L)
+    assert np.abs(d).max() <= 1e-8
+    assert np.abs(b["theta"] - ref.theta).max() <= 1e-10
+    ref.close(); sh.close()
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_overlapped_exchange_equals_plain(world):
     """Exchange overlapped with the interior update (afv_step_pack_overlapped): same cells, same order, same arithmetic
@@ -76,7 +161,7 @@ def test_overlapped_exchange_equals_plain(world):
     relax.close()
     out = []
     for overlap in (False, True):
-        sh = LoopbackShardedSimulator(pts, theta, phys, L, world, A0=A0, overlap=overlap)
+        sh = LoopbackShardedSimulator(pts, theta, phys, L, world, A0=A0, overlap="strips" if overlap else False)
         sh.step(0.01, 1.0, 2.4, 0.3, seed=9, n_steps=40)
         moved = sum(s.n_owned for s in sh.ranks)
         assert moved == len(pts)
@@ -101,7 +186,7 @@ def test_overlapped_exchange_follows_single_gpu_and_migrates():
     ref.step(0.01, 1.0, 0.0, 0.0, n_steps=200)
     pts = ref.pts.copy()
     ref.step(0.01, 1.0, 2.4, 0.3, theta=theta, seed=5, n_steps=30)
-    sh = LoopbackShardedSimulator(pts, theta, phys, L, 4, overlap=True)
+    sh = LoopbackShardedSimulator(pts, theta, phys, L, 4, overlap="strips")
     sh.build()
     owners0 = [set(s.store.results()[:, 4].cpu().numpy().astype(int).tolist()) for s in sh.ranks]
     for s in sh.ranks:
@@ -128,7 +213,7 @@ def test_violent_start_runs_as_exchange_then_step():
     phys = afv.PhysicalParams()
     ref = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
     ref.step(0.01, 1.0, 0.0, 0.0, n_steps=6)
-    sh = LoopbackShardedSimulator(pts, None, phys, L, 2, overlap=True)
+    sh = LoopbackShardedSimulator(pts, None, phys, L, 2, overlap="strips")
     sh.step(0.01, 1.0, 0.0, 0.0, n_steps=6)
     assert all(s.overlapped_steps == 0 for s in sh.ranks)
     d = sh.build()["pts"] - ref.pts
@@ -143,7 +228,7 @@ def test_overlapped_step_reports_a_cell_that_outruns_the_strip_margin():
     from pyafv_b200.sharded import LoopbackShardedSimulator
     pts, theta, A0, L = _setup(4000, 0.5, 3)
     phys = afv.PhysicalParams()
-    sh = LoopbackShardedSimulator(pts, np.zeros(len(pts)), phys, L, 2, overlap=True, strip_margin=0.05)
+    sh = LoopbackShardedSimulator(pts, np.zeros(len(pts)), phys, L, 2, overlap="strips", strip_margin=0.05)
     with pytest.raises(RuntimeError, match="strip margin|capacity"):
         sh.step(1.0, 0.0, 2.0, 0.0, seed=1, n_steps=3)          # every cell moves 2 l per step in +x
     sh.close()
