@@ -143,7 +143,7 @@ def run_ours(args) -> dict:
     else:
         from pyafv_b200.sharded import SlabShardedSimulator
         sim = SlabShardedSimulator(pts, theta, phys, L, rank=rank, world=world, device=local, stream=stream.cuda_stream,
-                                   overlap=args.overlap)
+                                   overlap=not args.no_overlap)
         h = sim._h
         def one_step(i):
             sim.step(STEP["dt"], STEP["mu"], STEP["v0"], STEP["Dr"], seed=7, n_steps=1)
@@ -175,8 +175,7 @@ def run_ours(args) -> dict:
     launches = int(h.lib.afv_launch_count(h._h)) - launches0
     ov_steps = getattr(sim, "overlapped_steps", 0) - ov0
     if world > 1 and rank == 0:
-        print(f"[bench] overlapped steps in the timed region: {ov_steps} of {args.steps}; largest |dx| of the recent steps: "
-              f"{[round(v, 3) for v in sim._dx_hist]}", file=sys.stderr)
+        print(f"[bench] overlapped steps in the timed region: {ov_steps} of {args.steps}; {sim.exchange_stats()}", file=sys.stderr)
     h.call("afv_get_stage_times", ms4.ctypes.data, l4.ctypes.data, 1)
     h.call("afv_set_profiling", 0)
     if world > 1:
@@ -268,7 +267,7 @@ def run_ours(args) -> dict:
                                       f"(BASELINE config[{3 if world == 1 else 4}] shape), {cells} cells/GPU, x-slabs",
                           "cells_per_gpu": cells, "box_L": L, **STEP,
                           "exchange": ("none (1 GPU)" if world == 1 else "per step, NCCL point-to-point with both ring neighbours, " +
-                                       ("overlapped with the sort and the interior geometry of the step (late cells)" if args.overlap else "then step")),
+                                       ("then step" if args.no_overlap else "overlapped with the sort and the interior geometry of the step (late cells)")),
                           "exchange_overlapped_steps": ov_steps,
                           "l2_policy": "per-step working set (ring records "
                           f"{n_local * 1024 / 1e6:.0f} MB + state) exceeds the 126 MB L2; no explicit flush"},
@@ -400,8 +399,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--reference-cells", type=int, default=200_000)
-    ap.add_argument("--overlap", action="store_true", help="N > 1: the exchange of a step travels while the step sorts its cells and "
-                    "builds its interior geometry (late cells); default: exchange, then step")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: exchange, then step (default: the exchange of a step travels while "
+                    "the step sorts its cells and builds its interior geometry -- late cells, DESIGN.md section 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

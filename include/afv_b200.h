@@ -20,7 +20,7 @@
  *       <- the user-level Euler / active-Langevin loop  examples/active_FV.py:43-54, examples/relaxation.py:41-45
  *   box_L > 0 (native periodic boundaries)
  *       <- tile_pbc + build + [:N]                     pyafv/_connectutil.py:12-96
- *   afv_set_slab / afv_pack_exchange / afv_finish_exchange / afv_step_pack_overlapped / afv_pack_owned (slab sharding)
+ *   afv_set_slab / afv_pack_exchange / afv_finish_exchange / afv_late_step_* / afv_pack_owned (slab sharding)
  *       <- decompose_points / _build_domain / _merge_results   pyafv/parallel_voronoi.py:125-338,351-418,590-633
  */
 #ifndef AFV_B200_H
@@ -178,23 +178,6 @@ int afv_finish_pair(AfvHandle h, const double *in0_dev, const double *in1_dev, i
 int afv_pack_exchange(AfvHandle h, double lo, double hi, double halo, double shift_left, double shift_right,
                       double *msg_left_dev, double *msg_right_dev, int64_t cap_rows);
 int afv_finish_exchange(AfvHandle h, const double *in_left_dev, const double *in_right_dev, int64_t cap_rows);
-/* The same exchange overlapped with the interior-cell update.  afv_step_pack_overlapped runs ONE step (as afv_step
- * with n_steps = 1 and the built-in noise generator) on the handle's stream, updating the owned cells within
- * halo + margin of the faces of the slab [lo, hi) first; once those are done the messages of the NEXT exchange are
- * packed on exchange_stream (a second cudaStream_t, e.g. the stream the NCCL transport is issued on) while the handle's
- * stream is still updating the interior.  The caller moves the messages on exchange_stream and calls
- * afv_finish_exchange_overlapped: its synchronisation (exchange_stream only) and append run there too, and the
- * handle's stream waits for the append before the next sort.  Preconditions: afv_set_slab, afv_set_deferred_checks(1),
- * halo cells fresh (one afv_pack_exchange / afv_finish_exchange before the first call).  margin bounds the distance in
- * x a cell may move in one step (a violation is reported as AFV_ERR_CAPACITY by a later finish); margin <= 0: the
- * handle chooses it -- every owned cell counts as a face cell in the first step, afterwards 4 x the largest |dx| of the
- * previous steps + r/2, at least 8 r.  Per-cell results of the step are not kept (use afv_step + afv_pack_owned when they are
- * needed). */
-int afv_step_pack_overlapped(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t seed, int64_t step, double lo, double hi,
-                             double halo, double margin, double shift_left, double shift_right, double *msg_left_dev,
-                             double *msg_right_dev, int64_t cap_rows, void *exchange_stream);
-int afv_finish_exchange_overlapped(AfvHandle h, const double *in_left_dev, const double *in_right_dev, int64_t cap_rows,
-                                   void *exchange_stream);
 /* Exchange overlapped with the geometry of the interior cells, exact for any displacement ("late cells").  Per step:
  *   afv_late_step_begin   handle's stream: sort of the cells on the device, geometry of the interior cells;
  *   afv_late_finish       exchange stream: one synchronisation (of that stream only) for the counts of the messages
@@ -218,10 +201,6 @@ int afv_late_step_end(AfvHandle h, double dt, double mu, double v0, double Dr, u
 int afv_get_exchange_stats(AfvHandle h, int64_t out[4]);
 /* make the handle's stream wait for everything issued so far on other_stream */
 int afv_stream_wait(AfvHandle h, void *other_stream);
-/* Largest |dx| any owned cell moved in one of the last two slab steps (deferred checks), as read by the last
- * afv_finish_exchange[_overlapped]; -1 before the first such step.  A driver uses it to decide when the overlapped
- * form is safe (calm dynamics) and when to fall back to exchange-then-step, which tolerates any displacement. */
-int afv_get_max_displacement(AfvHandle h, double *dx_out);
 /* after afv_build: rows (count,11) of the OWNED cells in device memory:
  * x, y, theta, A0, gid, fx, fy, area, perimeter, arclen, coord_num */
 int afv_pack_owned(AfvHandle h, double *rows_dev_out, int64_t capacity, int64_t *count);

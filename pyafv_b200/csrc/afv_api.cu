@@ -50,6 +50,7 @@ struct AfvContext {
     DevBuf late_keys, late_keys_sorted, late_perm, late_tmp;
     cudaEvent_t ev_sorted = nullptr, ev_late = nullptr, ev_force = nullptr, ev_pack = nullptr;
     int64_t late_steps = 0, late_deep_steps = 0;   // steps taken in the late form / of those, with the face pass over every cell
+    bool late_mode = false;            // stepping with afv_late_*: column-major bins and the slab variants of the geometry kernels
     bool pack_pending = false;         // ev_pack was recorded: the next sort waits for the ownership marks of that pack
     bool gid_is_perm = true;  // gid is a permutation of 0..n-1 (single-GPU use); false after set_cells_device
     // SoA state, double-buffered for the reorder
@@ -57,7 +58,6 @@ struct AfvContext {
     double *th[2] = {nullptr, nullptr}, *a0[2] = {nullptr, nullptr};
     int64_t *gid[2] = {nullptr, nullptr};
     unsigned char *owned[2] = {nullptr, nullptr};
-    unsigned char *marks = nullptr;   // per cell: MARK_DONE | exchange lists, written by the two-phase k_force
     int cur = 0;
     // cell list
     unsigned *keys = nullptr, *keys_sorted = nullptr;
@@ -75,8 +75,7 @@ struct AfvContext {
     unsigned char *hull_len = nullptr;
     RingOwn *ro = nullptr;
     RingSelf *self = nullptr;
-    int *flags = nullptr;         // device: [0] slow-path cells, [1] lookup misses, [2] max ring length, [3] hard overflows,
-                                  // [4], [5] largest |dx| of a step (float bits; even / odd overlapped steps)
+    int *flags = nullptr;         // device: [0] slow-path cells, [1] lookup misses, [2] max ring length, [3] hard overflows
     int *ovf_cells = nullptr, *ovf_index = nullptr, *ovf_len = nullptr;
     RingShared *ovf_rs = nullptr;
     RingOwn *ovf_ro = nullptr;
@@ -93,11 +92,6 @@ struct AfvContext {
     double *pair_host = nullptr;   // pinned [20]: counts sent / received, the deferred flags, the displacement slots
     double *pair_dev = nullptr;    // device [20]
     double pair_rng[4] = {0, 0, 0, 0};
-    // overlapped step + exchange: the face strips are done (ev_strip) / the received cells are appended (ev_append)
-    cudaEvent_t ev_strip = nullptr, ev_append = nullptr;
-    int64_t slab_steps = 0;        // deferred slab steps issued (parity selects the displacement slot flags[4 + parity])
-    double last_dx[2] = {-1.0, -1.0};   // largest |dx| of the last two slab steps as read by the last exchange (< 0: unknown)
-    double ov_margin = -1.0;       // adaptive strip margin for the next overlapped step (< 0: not known yet, every owned cell is a strip cell)
     // profiling
     bool profiling = false;
     struct Span { int stage; cudaEvent_t a, b; };
@@ -156,7 +150,6 @@ void free_all(AfvHandle h) {
     cudaFree(h->ovf_index); h->ovf_index = nullptr;
     cudaFree(h->ring_key); h->ring_key = nullptr;
     cudaFree(h->hull_slot); h->hull_slot = nullptr; cudaFree(h->hull_len); h->hull_len = nullptr;
-    cudaFree(h->marks); h->marks = nullptr;
     cudaFree(h->bin_start_late); h->bin_start_late = nullptr;
     h->keys = h->keys_sorted = nullptr; h->iota = h->perm = h->bin_start = nullptr; h->cub_tmp = nullptr;
     h->fx = h->fy = h->area = h->perim = h->arcl = nullptr; h->coord = nullptr; h->ring_len = nullptr;
@@ -217,7 +210,6 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     if ((rc = dev_alloc(h, &h->ring_key, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->hull_slot, (size_t)cap * KHULL_STRIDE))) return rc;
     if ((rc = dev_alloc(h, &h->hull_len, cap))) return rc;
-    if ((rc = dev_alloc(h, &h->marks, cap))) return rc;
     if ((rc = dev_alloc(h, &h->ro, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->self, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->ovf_index, cap))) return rc;
@@ -293,7 +285,8 @@ void periodic_grid(AfvHandle h, GridDesc &g) {
     g.inv_bx = (double)nbx / wx; g.inv_by = (double)nby / h->L;
     g.Lx = h->L; g.halfLx = 0.5 * h->L; g.Ly = h->L; g.halfLy = 0.5 * h->L;
     g.nbx = nbx; g.nby = nby; g.perx = h->slab ? 0 : 1; g.pery = 1;
-    g.swap = h->slab ? 1 : 0;   // x-slabs: columns contiguous, so that the face columns are the two ends of the sorted order
+    // late-cell stepping of an x-slab: columns contiguous, so that the face columns are the two ends of the sorted order
+    g.swap = (h->slab && h->late_mode) ? 1 : 0;
     g.pad_ = 0;
 }
 
@@ -387,12 +380,12 @@ int stage_geometry(AfvHandle h, GeomPass gp = GeomPass()) {
     if (n > 0 && gp.fast) {
         {
             StageTimer t(h, 1, st);
-            if (h->slab) k_hull<true><<<nblk(n, HULL_TPB), HULL_TPB, smem, st>>>(a, cmax);
+            if (h->late_mode) k_hull<true><<<nblk(n, HULL_TPB), HULL_TPB, smem, st>>>(a, cmax);
             else k_hull<false><<<nblk(n, HULL_TPB), HULL_TPB, smem, st>>>(a, cmax);
         }
         {
             StageTimer t(h, 2, st);
-            if (h->slab) k_ring<true><<<nblk(n, HULL_TPB), HULL_TPB, 0, st>>>(a);
+            if (h->late_mode) k_ring<true><<<nblk(n, HULL_TPB), HULL_TPB, 0, st>>>(a);
             else k_ring<false><<<nblk(n, HULL_TPB), HULL_TPB, 0, st>>>(a);
         }
         h->launches += 2;
@@ -408,15 +401,8 @@ int stage_geometry(AfvHandle h, GeomPass gp = GeomPass()) {
     return AFV_OK;
 }
 
-// Two-phase form of the update (slab sharding with overlap): the cells in the face strips first, then the interior;
-// `after_strips` (optional) runs between the two launches, e.g. to record the event the exchange stream waits for.
-struct StripPhases {
-    double strip_lo, strip_hi;     // strips: x < strip_lo or x >= strip_hi before the update
-    double lo, hi, halo;           // slab interval and halo width (exchange lists of the updated positions)
-};
-
 int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, double Dr, uint64_t seed, int64_t step,
-                const double *noise_row, const StripPhases *phases = nullptr, cudaEvent_t after_strips = nullptr, int disp_slot = -1) {
+                const double *noise_row) {
     StageTimer t(h, 3);
     const int n = (int)h->n;
     const int c = h->cur;
@@ -427,21 +413,8 @@ int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, doub
     a.do_step = do_step ? 1 : 0; a.xy = h->xy[c]; a.theta = h->th[c];
     a.dt = dt; a.mu = mu; a.v0 = v0; a.noise_amp = std::sqrt(2.0 * Dr * dt); a.seed = seed; a.step = step;
     a.noise = noise_row; a.Lx = h->slab ? 0.0 : h->L; a.Ly = h->L;
-    a.phase = 0; a.strip_lo = a.strip_hi = 0.0; a.xlo = a.xhi = a.xhalo = 0.0; a.marks = h->marks;
-    a.disp_max = disp_slot >= 0 ? reinterpret_cast<unsigned *>(h->flags + disp_slot) : nullptr;
-    if (!phases) {
-        k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
-        h->launches += 1;
-    } else {
-        a.strip_lo = phases->strip_lo; a.strip_hi = phases->strip_hi; a.xlo = phases->lo; a.xhi = phases->hi; a.xhalo = phases->halo;
-        CK(cudaMemsetAsync(h->marks, 0, (size_t)n, h->stream));
-        a.phase = 1;
-        k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
-        if (after_strips) CK(cudaEventRecord(after_strips, h->stream));
-        a.phase = 2;
-        k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
-        h->launches += 2;
-    }
+    k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
+    h->launches += 1;
     CK(cudaGetLastError());
     return AFV_OK;
 }
@@ -570,8 +543,6 @@ void afv_destroy(AfvHandle h) {
     cudaFree(h->pair_cnt); cudaFree(h->pair_dev); cudaFreeHost(h->pair_host);
     for (cudaEvent_t e : {h->ev_sorted, h->ev_late, h->ev_force, h->ev_pack}) if (e) cudaEventDestroy(e);
     for (DevBuf *b : {&h->late_keys, &h->late_keys_sorted, &h->late_perm, &h->late_tmp}) cudaFree(b->p);
-    if (h->ev_strip) cudaEventDestroy(h->ev_strip);
-    if (h->ev_append) cudaEventDestroy(h->ev_append);
     for (DevBuf *b : {&h->scratch_a, &h->scratch_b, &h->noise_buf, &h->conn_buf, &h->ring_types, &h->ring_xy, &h->ring_off}) cudaFree(b->p);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -653,6 +624,7 @@ int afv_build(AfvHandle h, unsigned flags) {
     CHECK_H(h);
     h->n_conn = -1; h->n_ring = -1;
     if (h->n == h->n_dead) { h->n = h->n_dead = 0; }   // only stale halo copies left
+    h->late_mode = false;
     if (h->n == 0) { h->built = true; h->n_conn = 0; h->n_ring = 0; return AFV_OK; }
     int rc;
     CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
@@ -705,6 +677,7 @@ int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t s
     if (n_steps < 0 || Dr < 0.0 || !(dt >= 0.0)) { h->err = "invalid step arguments"; return AFV_ERR_ARG; }
     if (h->n == h->n_dead) { h->n = h->n_dead = 0; }
     if (h->n == 0 || n_steps == 0) return AFV_OK;
+    h->late_mode = false;
     int rc;
     const double *noise_dev = nullptr;
     if (noise_host) {
@@ -717,18 +690,11 @@ int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t s
     const bool deferred = h->defer_checks && !noise_host;
     if (!deferred) CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
     for (int s = 0; s < n_steps; ++s) {
-        int disp_slot = -1;
-        if (deferred) {
-            CK(cudaMemsetAsync(h->flags, 0, sizeof(int), h->stream));   // the slow-path queue restarts every step
-            if (h->slab) {   // largest |dx| of the step, read by the next exchange (drives the overlapped form)
-                disp_slot = 4 + (int)(h->slab_steps++ & 1);
-                CK(cudaMemsetAsync(h->flags + disp_slot, 0, sizeof(int), h->stream));
-            }
-        }
+        if (deferred) CK(cudaMemsetAsync(h->flags, 0, sizeof(int), h->stream));   // the slow-path queue restarts every step
         if ((rc = stage_sort(h))) return rc;
         // open boundaries: the local density is unknown, so the capacity is checked (and grown) before the positions move
         if ((rc = (h->L > 0.0 ? stage_geometry(h) : geometry_checked(h)))) return rc;
-        if ((rc = stage_force(h, true, dt, mu, v0, Dr, seed, step0 + s, noise_dev ? noise_dev + (size_t)s * h->n : nullptr, nullptr, nullptr, disp_slot))) return rc;
+        if ((rc = stage_force(h, true, dt, mu, v0, Dr, seed, step0 + s, noise_dev ? noise_dev + (size_t)s * h->n : nullptr))) return rc;
     }
     if (!deferred && (rc = check_flags(h))) return rc;   // also synchronises: noise_host is borrowed for the call only
     h->built = true;

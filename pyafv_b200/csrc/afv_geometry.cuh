@@ -279,7 +279,7 @@ constexpr int CMAX_HARD = 128;   // upper bound of the per-cell candidate list (
 // SLAB = false: one box, every cell, rows of bins contiguous (the single-GPU path, nothing of the slab machinery is
 // compiled in).  SLAB = true: an x-slab -- columns contiguous, pass filters, the late cells' bin table.
 template <bool SLAB>
-__global__ void __launch_bounds__(HULL_TPB, HULL_MIN_BLOCKS) k_hull(GeomArgs a, const int cmax) {
+__global__ void __launch_bounds__(HULL_TPB, SLAB ? HULL_MIN_BLOCKS - 1 : HULL_MIN_BLOCKS) k_hull(GeomArgs a, const int cmax) {
     extern __shared__ int s_idx[];               // [cmax][HULL_TPB]: sorted slots of the in-range neighbours of each lane's cell
     const int tid = threadIdx.x;
     const int t_ = blockIdx.x * HULL_TPB + tid;

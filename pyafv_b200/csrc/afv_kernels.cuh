@@ -142,16 +142,7 @@ struct ForceArgs {
     int64_t step;
     const double *noise;           // nullptr -> Philox; else row of this step, indexed by gid
     double Lx, Ly;                 // periodic wrap of the updated positions per direction (0 = none)
-    // two-phase update of a slab (phase != 0): phase 1 handles the cells in the face strips (x < strip_lo or
-    // x >= strip_hi before the update) and writes marks[s] = MARK_DONE | exchange lists of the updated position; phase 2
-    // handles the rest while the exchange of the strip cells is already under way on another stream.
-    int phase;
-    double strip_lo, strip_hi;
-    double xlo, xhi, xhalo;        // slab interval and halo width: the exchange lists of the updated positions
-    unsigned char *marks;
-    unsigned *disp_max;            // largest |dx| of the step as float bits (non-negative floats order like integers)
 };
-constexpr unsigned char MARK_DONE = 0x80;
 
 // exchange lists of an owned cell at x (bit q set = member of list q, see k_exchange_count)
 __device__ __forceinline__ unsigned xch_lists(double x, unsigned char own, double lo, double hi, double halo) {
@@ -215,13 +206,6 @@ __device__ __forceinline__ bool lookup_edge(const ForceArgs &a, int j, int self,
 __global__ void __launch_bounds__(128, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n) return;
-    if (a.phase == 1) {
-        const double x0 = a.xy[s].x;
-        if (!(x0 < a.strip_lo || x0 >= a.strip_hi)) return;
-        a.marks[s] = MARK_DONE;
-    } else if (a.phase == 2) {
-        if (a.marks[s] & MARK_DONE) return;
-    }
     if (a.owned[s] != CELL_OWNED) { a.fx[s] = 0.0; a.fy[s] = 0.0; return; }
     int E = a.ring_len[s];
     const double r = a.ph.r, r2 = r * r;
@@ -311,15 +295,6 @@ __global__ void __launch_bounds__(128, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
             xi_ = a.noise ? a.noise[id] : philox_normal(a.seed, id, a.step);
         }
         a.xy[s] = make_double2(xn, yn); a.theta[s] = th + a.noise_amp * xi_;
-        if (a.disp_max) {
-            const unsigned db = __float_as_uint(__double2float_ru(fabs(xn - pos.x)));
-            if (db > *reinterpret_cast<volatile unsigned *>(a.disp_max)) atomicMax(a.disp_max, db);
-        }
-        if (a.phase) {
-            const unsigned m = xch_lists(xn, CELL_OWNED, a.xlo, a.xhi, a.xhalo);
-            if (a.phase == 1) a.marks[s] = (unsigned char)(MARK_DONE | m);
-            else if (m) atomicAdd(&a.flags[3], 1);   // moved further than the strip margin in one step: the exchange missed it
-        }
     }
 }
 
@@ -473,20 +448,13 @@ __global__ void k_pack_message(const int *__restrict__ idx, const int *__restric
 // owner) followed by the halo rows.
 // Owned cells fall into up to four lists (xch_lists above): q = 0 transfers to the left rank (x < lo), 1 halo rows for
 // the left rank (lo <= x < lo + halo), 2 transfers to the right rank (x >= hi), 3 halo rows for the right rank
-// (hi - halo <= x < hi).  `marks` (optional): list bits already written by a two-phase k_force.
+// (hi - halo <= x < hi).
 constexpr int XCH_TPB = 256;
-__device__ __forceinline__ unsigned xch_lists_of(const double2 *xy, const unsigned char *owned, const unsigned char *marks, int i,
-                                                 double lo, double hi, double halo) {
-    const unsigned char own = owned[i];
-    if (own != CELL_OWNED) return 0u;
-    return marks ? (unsigned)(marks[i] & 0x0f) : xch_lists(xy[i].x, own, lo, hi, halo);
-}
 // pass 1: members of every list per block
-__global__ void __launch_bounds__(XCH_TPB) k_exchange_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned,
-                                                            const unsigned char *__restrict__ marks, int n, double lo, double hi, double halo,
-                                                            int *__restrict__ blk_cnt) {
+__global__ void __launch_bounds__(XCH_TPB) k_exchange_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n,
+                                                            double lo, double hi, double halo, int *__restrict__ blk_cnt) {
     const int i = blockIdx.x * XCH_TPB + threadIdx.x;
-    const unsigned m = (i < n) ? xch_lists_of(xy, owned, marks, i, lo, hi, halo) : 0u;
+    const unsigned m = (i < n) ? xch_lists(xy[i].x, owned[i], lo, hi, halo) : 0u;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int c = __syncthreads_count((m >> q) & 1u);
@@ -544,7 +512,7 @@ __global__ void __launch_bounds__(1024) k_exchange_scan(const int *__restrict__ 
 // become CELL_DEAD (the next sort drops them), cells that left the slab stay as halo copies of their new owner's cell.
 __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__restrict__ xy, const double *__restrict__ th,
                                                            const double *__restrict__ a0, const int64_t *__restrict__ gid,
-                                                           unsigned char *__restrict__ owned, const unsigned char *__restrict__ marks, int n,
+                                                           unsigned char *__restrict__ owned, int n,
                                                            double lo, double hi, double halo, double shift_left, double shift_right,
                                                            double deep_lo, double deep_hi, const int *__restrict__ blk_off,
                                                            const int *__restrict__ totals, int cap, double *__restrict__ msg_left,
@@ -555,7 +523,7 @@ __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__rest
     double2 p = make_double2(0.0, 0.0);
     unsigned char own = CELL_DEAD;
     unsigned m = 0u;
-    if (i < n) { p = xy[i]; own = owned[i]; m = xch_lists_of(xy, owned, marks, i, lo, hi, halo); }
+    if (i < n) { p = xy[i]; own = owned[i]; m = xch_lists(p.x, own, lo, hi, halo); }
     int rank_in_warp[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -629,7 +597,7 @@ __global__ void k_gather_counts8(const int *__restrict__ c, const double *__rest
     out[0] = (double)c[0]; out[1] = (double)c[1]; out[2] = (double)c[2]; out[3] = (double)c[3];
     out[4] = in0 ? in0[0] : 0.0; out[5] = in0 ? in0[1] : 0.0; out[6] = in1 ? in1[0] : 0.0; out[7] = in1 ? in1[1] : 0.0;
     out[8] = (double)flags[0]; out[9] = (double)flags[1]; out[10] = (double)flags[2]; out[11] = (double)flags[3];
-    out[12] = (double)__int_as_float(flags[4]); out[13] = (double)__int_as_float(flags[5]);
+    out[12] = out[13] = 0.0;
     out[14] = in0 ? in0[2] : 0.0; out[15] = in1 ? in1[2] : 0.0;
     out[16] = bin_start ? (double)bin_start[bin_a] : 0.0; out[17] = bin_start ? (double)bin_start[bin_b] : 0.0;   // ends of the face columns
 }

@@ -84,18 +84,6 @@ class GpuCellStore:
     def finish_exchange(self, from_left: torch.Tensor, from_right: torch.Tensor, cap: int) -> None:
         self.h.call("afv_finish_exchange", from_left.data_ptr(), from_right.data_ptr(), int(cap))
 
-    def step_pack_overlapped(self, geo, cap: int, margin: float, exchange_stream: int, dt, mu, v0, Dr, seed, step_index):
-        """One step on the handle's stream with the face strips first; the next exchange's messages are packed on
-        ``exchange_stream`` while the interior is still being updated (``afv_step_pack_overlapped``)."""
-        ml, mr = self._msg("xl", cap), self._msg("xr", cap)
-        self.h.call("afv_step_pack_overlapped", float(dt), float(mu), float(v0), float(Dr), C.c_uint64(int(seed)), C.c_int64(int(step_index)),
-                    float(geo.lo), float(geo.hi), float(geo.halo), float(margin), float(geo.shift_to_left), float(geo.shift_to_right),
-                    ml.data_ptr(), mr.data_ptr(), int(cap), C.c_void_p(int(exchange_stream)))
-        return ml, mr
-
-    def finish_exchange_overlapped(self, from_left: torch.Tensor, from_right: torch.Tensor, cap: int, exchange_stream: int) -> None:
-        self.h.call("afv_finish_exchange_overlapped", from_left.data_ptr(), from_right.data_ptr(), int(cap), C.c_void_p(int(exchange_stream)))
-
     # -- exchange overlapped with the interior geometry: the received rows become "late" cells (afv_late_*) --
     def late_begin(self, cap: int) -> None:
         self.h.call("afv_late_step_begin", int(cap))
@@ -200,28 +188,19 @@ class SlabShardedSimulator:
             the Philox noise stream is keyed by them, so results do not depend on the number of GPUs).
         A0: per-cell preferred areas (default ``phys.A0``).
         comm: communicator (default :class:`TorchDistComm`); ``None`` with ``world == 1``.
-        overlap: how ``step()`` combines the exchange with the computation.
-            ``False`` (default): exchange, then step.
-            ``True`` / ``"late"``: the exchange for a step is packed right after the previous update and travels on a
-            second stream while the step already sorts its cells and builds the geometry of its interior cells; what
-            arrives joins as *late cells* (a bin table of their own) before the cells near the faces are built.  Exact
-            for any displacement (``afv_late_step_begin`` / ``afv_late_finish`` / ``afv_late_step_end``).
-            ``"strips"``: the older form -- the cells near the faces are updated first and the exchange runs while the
-            interior is still being updated.  It needs a bound on |dx| per step, so it engages only while the dynamics
-            is calm (the largest |dx| of each of the last ``CALM_STEPS`` steps stayed below ``r``).
-        strip_margin: with ``overlap="strips"``, the bound on |dx| per step; engages that form unconditionally
-            (a violation raises at a later exchange).  Default: chosen by the library from the displacements it
-            observes (4 x the largest one + r/2, at least 8 r).
+        overlap: ``False`` (default): exchange, then step.  ``True``: the exchange for a step is packed right after the
+            previous update and travels on a second stream while the step already sorts its cells and builds the
+            geometry of its interior cells; what arrives joins as *late cells* (a bin table of their own) and the cells
+            near the faces are built next to the interior ones.  Exact for any displacement (``afv_late_step_begin`` /
+            ``afv_late_finish`` / ``afv_late_step_end``).
         exchange_stream: ``torch.cuda.Stream`` for the overlapped exchange (default: a new high-priority one).  For
             the transport to overlap as well, create the NCCL process group with
             ``pg_options=ProcessGroupNCCL.Options(is_high_priority_stream=True)``.
     """
 
-    CALM_STEPS = 8      # steps in a row with every |dx| < r before the overlapped form engages
-
     def __init__(self, pts, theta, phys, L: float, *, rank: int = 0, world: int = 1, device: int = 0, stream: int | None = None,
-                 gids=None, A0=None, halo_width: float | None = None, comm=None, overlap: bool | str = False,
-                 strip_margin: float | None = None, exchange_stream=None):
+                 gids=None, A0=None, halo_width: float | None = None, comm=None, overlap: bool = False,
+                 exchange_stream=None):
         from . import _lib
         from .finite_voronoi import _as_params
         self.phys, self.L, self.rank, self.world = phys, float(L), rank, world
@@ -248,16 +227,12 @@ class SlabShardedSimulator:
         self._step_index = 0
         self._cap = None
         self._halo_fresh = False          # the halo copies on the device belong to the current positions
-        if overlap not in (False, True, "late", "strips"):
-            raise ValueError("overlap must be False, True, 'late' or 'strips'")
-        self.overlap = ("late" if overlap is True else overlap) if world > 1 else False
-        self._inbox = None                # late form: messages packed for the current positions, transported, not yet appended
-        self.strip_margin = 0.0 if strip_margin is None else float(strip_margin)      # <= 0: adaptive
-        self._dx_hist = []                # largest |dx| of the recent steps, newest last
+        self.overlap = bool(overlap) and world > 1
+        self._inbox = None                # overlapped form: messages packed for the current positions, on their way, not yet appended
         self.overlapped_steps = 0         # steps taken in the overlapped form so far
         self._xs = None
         if self.overlap:
-            # high priority: its blocks are dispatched ahead of the pending blocks of the interior update
+            # high priority: its blocks (pack, append, the face pass) are dispatched ahead of the pending blocks of the interior pass
             self._xs = exchange_stream if exchange_stream is not None else torch.cuda.Stream(self.device, priority=-1)
 
     @property
@@ -286,42 +261,12 @@ class SlabShardedSimulator:
     def exchange_in(self, from_left, from_right) -> None:
         self.store.finish_exchange(from_left, from_right, self._caps()[0])
         self._halo_fresh = True
-        self._note_displacement()
-
-    def _note_displacement(self) -> None:
-        dx = C.c_double(-1.0)
-        self._h.call("afv_get_max_displacement", C.byref(dx))
-        if dx.value >= 0.0:
-            self._dx_hist = (self._dx_hist + [dx.value])[-self.CALM_STEPS:]
-
-    def _overlap_engaged(self) -> bool:
-        if self.overlap != "strips":
-            return False
-        if self.strip_margin > 0.0:
-            return True
-        return len(self._dx_hist) == self.CALM_STEPS and max(self._dx_hist) < self.phys.r
-
-    def step_and_pack(self, dt, mu, v0, Dr, seed):
-        """Overlapped phase 1: one step (needs fresh halo copies) + the messages of the next exchange, packed on the
-        exchange stream as soon as the cells near the faces are updated."""
-        msgs = self.store.step_pack_overlapped(self.geo, self._caps()[0], self.strip_margin, self._xs.cuda_stream, dt, mu, v0, Dr, seed,
-                                               self._step_index)
-        self._step_index += 1
-        self.overlapped_steps += 1
-        self._halo_fresh = False
-        return msgs
-
-    def exchange_in_overlapped(self, from_left, from_right) -> None:
-        """Overlapped phase 2 (after the transport on the exchange stream): append what arrived."""
-        self.store.finish_exchange_overlapped(from_left, from_right, self._caps()[0], self._xs.cuda_stream)
-        self._halo_fresh = True
-        self._note_displacement()
 
     def _refresh_halo(self) -> None:
         """Halo copies for the current positions, appended the plain way (before a build or an exchange-then-step)."""
         if self.world == 1 or self._halo_fresh:
             return
-        if self._inbox is not None:       # left over from the late form: already packed and on its way
+        if self._inbox is not None:       # left over from the overlapped form: already packed and on its way
             self.store.stream_wait(self._xs.cuda_stream)
             inbox, self._inbox = self._inbox, None
             self.exchange_in(*inbox)
@@ -333,7 +278,7 @@ class SlabShardedSimulator:
         self._h.call("afv_get_exchange_stats", out.ctypes.data)
         return dict(late_steps=int(out[0]), full_face_passes=int(out[1]), late_cells=int(out[2]), face_columns=int(out[3]))
 
-    # -- late form, phase by phase (a loopback driver interleaves the ranks of one process) --
+    # -- overlapped form, phase by phase (a loopback driver interleaves the ranks of one process) --
     def late_begin(self) -> None:
         self.store.late_begin(self._caps()[0])
 
@@ -365,26 +310,20 @@ class SlabShardedSimulator:
     def step(self, dt: float, mu: float = 1.0, v0: float = 0.0, Dr: float = 0.0, *, seed: int = 0, n_steps: int = 1) -> None:
         """``n_steps`` of: one exchange with the ring neighbours (cells that left the slab during the previous update
         change owner, halo cells are refreshed), then the fused build + force + update.  With ``overlap`` the exchange
-        for step k+1 runs on the exchange stream while step k is still updating its interior cells."""
+        travels while the step sorts its cells and builds its interior geometry."""
         for _ in range(n_steps):
-            if self.overlap == "late":
-                if self._inbox is None:   # first step of a run: pack and transport on the handle's stream
-                    self._halo_fresh = False
-                    self._inbox = self.comm.exchange_fixed(*self.exchange_out())
-                self.late_begin()
-                self.late_finish()
-                msgs = self.late_end(dt, mu, v0, Dr, seed)
-                with torch.cuda.stream(self._xs):
-                    self._inbox = self.comm.exchange_fixed(*msgs)
-                continue
-            self._refresh_halo()          # a no-op after a "strips" step: it leaves fresh halo copies behind
-            if self._overlap_engaged():
-                msgs = self.step_and_pack(dt, mu, v0, Dr, seed)
-                with torch.cuda.stream(self._xs):
-                    inbox = self.comm.exchange_fixed(*msgs)
-                self.exchange_in_overlapped(*inbox)
-            else:
+            if not self.overlap:
+                self._refresh_halo()
                 self.compute_step(dt, mu, v0, Dr, seed)
+                continue
+            if self._inbox is None:       # first step of a run: pack and transport on the handle's stream
+                self._halo_fresh = False
+                self._inbox = self.comm.exchange_fixed(*self.exchange_out())
+            self.late_begin()
+            self.late_finish()
+            msgs = self.late_end(dt, mu, v0, Dr, seed)
+            with torch.cuda.stream(self._xs):
+                self._inbox = self.comm.exchange_fixed(*msgs)
 
     def build(self) -> dict[str, np.ndarray]:
         """Forces and geometry of the owned cells (keys of the reference's merged dict, ``parallel_voronoi.py:596-611``,
@@ -440,8 +379,7 @@ def results_dict(res: torch.Tensor) -> dict[str, np.ndarray]:
 class LoopbackShardedSimulator:
     """``world`` slabs driven from one process on one device; same phases as the distributed run."""
 
-    def __init__(self, pts, theta, phys, L: float, world: int, *, device: int = 0, A0=None, halo_width=None, overlap: bool | str = False,
-                 strip_margin=None):
+    def __init__(self, pts, theta, phys, L: float, world: int, *, device: int = 0, A0=None, halo_width=None, overlap: bool = False):
         pts = np.asarray(pts, dtype=np.float64)
         N = pts.shape[0]
         theta = np.zeros(N) if theta is None else np.asarray(theta, dtype=np.float64)
@@ -450,22 +388,20 @@ class LoopbackShardedSimulator:
         owner = np.minimum((pts[:, 0] // W).astype(int), world - 1)
         self.ranks = []
         stream = torch.cuda.current_stream(torch.device("cuda", device)).cuda_stream   # one stream for every rank
-        if overlap not in (False, True, "late", "strips"):
-            raise ValueError("overlap must be False, True, 'late' or 'strips'")
-        self.overlap = ("late" if overlap is True else overlap) if world > 1 else False
-        self._inbox = None                # late form: messages packed for the current positions, transported, not yet appended
+        self.overlap = bool(overlap) and world > 1
+        self._inbox = None                # overlapped form: messages packed for the current positions, on their way, not yet appended
         xs = torch.cuda.Stream(torch.device("cuda", device), priority=-1) if self.overlap else None   # and one exchange stream
         for rk in range(world):
             m = owner == rk
             self.ranks.append(SlabShardedSimulator(pts[m], theta[m], phys, L, rank=rk, world=world, device=device,
                                                    gids=np.flatnonzero(m), A0=A0[m], halo_width=halo_width, comm=False, stream=stream,
-                                                   overlap=self.overlap, strip_margin=strip_margin, exchange_stream=xs))
+                                                   overlap=self.overlap, exchange_stream=xs))
         self.world, self.N = world, N
 
     def _refresh_halo(self) -> None:
         if self.world == 1 or all(s._halo_fresh for s in self.ranks):
             return
-        if all(s._inbox is not None for s in self.ranks):      # left over from the late form
+        if all(s._inbox is not None for s in self.ranks):      # left over from the overlapped form
             for sim in self.ranks:
                 sim._refresh_halo()
         else:
@@ -474,28 +410,23 @@ class LoopbackShardedSimulator:
 
     def step(self, dt, mu=1.0, v0=0.0, Dr=0.0, *, seed=0, n_steps=1) -> None:
         for _ in range(n_steps):
-            if self.overlap == "late":
-                if any(s._inbox is None for s in self.ranks):
-                    for sim in self.ranks:
-                        sim._halo_fresh = False
-                    for sim, inbox in zip(self.ranks, loopback_exchange([s.exchange_out() for s in self.ranks])):
-                        sim._inbox = inbox
-                for sim in self.ranks:
-                    sim.late_begin()
-                for sim in self.ranks:
-                    sim.late_finish()
-                msgs = [sim.late_end(dt, mu, v0, Dr, seed) for sim in self.ranks]
-                for sim, inbox in zip(self.ranks, loopback_exchange(msgs)):
-                    sim._inbox = inbox
-                continue
-            self._refresh_halo()
-            if self.overlap == "strips" and all(sim._overlap_engaged() for sim in self.ranks):
-                msgs = [sim.step_and_pack(dt, mu, v0, Dr, seed) for sim in self.ranks]
-                for sim, inbox in zip(self.ranks, loopback_exchange(msgs)):
-                    sim.exchange_in_overlapped(*inbox)
-            else:
+            if not self.overlap:
+                self._refresh_halo()
                 for sim in self.ranks:
                     sim.compute_step(dt, mu, v0, Dr, seed)
+                continue
+            if any(s._inbox is None for s in self.ranks):
+                for sim in self.ranks:
+                    sim._halo_fresh = False
+                for sim, inbox in zip(self.ranks, loopback_exchange([s.exchange_out() for s in self.ranks])):
+                    sim._inbox = inbox
+            for sim in self.ranks:
+                sim.late_begin()
+            for sim in self.ranks:
+                sim.late_finish()
+            msgs = [sim.late_end(dt, mu, v0, Dr, seed) for sim in self.ranks]
+            for sim, inbox in zip(self.ranks, loopback_exchange(msgs)):
+                sim._inbox = inbox
 
     def build(self) -> dict[str, np.ndarray]:
         """Merged dict in global cell order (the reference's ``_merge_results``)."""

@@ -11,7 +11,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 rng = np.random.default_rng(0)
 L = float(np.sqrt(N))
 pts, th = rng.random((N, 2)) * L, 2 * np.pi * rng.random(N)
-for overlap in (False, "late", False, "late"):
+for overlap in (False, True, False, True):
     sh = LoopbackShardedSimulator(pts, th, afv.PhysicalParams(), L, 2, overlap=overlap)
     sh.step(0.01, 1.0, 2.4, 0.3, seed=7, n_steps=10)
     torch.cuda.synchronize(); t0 = time.perf_counter()

@@ -110,7 +110,7 @@ def test_late_cells_beyond_the_face_columns_trigger_the_full_face_pass():
     ref = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
     ref.update_preferred_areas(A0)
     a = ref.build(connect=False, rings=False)
-    sh = LoopbackShardedSimulator(pts, np.zeros(len(pts)), phys, L, 3, A0=A0, overlap="late")
+    sh = LoopbackShardedSimulator(pts, np.zeros(len(pts)), phys, L, 3, A0=A0, overlap=True)
     sh.step(1.0, 0.0, 5.5, 0.0, seed=1, n_steps=4)              # mu = 0: pure drift
     stats = [s.exchange_stats() for s in sh.ranks]
     assert all(st["full_face_passes"] >= 3 for st in stats), stats
@@ -134,7 +134,7 @@ def test_late_cell_exchange_follows_single_gpu():
     ref.step(0.01, 1.0, 0.0, 0.0, n_steps=200)
     pts = ref.pts.copy()
     ref.step(0.01, 1.0, 2.4, 0.3, theta=theta, seed=5, n_steps=30)
-    sh = LoopbackShardedSimulator(pts, theta, phys, L, 4, overlap="late")
+    sh = LoopbackShardedSimulator(pts, theta, phys, L, 4, overlap=True)
     for s in sh.ranks:
         s._step_index = 200
     sh.step(0.01, 1.0, 2.4, 0.3, seed=5, n_steps=30)
@@ -145,90 +145,3 @@ def test_late_cell_exchange_follows_single_gpu():
     assert np.abs(d).max() <= 1e-8
     assert np.abs(b["theta"] - ref.theta).max() <= 1e-10
     ref.close(); sh.close()
-
-
-@pytest.mark.parametrize("world", [2, 3])
-def test_overlapped_exchange_equals_plain(world):
-    """Exchange overlapped with the interior update (afv_step_pack_overlapped): same cells, same order, same arithmetic
-    as exchange-then-step, so the trajectories are bit-identical; cells migrate and halo copies turn over on the way."""
-    import pyafv_b200 as afv
-    from pyafv_b200.sharded import LoopbackShardedSimulator
-    pts, theta, A0, L = _setup(8000, 0.6, 21)
-    phys = afv.PhysicalParams()
-    relax = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
-    relax.step(0.01, 1.0, 0.0, 0.0, n_steps=200)
-    pts = relax.pts.copy()
-    relax.close()
-    out = []
-    for overlap in (False, True):
-        sh = LoopbackShardedSimulator(pts, theta, phys, L, world, A0=A0, overlap="strips" if overlap else False)
-        sh.step(0.01, 1.0, 2.4, 0.3, seed=9, n_steps=40)
-        moved = sum(s.n_owned for s in sh.ranks)
-        assert moved == len(pts)
-        sh.step(0.01, 1.0, 2.4, 0.3, seed=9, n_steps=5)       # a second call continues without a fresh exchange
-        # the overlapped form engages once the dynamics was calm for CALM_STEPS steps
-        assert all(s.overlapped_steps == (45 - s.CALM_STEPS if overlap else 0) for s in sh.ranks), [s.overlapped_steps for s in sh.ranks]
-        out.append(sh.build())
-        sh.close()
-    a, b = out
-    assert np.array_equal(a["gids"], b["gids"])
-    for k in ("pts", "theta", "forces", "areas", "perimeters", "arclens", "coord_nums"):
-        assert np.array_equal(a[k], b[k]), k
-
-
-def test_overlapped_exchange_follows_single_gpu_and_migrates():
-    """Overlapped sharded run against the single-handle run, long enough for many ownership transfers."""
-    import pyafv_b200 as afv
-    from pyafv_b200.sharded import LoopbackShardedSimulator
-    pts, theta, A0, L = _setup(6000, 0.4, 12)
-    phys = afv.PhysicalParams()
-    ref = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
-    ref.step(0.01, 1.0, 0.0, 0.0, n_steps=200)
-    pts = ref.pts.copy()
-    ref.step(0.01, 1.0, 2.4, 0.3, theta=theta, seed=5, n_steps=30)
-    sh = LoopbackShardedSimulator(pts, theta, phys, L, 4, overlap="strips")
-    sh.build()
-    owners0 = [set(s.store.results()[:, 4].cpu().numpy().astype(int).tolist()) for s in sh.ranks]
-    for s in sh.ranks:
-        s._step_index = 200
-    sh.step(0.01, 1.0, 2.4, 0.3, seed=5, n_steps=30)
-    assert all(s.overlapped_steps > 0 for s in sh.ranks)
-    b = sh.build()
-    d = b["pts"] - ref.pts
-    d -= L * np.round(d / L)
-    assert np.abs(d).max() <= 1e-8
-    assert np.abs(b["theta"] - ref.theta).max() <= 1e-10
-    owners1 = [set(s.store.results()[:, 4].cpu().numpy().astype(int).tolist()) for s in sh.ranks]
-    assert sum(len(o) for o in owners1) == len(pts)
-    assert any(o0 != o1 for o0, o1 in zip(owners0, owners1))      # cells did change owner
-    ref.close(); sh.close()
-
-
-def test_violent_start_runs_as_exchange_then_step():
-    """From an unrelaxed random configuration single cells jump many radii per step: the overlapped form must stay
-    disengaged (exchange-then-step tolerates any displacement) and the run must match the single-handle one."""
-    import pyafv_b200 as afv
-    from pyafv_b200.sharded import LoopbackShardedSimulator
-    pts, theta, A0, L = _setup(6000, 1.0, 33)
-    phys = afv.PhysicalParams()
-    ref = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
-    ref.step(0.01, 1.0, 0.0, 0.0, n_steps=6)
-    sh = LoopbackShardedSimulator(pts, None, phys, L, 2, overlap="strips")
-    sh.step(0.01, 1.0, 0.0, 0.0, n_steps=6)
-    assert all(s.overlapped_steps == 0 for s in sh.ranks)
-    d = sh.build()["pts"] - ref.pts
-    d -= L * np.round(d / L)
-    assert np.abs(d).max() <= 1e-8
-    ref.close(); sh.close()
-
-
-def test_overlapped_step_reports_a_cell_that_outruns_the_strip_margin():
-    """A cell of the interior that ends up in an exchange list within one step was not sent: the run must fail loudly."""
-    import pyafv_b200 as afv
-    from pyafv_b200.sharded import LoopbackShardedSimulator
-    pts, theta, A0, L = _setup(4000, 0.5, 3)
-    phys = afv.PhysicalParams()
-    sh = LoopbackShardedSimulator(pts, np.zeros(len(pts)), phys, L, 2, overlap="strips", strip_margin=0.05)
-    with pytest.raises(RuntimeError, match="strip margin|capacity"):
-        sh.step(1.0, 0.0, 2.0, 0.0, seed=1, n_steps=3)          # every cell moves 2 l per step in +x
-    sh.close()
