@@ -48,7 +48,7 @@ struct AfvContext {
     int face_cols = 0;
     int64_t face_len0 = 0, face_s1 = 0;   // sorted cells in the first face_cols columns / first slot of the last face_cols columns
     DevBuf late_keys, late_keys_sorted, late_perm, late_tmp;
-    cudaEvent_t ev_sorted = nullptr, ev_late = nullptr, ev_force = nullptr, ev_pack = nullptr;
+    cudaEvent_t ev_sorted = nullptr, ev_late = nullptr, ev_force = nullptr, ev_pack = nullptr, ev_interior = nullptr;
     int64_t late_steps = 0, late_deep_steps = 0;   // steps taken in the late form / of those, with the face pass over every cell
     bool late_mode = false;            // stepping with afv_late_*: column-major bins and the slab variants of the geometry kernels
     bool pack_pending = false;         // ev_pack was recorded: the next sort waits for the ownership marks of that pack
@@ -70,15 +70,17 @@ struct AfvContext {
     // results (sorted order)
     double *fx = nullptr, *fy = nullptr, *area = nullptr, *perim = nullptr, *arcl = nullptr;
     int *coord = nullptr;
-    unsigned char *ring_len = nullptr;
-    int *ring_key = nullptr, *hull_slot = nullptr;
-    unsigned char *hull_len = nullptr;
-    RingOwn *ro = nullptr;
-    RingSelf *self = nullptr;
+    unsigned char *ring_len = nullptr, *n_arc = nullptr;
+    double2 *ring_h = nullptr;    // slot-major ring: vertices
+    int *ring_nbr = nullptr;      //                  neighbour slot across the leaving edge (ARC = arc)
+    int2 *arc_key = nullptr;      // slot-major arcs (afv_device.cuh)
+    double4 *arc_pts = nullptr;
+    CellRec *rec = nullptr;       // per cell: position + energy prefactors, gathered by the neighbours in k_force
     int *flags = nullptr;         // device: [0] slow-path cells, [1] lookup misses, [2] max ring length, [3] hard overflows
-    int *ovf_cells = nullptr, *ovf_index = nullptr, *ovf_len = nullptr;
-    RingShared *ovf_rs = nullptr;
-    RingOwn *ovf_ro = nullptr;
+    int *ovf_cells = nullptr, *ovf_index = nullptr, *ovf_len = nullptr, *ovf_hull = nullptr, *ovf_m = nullptr, *ovf_ring_nbr = nullptr;
+    double2 *ovf_ring_h = nullptr;
+    int2 *ovf_arc_key = nullptr;
+    double4 *ovf_arc_pts = nullptr;
     int h_flags[4] = {0, 0, 0, 0};
     // scratch
     DevBuf scratch_a, scratch_b, noise_buf, conn_buf, ring_types, ring_xy, ring_off;
@@ -146,14 +148,15 @@ void free_all(AfvHandle h) {
     }
     cudaFree(h->keys); cudaFree(h->keys_sorted); cudaFree(h->iota); cudaFree(h->perm); cudaFree(h->bin_start);
     cudaFree(h->cub_tmp); cudaFree(h->fx); cudaFree(h->fy); cudaFree(h->area); cudaFree(h->perim); cudaFree(h->arcl);
-    cudaFree(h->coord); cudaFree(h->ring_len); cudaFree(h->ro); cudaFree(h->self); h->self = nullptr; cudaFree(h->cnt); cudaFree(h->off);
+    cudaFree(h->coord); cudaFree(h->ring_len); cudaFree(h->cnt); cudaFree(h->off);
+    cudaFree(h->ring_h); h->ring_h = nullptr; cudaFree(h->ring_nbr); h->ring_nbr = nullptr;
+    cudaFree(h->arc_key); h->arc_key = nullptr; cudaFree(h->arc_pts); h->arc_pts = nullptr;
+    cudaFree(h->n_arc); h->n_arc = nullptr; cudaFree(h->rec); h->rec = nullptr;
     cudaFree(h->ovf_index); h->ovf_index = nullptr;
-    cudaFree(h->ring_key); h->ring_key = nullptr;
-    cudaFree(h->hull_slot); h->hull_slot = nullptr; cudaFree(h->hull_len); h->hull_len = nullptr;
     cudaFree(h->bin_start_late); h->bin_start_late = nullptr;
     h->keys = h->keys_sorted = nullptr; h->iota = h->perm = h->bin_start = nullptr; h->cub_tmp = nullptr;
     h->fx = h->fy = h->area = h->perim = h->arcl = nullptr; h->coord = nullptr; h->ring_len = nullptr;
-    h->ro = nullptr; h->cnt = h->off = nullptr;
+    h->cnt = h->off = nullptr;
     h->cap = 0;
 }
 
@@ -207,11 +210,12 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     if ((rc = dev_alloc(h, &h->arcl, cap))) return rc;
     if ((rc = dev_alloc(h, &h->coord, cap))) return rc;
     if ((rc = dev_alloc(h, &h->ring_len, cap))) return rc;
-    if ((rc = dev_alloc(h, &h->ring_key, (size_t)cap * RS))) return rc;
-    if ((rc = dev_alloc(h, &h->hull_slot, (size_t)cap * KHULL_STRIDE))) return rc;
-    if ((rc = dev_alloc(h, &h->hull_len, cap))) return rc;
-    if ((rc = dev_alloc(h, &h->ro, (size_t)cap * RS))) return rc;
-    if ((rc = dev_alloc(h, &h->self, (size_t)cap * RS))) return rc;
+    if ((rc = dev_alloc(h, &h->n_arc, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->rec, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->ring_h, (size_t)cap * RS))) return rc;
+    if ((rc = dev_alloc(h, &h->ring_nbr, (size_t)cap * RS))) return rc;
+    if ((rc = dev_alloc(h, &h->arc_key, (size_t)cap * ARC_MAX))) return rc;
+    if ((rc = dev_alloc(h, &h->arc_pts, (size_t)cap * ARC_MAX))) return rc;
     if ((rc = dev_alloc(h, &h->ovf_index, cap))) return rc;
     if ((rc = dev_alloc(h, &h->cnt, cap + 1))) return rc;
     if ((rc = dev_alloc(h, &h->off, cap + 1))) return rc;
@@ -266,7 +270,7 @@ void collect_spans(AfvHandle h) {
     h->spans.clear();
 }
 
-RingView ring_view(AfvHandle h) { return RingView{h->self, h->ro, h->ring_len, h->ovf_index, h->ovf_len, h->ovf_rs, h->ovf_ro, (size_t)h->cap}; }
+RingView ring_view(AfvHandle h) { return RingView{h->ring_h, h->ring_nbr, h->ring_len, h->ovf_index, h->ovf_len, h->ovf_ring_h, h->ovf_ring_nbr, (size_t)h->cap}; }
 
 PhysDev phys_dev(const AfvParams &p) { return PhysDev{p.r, p.P0, p.KA, p.KP, p.Lambda, p.delta}; }
 
@@ -362,9 +366,11 @@ int stage_geometry(AfvHandle h, GeomPass gp = GeomPass()) {
     GeomArgs a;
     a.face_len0 = (int)h->face_len0; a.face_len1 = (int)face_len1; a.face_s1 = (int)h->face_s1;
     a.xy = h->xy[c]; a.a0 = h->a0[c]; a.keys = h->keys_sorted; a.bin_start = h->bin_start; a.grid = h->d_grid;
-    a.n = n; a.ph = phys_dev(h->prm); a.ro = h->ro; a.self = h->self; a.stride = (size_t)h->cap; a.ring_len = h->ring_len; a.ring_key = h->ring_key; a.hull_slot = h->hull_slot; a.hull_len = h->hull_len;
-    a.area = h->area; a.perim = h->perim; a.arcl = h->arcl; a.coord = h->coord; a.flags = h->flags;
-    a.ovf_cells = h->ovf_cells; a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
+    a.n = n; a.ph = phys_dev(h->prm); a.stride = (size_t)h->cap;
+    a.ring_h = h->ring_h; a.ring_nbr = h->ring_nbr; a.ring_len = h->ring_len; a.arc_key = h->arc_key; a.arc_pts = h->arc_pts; a.n_arc = h->n_arc;
+    a.rec = h->rec; a.area = h->area; a.perim = h->perim; a.arcl = h->arcl; a.coord = h->coord; a.flags = h->flags;
+    a.ovf_cells = h->ovf_cells; a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_hull = h->ovf_hull; a.ovf_m = h->ovf_m;
+    a.ovf_ring_h = h->ovf_ring_h; a.ovf_ring_nbr = h->ovf_ring_nbr; a.ovf_arc_key = h->ovf_arc_key; a.ovf_arc_pts = h->ovf_arc_pts;
     a.n_main = (int)h->n_main; a.bin_start_late = (gp.late && h->n_late > 0) ? h->bin_start_late : nullptr;
     a.filter = gp.filter; a.face_cols = h->face_cols;
     // candidate-list capacity per cell (shared memory scales with it): for a periodic box the mean number of cells
@@ -375,20 +381,13 @@ int stage_geometry(AfvHandle h, GeomPass gp = GeomPass()) {
         h->cmax_hint = std::max(h->cmax_hint, std::min(CMAX_HARD, std::max(24, (int)(1.8 * mean) + 12)));
     }
     int cmax = h->cmax_hint;
-    const size_t smem = (size_t)cmax * HULL_TPB * sizeof(int);
+    const size_t smem = geom_smem_bytes(cmax);
     cudaStream_t st = gp.stream ? gp.stream : h->stream;
     if (n > 0 && gp.fast) {
-        {
-            StageTimer t(h, 1, st);
-            if (h->late_mode) k_hull<true><<<nblk(n, HULL_TPB), HULL_TPB, smem, st>>>(a, cmax);
-            else k_hull<false><<<nblk(n, HULL_TPB), HULL_TPB, smem, st>>>(a, cmax);
-        }
-        {
-            StageTimer t(h, 2, st);
-            if (h->late_mode) k_ring<true><<<nblk(n, HULL_TPB), HULL_TPB, 0, st>>>(a);
-            else k_ring<false><<<nblk(n, HULL_TPB), HULL_TPB, 0, st>>>(a);
-        }
-        h->launches += 2;
+        StageTimer t(h, 1, st);
+        if (h->late_mode) k_geom<true><<<nblk(n, GEOM_TPB), GEOM_TPB, smem, st>>>(a, cmax);
+        else k_geom<false><<<nblk(n, GEOM_TPB), GEOM_TPB, smem, st>>>(a, cmax);
+        h->launches += 1;
     }
     if (gp.slow) {
         StageTimer t(h, 5, st);
@@ -407,8 +406,10 @@ int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, doub
     const int n = (int)h->n;
     const int c = h->cur;
     ForceArgs a;
-    a.ro = h->ro; a.self = h->self; a.stride = (size_t)h->cap; a.ring_len = h->ring_len; a.ring_key = h->ring_key; a.owned = h->owned[c]; a.gid = h->gid[c]; a.n = n;
-    a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_rs = h->ovf_rs; a.ovf_ro = h->ovf_ro;
+    a.ring_h = h->ring_h; a.ring_nbr = h->ring_nbr; a.stride = (size_t)h->cap; a.ring_len = h->ring_len; a.rec = h->rec;
+    a.n_arc = h->n_arc; a.arc_key = h->arc_key; a.arc_pts = h->arc_pts; a.grid = h->d_grid; a.owned = h->owned[c]; a.gid = h->gid[c]; a.n = n;
+    a.ovf_index = h->ovf_index; a.ovf_len = h->ovf_len; a.ovf_ring_h = h->ovf_ring_h; a.ovf_ring_nbr = h->ovf_ring_nbr;
+    a.ovf_arc_key = h->ovf_arc_key; a.ovf_arc_pts = h->ovf_arc_pts;
     a.ph = phys_dev(h->prm); a.fx = h->fx; a.fy = h->fy; a.flags = h->flags;
     a.do_step = do_step ? 1 : 0; a.xy = h->xy[c]; a.theta = h->th[c];
     a.dt = dt; a.mu = mu; a.v0 = v0; a.noise_amp = std::sqrt(2.0 * Dr * dt); a.seed = seed; a.step = step;
@@ -479,7 +480,7 @@ extern "C" {
 
 const char *afv_build_info(void) {
     static char buf[160];
-    snprintf(buf, sizeof buf, "afv_b200 sm_100a; ring_stride=%d; hull_capacity=%d; slow_path=%d/%d; cuda_runtime=%d", RS, KHULL, KPOLY_SLOW, RS_SLOW, CUDART_VERSION);
+    snprintf(buf, sizeof buf, "afv_b200 sm_100a; ring_stride=%d; polygon_capacity=%d; slow_path=%d/%d; cuda_runtime=%d", RS, KP, KPOLY_SLOW, RS_SLOW, CUDART_VERSION);
     return buf;
 }
 
@@ -509,25 +510,29 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else {
         e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete h; return AFV_ERR_CUDA; }
+        if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); h->stream = nullptr; afv_destroy(h); return AFV_ERR_CUDA; }
         h->own_stream = true;
     }
     if (cudaMalloc((void **)&h->d_grid, sizeof(GridDesc)) != cudaSuccess || cudaMalloc((void **)&h->flags, 8 * sizeof(int)) != cudaSuccess ||
         cudaMalloc((void **)&h->bbox_part, 4 * 1024 * sizeof(double)) != cudaSuccess) {
-        g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
+        g_create_error = "cudaMalloc failed"; afv_destroy(h); return AFV_ERR_CUDA;
     }
     if (cudaMalloc((void **)&h->ovf_cells, OVF_MAX * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->ovf_len, OVF_MAX * sizeof(int)) != cudaSuccess ||
-        cudaMalloc((void **)&h->ovf_rs, (size_t)OVF_MAX * RS_SLOW * sizeof(RingShared)) != cudaSuccess ||
-        cudaMalloc((void **)&h->ovf_ro, (size_t)OVF_MAX * RS_SLOW * sizeof(RingOwn)) != cudaSuccess) {
-        g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
+        cudaMalloc((void **)&h->ovf_hull, (size_t)OVF_MAX * KPOLY_SLOW * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&h->ovf_m, (size_t)OVF_MAX * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&h->ovf_ring_h, (size_t)OVF_MAX * RS_SLOW * sizeof(double2)) != cudaSuccess ||
+        cudaMalloc((void **)&h->ovf_ring_nbr, (size_t)OVF_MAX * RS_SLOW * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&h->ovf_arc_key, (size_t)OVF_MAX * ARC_SLOW * sizeof(int2)) != cudaSuccess ||
+        cudaMalloc((void **)&h->ovf_arc_pts, (size_t)OVF_MAX * ARC_SLOW * sizeof(double4)) != cudaSuccess) {
+        g_create_error = "cudaMalloc failed"; afv_destroy(h); return AFV_ERR_CUDA;
     }
     if (cudaMalloc((void **)&h->pair_cnt, 4 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 20 * sizeof(double)) != cudaSuccess ||
         cudaHostAlloc((void **)&h->pair_host, 20 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
-        g_create_error = "cudaMalloc failed"; delete h; return AFV_ERR_CUDA;
+        g_create_error = "cudaMalloc failed"; afv_destroy(h); return AFV_ERR_CUDA;
     }
     cudaMemsetAsync(h->flags, 0, 8 * sizeof(int), h->stream);
-    cudaFuncSetAttribute(k_hull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(int));
-    cudaFuncSetAttribute(k_hull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX_HARD * HULL_TPB * (int)sizeof(int));
+    cudaFuncSetAttribute(k_geom<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geom_smem_bytes(CMAX_HARD));
+    cudaFuncSetAttribute(k_geom<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geom_smem_bytes(CMAX_HARD));
 
     *out = h;
     return AFV_OK;
@@ -536,17 +541,18 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
 void afv_destroy(AfvHandle h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     free_all(h);
     cudaFree(h->d_grid); cudaFree(h->flags); cudaFree(h->bbox_part);
-    cudaFree(h->ovf_cells); cudaFree(h->ovf_len); cudaFree(h->ovf_rs); cudaFree(h->ovf_ro);
+    cudaFree(h->ovf_cells); cudaFree(h->ovf_len); cudaFree(h->ovf_hull); cudaFree(h->ovf_m); cudaFree(h->ovf_ring_h); cudaFree(h->ovf_ring_nbr);
+    cudaFree(h->ovf_arc_key); cudaFree(h->ovf_arc_pts);
     cudaFree(h->pair_cnt); cudaFree(h->pair_dev); cudaFreeHost(h->pair_host);
-    for (cudaEvent_t e : {h->ev_sorted, h->ev_late, h->ev_force, h->ev_pack}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->ev_sorted, h->ev_late, h->ev_force, h->ev_pack, h->ev_interior}) if (e) cudaEventDestroy(e);
     for (DevBuf *b : {&h->late_keys, &h->late_keys_sorted, &h->late_perm, &h->late_tmp}) cudaFree(b->p);
     for (DevBuf *b : {&h->scratch_a, &h->scratch_b, &h->noise_buf, &h->conn_buf, &h->ring_types, &h->ring_xy, &h->ring_off}) cudaFree(b->p);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
-    if (h->own_stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
@@ -690,7 +696,7 @@ int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t s
     const bool deferred = h->defer_checks && !noise_host;
     if (!deferred) CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
     for (int s = 0; s < n_steps; ++s) {
-        if (deferred) CK(cudaMemsetAsync(h->flags, 0, sizeof(int), h->stream));   // the slow-path queue restarts every step
+        CK(cudaMemsetAsync(h->flags, 0, sizeof(int), h->stream));   // the slow-path queue restarts every step (the error counters run on)
         if ((rc = stage_sort(h))) return rc;
         // open boundaries: the local density is unknown, so the capacity is checked (and grown) before the positions move
         if ((rc = (h->L > 0.0 ? stage_geometry(h) : geometry_checked(h)))) return rc;

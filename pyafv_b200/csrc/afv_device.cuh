@@ -40,27 +40,27 @@ __device__ __forceinline__ void bin_xy(const GridDesc &g, unsigned key, int &bx,
     bx = g.swap ? line : pos; by = g.swap ? pos : line;
 }
 
-// Shared part of a ring entry: what OTHER cells read during the force gather.  32 B = one DRAM sector.
-struct __align__(16) RingShared {
-    double gx, gy; // 2KA(A-A0) dA/dh + 2KP(P-P0) dP/dh of the OWNING cell at this vertex  (one 16-byte load)
-    double w;    // arc-end weight 2KA(A-A0) da + (2KP(P-P0) + Lambda) dl of the owning cell (outer vertices only)
-    int nbr;     // sorted slot of the neighbour across the edge LEAVING this vertex, ARC for an arc
-    int type;    // 1 straight contact edge, 0 arc  (finite_voronoi.py:441-459)
+// What a neighbour needs from a cell during the force gather: its position and the two energy prefactors
+// cA = 2 KA (A - A0), cP = 2 KP (P - P0).  32 B = one DRAM sector, so one gather per ring edge.
+// With these two scalars cell i can rebuild, from positions it already holds, every term of dE_j/dr_i that passes
+// through an inner vertex (circumcentre) -- see k_force.  Only outer vertices (circle-circle intersections, whose
+// Jacobian the reference regularises with delta) need one more datum from the neighbour: the far end of the
+// neighbour's arc that starts / ends there (ArcTable below).
+struct __align__(16) CellRec {
+    double x, y;    // copy of the cell centre (same bits as xy[])
+    double cA, cP;  // 2 KA (A - A0), 2 KP (P - P0)
 };
 
-// Private part of a ring entry: only the owning cell reads it back.  Stored SLOT-MAJOR, entry e of cell s at
-// [e * stride + s] (stride = allocated cells), so that the lanes of a warp -- consecutive cells working on the same
-// entry -- touch consecutive 32-byte records instead of 32 different cache lines.
-struct __align__(16) RingOwn {
-    double hx, hy;  // vertex position relative to the cell centre
-    double px, py;  // r_nbr - r_cell (minimum image) for the edge leaving this vertex (undefined for arcs)
-};
-// The owner's copy of its own gradient record, slot-major like RingOwn.  While k_ring runs, gx/gy hold scratch
-// (1/length of the straight edge leaving the vertex, or the cross/dot of an arc's end points).
-struct __align__(16) RingSelf {
-    double gx, gy, w;
-    int nbr, type;
-};
+// Ring storage, slot-major (entry e of cell s at [e * stride + s], stride = allocated cells), so that the lanes of a
+// warp -- consecutive cells working on the same entry -- touch consecutive words:
+//   ring_h[e]   vertex position relative to the cell centre (double2)
+//   ring_nbr[e] sorted slot of the neighbour across the edge LEAVING this vertex (clockwise), ARC for an arc
+// Arcs, slot-major as well (arc q of cell s): arc_key = (slot of the neighbour whose contact edge ENDS where the arc
+// starts, slot of the neighbour whose contact edge STARTS where the arc ends), arc_pts = (start x, y, end x, y)
+// relative to the cell centre.  A ring of E entries has at most E/2 arcs; the fast path stores 4 (a cell with more free
+// boundary pieces than that goes to the pool like a cell with a long ring).
+constexpr int ARC_MAX = 4;
+constexpr int ARC_SLOW = RS_SLOW / 2;
 
 __device__ __forceinline__ double min_image(double d, double L, double halfL) {
     if (d > halfL) d -= L;

@@ -1,19 +1,15 @@
 // K2: geometry of the finite-Voronoi cells.  Included by afv_kernels.cuh inside namespace afv.
 //
-// Fast path (k_geometry_hull): one thread per cell; the in-range neighbours of each cell are gathered once into
-// shared memory ([entry][lane] layout, conflict free) and the Voronoi polygon is found by gift wrapping in the
-// dual plane (half-plane p.x <= |p|^2/2  <->  dual point 2p/|p|^2; the cell's edges are the hull vertices, in
-// counter-clockwise order).  The loops are regular (hull steps x candidates), warp-uniform in their bounds, hold no
-// per-thread arrays while wrapping, and need no division; a vertex is computed once per final edge as the
-// intersection of its two bisectors.  Cells with too many in-range neighbours / hull vertices / ring entries are
-// queued for the slow path.
+// k_geom (fast path): one thread per cell.  The neighbours within 2r are gathered once into shared memory, the Voronoi
+// polygon is the bounding square clipped by their bisector half-planes (a linked list of edges in shared memory, the
+// links in a register), and the ring is walked right away, exactly as the reference defines it
+// (finite_voronoi.py:363-459), with area / perimeter / arc length (cell_geom.pyx:432-475) accumulated on the fly.
+// What it leaves behind for the force gather is small: the ring (vertex + neighbour slot, 20 B per entry), the arcs,
+// and ONE 32-byte record per cell with the energy prefactors 2KA(A-A0), 2KP(P-P0) -- no per-vertex gradient records.
 //
-// Slow path (k_geometry_slow): the queued cells, one thread each, by in-place clipping of a bounding square
-// (afv_device.cuh: clip_polygon) with large local arrays; long rings go to the overflow pool.
-//
-// Both paths then share finish_cell(): ring emission exactly as the reference defines it
-// (finite_voronoi.py:363-459), area / perimeter / arc length (cell_geom.pyx:432-475), per-vertex energy gradients
-// of this cell (cell_geom.pyx:478-539), written as ring records.
+// k_geometry_slow: cells whose neighbourhood / polygon / ring exceeds the fast-path capacity, one thread each:
+// in-place clipping of a bounding square (afv_device.cuh: clip_polygon) with large local arrays gives the polygon, a
+// ring walk that rebuilds the vertices from consecutive edges then writes into the overflow pool.
 
 struct GeomArgs {
     const double2 *xy;
@@ -23,22 +19,27 @@ struct GeomArgs {
     const GridDesc *grid;
     int n;
     PhysDev ph;
-    RingOwn *ro;               // slot-major, stride `stride`
-    RingSelf *self;            // slot-major, stride `stride`: gradient records, gathered by the neighbours in k_force
     size_t stride;             // allocated cells
-    unsigned char *ring_len;
-    int *hull_slot;            // [KHULL_STRIDE * stride], slot-major: polygon edges found by k_hull (neighbour slot, or -2 for the edge at infinity)
-    unsigned char *hull_len;   // [n] number of polygon edges; HULL_QUEUED when the cell went to the slow path
-    int *ring_key;             // [n * RS] neighbour slot of every ring entry (ARC for arcs; stale beyond ring_len): what k_force scans
+    double2 *ring_h;           // [RS * stride] slot-major ring vertices (relative to the cell centre)
+    int *ring_nbr;             // [RS * stride] slot-major: neighbour slot across the edge leaving the vertex, ARC for an arc
+    unsigned char *ring_len;   // [n] ring entries; RING_IN_POOL when the ring lives in the overflow pool
+    int2 *arc_key;             // [ARC_MAX * stride] slot-major, see afv_device.cuh
+    double4 *arc_pts;          // [ARC_MAX * stride]
+    unsigned char *n_arc;      // [n]
+    CellRec *rec;              // [n] what the neighbours gather in k_force
     double *area, *perim, *arcl;
     int *coord;
     int *flags;                // [0] cells sent to the slow path, [1] lookup misses, [2] max ring length, [3] hard overflows
     // slow path (cells whose neighbourhood / polygon / ring exceeds the fast-path capacity)
-    int *ovf_cells;            // [OVF_MAX] sorted slots queued by the fast kernel
+    int *ovf_cells;            // [OVF_MAX] sorted slots queued by the fast kernels
     int *ovf_index;            // [n] slot -> pool index, valid where ring_len == RING_IN_POOL
     int *ovf_len;              // [OVF_MAX] ring length of pooled rings
-    RingShared *ovf_rs;        // [OVF_MAX * RS_SLOW]
-    RingOwn *ovf_ro;
+    int *ovf_hull;             // [OVF_MAX * KPOLY_SLOW] polygon of a queued cell (neighbour slots counter-clockwise, -2: edge at infinity)
+    int *ovf_m;                // [OVF_MAX] its edge count when k_geom handed the polygon over, 0: clip from scratch
+    double2 *ovf_ring_h;       // [OVF_MAX * RS_SLOW]
+    int *ovf_ring_nbr;         // [OVF_MAX * RS_SLOW]
+    int2 *ovf_arc_key;         // [OVF_MAX * ARC_SLOW]
+    double4 *ovf_arc_pts;      // [OVF_MAX * ARC_SLOW]
     // late cells (slab sharding with the exchange overlapped): cells appended behind the sorted ones AFTER the sort,
     // slots n_main .. n-1, with a bin table of their own (entries relative to n_main)
     int n_main;
@@ -68,164 +69,6 @@ __device__ __forceinline__ bool pass_selects(const GeomArgs &a, const GridDesc &
 }
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
-constexpr int KHULL_STRIDE = 16;
-constexpr int HULL_QUEUED = 255;
-
-// ------------------------------------------------------------------------------------------------------
-// Shared second half.  Input: the convex polygon of the cell, counter-clockwise, relative to the centre: vertex k,
-// and for the edge from vertex k to vertex k+1 the displacement (px,py) of the neighbour whose bisector carries
-// it and that neighbour's sorted slot `lab` (< 0: side of the bounding square).
-// LOCKSTEP: every lane of the warp calls this (invalid lanes with m = 0); loop bounds are warp maxima so that the
-// expensive bodies run converged.
-// ------------------------------------------------------------------------------------------------------
-template <int K, int R, bool SLOW>
-__device__ __forceinline__ void finish_cell(const GeomArgs &a, const int s, const int pool_idx, const bool live, bool ok,
-                                            const double (&vx)[K], const double (&vy)[K], const double (&px)[K],
-                                            const double (&py)[K], const int (&lab)[K], const int m) {
-    constexpr bool LOCKSTEP = !SLOW;
-    const double r = a.ph.r, r2 = r * r;
-    const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
-
-    // ---- ring, clockwise: edge k of the ccw polygon is walked from vertex k+1 to vertex k ----
-    double hx[R], hy[R], qx[R], qy[R];
-    int typ[R], nbr[R];
-    int E = 0;
-    const int mm = (live && ok) ? m : 0;
-    const int mloop = LOCKSTEP ? __reduce_max_sync(FULL_MASK, mm) : mm;
-    for (int kk = 0; kk < mloop; ++kk) {
-        if (kk < mm && ok) {
-            const int k = mm - 1 - kk;
-            const int j = lab[k];
-            if (j >= 0) {                                  // j < 0: side of the bounding square (the reference's ray-ray pair)
-                if (E + 2 > R) ok = false;                 // an edge emits at most 2 entries
-                else {
-                    const int k1 = (k + 1 == mm) ? 0 : k + 1;
-                    const double V1x = vx[k1], V1y = vy[k1], V2x = vx[k], V2y = vy[k];
-                    const double ex = px[k], ey = py[k];
-                    if (V1x * V1x + V1y * V1y <= r2) {     // inner start vertex: d1 <= r  (finite_voronoi.py:375-377)
-                        hx[E] = V1x; hy[E] = V1y; qx[E] = ex; qy[E] = ey; typ[E] = 1; nbr[E] = j; ++E;
-                    }
-                    const double d2c = 0.25 * (ex * ex + ey * ey);   // |C|^2, C = p/2 the foot of the bisector
-                    if (d2c < r2) {                        // bisector crosses the disk (finite_voronoi.py:395-407)
-                        // clockwise unit vector along the bisector: u = (ey, -ex)/|p|
-                        const double inv = 0.5 / sqrt(d2c);
-                        const double ux = ey * inv, uy = -ex * inv;
-                        const double t1 = V1x * ux + V1y * uy, t2 = V2x * ux + V2y * uy;
-                        const double tr = sqrt(r2 - d2c);
-                        const double Cx = 0.5 * ex, Cy = 0.5 * ey;
-                        if (-tr < t2 && -tr > t1) {        // entry point: the straight edge starts on the circle
-                            hx[E] = Cx - tr * ux; hy[E] = Cy - tr * uy; qx[E] = ex; qy[E] = ey; typ[E] = 1; nbr[E] = j; ++E;
-                        }
-                        if (tr < t2 && tr > t1) {          // exit point: an arc starts here
-                            hx[E] = Cx + tr * ux; hy[E] = Cy + tr * uy; qx[E] = ex; qy[E] = ey; typ[E] = 0; nbr[E] = ARC; ++E;
-                        }
-                    }
-                }
-            }
-        }
-    }
-
-    if (live && !ok) {
-        if (!SLOW) {  // queue the cell for the large-capacity kernel
-            const int idx = atomicAdd(&a.flags[0], 1);
-            if (idx < OVF_MAX) a.ovf_cells[idx] = s; else atomicAdd(&a.flags[3], 1);
-            a.ring_len[s] = 0;
-        } else {
-            atomicAdd(&a.flags[3], 1);  // exceeded even the slow-path capacity: the host reports AFV_ERR_CAPACITY
-        }
-    }
-    const bool act = live && (ok || SLOW);     // this lane writes results
-    if (!ok) E = 0;
-
-    // ---- measures (cell_geom.pyx:402-475) ----
-    const bool ringed = act && E >= 2;
-    if (act && E < 2) {
-        a.area[s] = PI * r2; a.perim[s] = TWO_PI * r; a.arcl[s] = TWO_PI * r; a.coord[s] = 0;
-        a.ring_len[s] = 0;
-    }
-    const int EE = ringed ? E : 0;
-    const int Eloop = LOCKSTEP ? __reduce_max_sync(FULL_MASK, EE) : EE;
-    double ux_[R], uy_[R];   // unit vector (v1 - v2)/|v1 - v2| of straight edge e, 0 for arcs
-    int arc_e[R / 2 + 1];
-    int n_arc = 0;
-    double A = 0.0, P = 0.0, Larc = 0.0;
-    int z = 0;
-    for (int e = 0; e < Eloop; ++e) {
-        if (e < EE) {
-            const int e2 = (e + 1 == EE) ? 0 : e + 1;
-            if (typ[e] == 1) {
-                const double v1x = hx[e], v1y = hy[e], v2x = hx[e2], v2y = hy[e2];
-                const double sx = v1x - v2x, sy = v1y - v2y;
-                const double l2 = sx * sx + sy * sy;
-                const double l = sqrt(l2);
-                P += l;
-                A += -0.5 * (v1x * v2y - v1y * v2x);
-                const double il = l > 0.0 ? 1.0 / l : 0.0;
-                ux_[e] = sx * il; uy_[e] = sy * il;
-                ++z;
-            } else {
-                ux_[e] = 0.0; uy_[e] = 0.0;
-                if (n_arc < R / 2 + 1) arc_e[n_arc++] = e;
-            }
-        }
-    }
-    // arcs, compacted so that the lanes of a warp evaluate their atan2 together
-    const int aloop = LOCKSTEP ? __reduce_max_sync(FULL_MASK, n_arc) : n_arc;
-    for (int q = 0; q < aloop; ++q) {
-        if (q < n_arc) {
-            const int e = arc_e[q];
-            const int e2 = (e + 1 == EE) ? 0 : e + 1;
-            const double v1x = hx[e], v1y = hy[e], v2x = hx[e2], v2y = hy[e2];
-            double ang = atan2(v2x * v1y - v2y * v1x, v1x * v2x + v1y * v2y);  // angle(v1) - angle(v2)
-            if (ang < 0.0) ang += TWO_PI;
-            Larc += r * ang;
-            A += 0.5 * r2 * ang;
-        }
-    }
-    P += Larc;
-
-    RingShared *rs = nullptr;       // only pooled rings have per-cell records
-    RingOwn *ro = a.ro + s;
-    size_t ros = a.stride;          // RingOwn / RingSelf element stride (slot-major), 1 inside the overflow pool
-    bool pooled = false;
-    double cA = 0.0, cP = 0.0, cL = 0.0;
-    if (ringed) {
-        a.area[s] = A; a.perim[s] = P; a.arcl[s] = Larc; a.coord[s] = z;
-        if (SLOW && E > RS) {
-            a.ring_len[s] = RING_IN_POOL; a.ovf_index[s] = pool_idx; a.ovf_len[pool_idx] = E;
-            rs = a.ovf_rs + (size_t)pool_idx * RS_SLOW; ro = a.ovf_ro + (size_t)pool_idx * RS_SLOW; ros = 1; pooled = true;
-        } else {
-            a.ring_len[s] = (unsigned char)E;
-        }
-        if (E > 12) atomicMax(&a.flags[2], E);
-        cA = 2.0 * a.ph.KA * (A - a.a0[s]);
-        cP = 2.0 * a.ph.KP * (P - a.ph.P0);
-        cL = cP + a.ph.Lambda;
-    }
-
-    // ---- per-vertex gradients of this cell (cell_geom.pyx:478-539) ----
-    for (int e = 0; e < Eloop; ++e) {
-        if (e < EE) {
-            const int e2 = (e + 1 == EE) ? 0 : e + 1, e0 = (e == 0) ? EE - 1 : e - 1;
-            // dA/dv1 = 0.5 (perp(v0) - perp(v2)), perp(u) = (uy, -ux);  dP/dv1 = u(e) - u(e-1)
-            const double gx = cA * 0.5 * (hy[e0] - hy[e2]) + cP * (ux_[e] - ux_[e0]);
-            const double gy = cA * 0.5 * (hx[e2] - hx[e0]) + cP * (uy_[e] - uy_[e0]);
-            double w = 0.0;
-            if (typ[e] == 0)        // an arc starts here: da = +0.5 r^2 (1 - cos D), dl = +r
-                w = cA * 0.5 * (r2 - (hx[e] * hx[e2] + hy[e] * hy[e2])) + cL * r;
-            else if (typ[e0] == 0)  // an arc ends here
-                w = -(cA * 0.5 * (r2 - (hx[e0] * hx[e] + hy[e0] * hy[e])) + cL * r);
-            RingOwn q; q.hx = hx[e]; q.hy = hy[e]; q.px = qx[e]; q.py = qy[e];
-            ro[e * ros] = q;
-            if (pooled) { RingShared o; o.nbr = nbr[e]; o.type = typ[e]; o.gx = gx; o.gy = gy; o.w = w; rs[e] = o; }
-            else { RingSelf f; f.gx = gx; f.gy = gy; f.w = w; f.nbr = nbr[e]; f.type = typ[e]; a.self[e * a.stride + s] = f; }
-        }
-    }
-    if (ringed && E <= RS) {   // the compact key row that k_force scans (entries beyond ring_len are stale)
-        int *key = a.ring_key + (size_t)s * RS;
-        for (int e = 0; e < EE; ++e) key[e] = nbr[e];
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------
 // candidate runs of one line of bins (a row; a column when the grid is swapped): positions pos-1..pos+1 of the line as
@@ -269,184 +112,319 @@ __device__ __forceinline__ int cell_rows(const int nline, const bool per, int li
 // ------------------------------------------------------------------------------------------------------
 // fast path
 // ------------------------------------------------------------------------------------------------------
-constexpr int HULL_TPB = 128;
-constexpr int KHULL = 16;        // hull vertices (= polygon edges) on the fast path
-constexpr int CMAX_HARD = 128;   // upper bound of the per-cell candidate list (the launch picks cmax <= this); < 255 (8-bit hull indices)
+constexpr int GEOM_TPB = 64;
+constexpr int KP = 14;           // polygon edges on the fast path (<= 16: the links are 4-bit)
+constexpr int CMAX_HARD = 128;   // upper bound of the per-cell candidate list (the launch picks cmax <= this); < 252 (8-bit labels)
+constexpr int LAB_SIDE = -2;     // polygon-edge labels LAB_SIDE - q: side q of the bounding square (labels >= 0: sorted slots)
 
-#ifndef HULL_MIN_BLOCKS
-#define HULL_MIN_BLOCKS 10
+inline size_t geom_smem_bytes(int cmax) { return (size_t)GEOM_TPB * ((size_t)cmax * sizeof(int) + (size_t)KP * (sizeof(double2) + sizeof(int))); }
+
+#ifndef GEOM_MIN_BLOCKS
+#define GEOM_MIN_BLOCKS 8
 #endif
+// One thread per cell, everything between the candidate gather and the ring on chip:
+// (1) gather: the sorted slots of all neighbours within 2r, from the 3 bin rows (<= 2 contiguous runs each), into a
+//     per-thread list in shared memory ([entry][thread], conflict free);
+// (2) polygon: a bounding square (half side 2r) clipped by the bisector half-plane of every listed neighbour.  The
+//     polygon (vertex + edge label per slot, <= KP slots, counter-clockwise) lives in shared memory.  Per neighbour one
+//     unrolled pass evaluates every vertex against the half-plane (one 16-byte shared load + 2 FMAs each) into a bit
+//     mask; the edges that leave / re-enter the half-plane follow from two bit operations, the (<= 2) new vertices are
+//     the intersections of the two generating bisectors (a vertex is a function of its generating triple only,
+//     independent of the order of the cuts), and the list is patched in place;
+// (3) ring + measures: the walk of k_geometry_slow's ring_cell, but with the vertices at hand: clockwise, starting at
+//     the edge of the nearest neighbour (so that every sum is taken in an order the geometry defines, not the sort).
+// Cells with more than cmax neighbours, KP polygon edges, RS ring entries or ARC_MAX arcs are queued for
+// k_geometry_slow.
 // SLAB = false: one box, every cell, rows of bins contiguous (the single-GPU path, nothing of the slab machinery is
 // compiled in).  SLAB = true: an x-slab -- columns contiguous, pass filters, the late cells' bin table.
 template <bool SLAB>
-__global__ void __launch_bounds__(HULL_TPB, SLAB ? HULL_MIN_BLOCKS - 1 : HULL_MIN_BLOCKS) k_hull(GeomArgs a, const int cmax) {
-    extern __shared__ int s_idx[];               // [cmax][HULL_TPB]: sorted slots of the in-range neighbours of each lane's cell
+__global__ void __launch_bounds__(GEOM_TPB, GEOM_MIN_BLOCKS) k_geom(GeomArgs a, const int cmax) {
+    extern __shared__ double2 s_mem[];
     const int tid = threadIdx.x;
-    const int t_ = blockIdx.x * HULL_TPB + tid;
+    double2 *const sv = s_mem + tid;                                                       // [KP][TPB] start vertex of edge k
+    int *const sl = reinterpret_cast<int *>(s_mem + KP * GEOM_TPB) + tid;                  // [KP][TPB] label: sorted slot of the neighbour, or LAB_SIDE - q
+    int *const si = reinterpret_cast<int *>(s_mem + KP * GEOM_TPB) + KP * GEOM_TPB + tid;  // [cmax][TPB] sorted slots of the neighbours
+    constexpr int T = GEOM_TPB;
+    const int t_ = blockIdx.x * GEOM_TPB + tid;
     bool live = t_ < a.n;
     const int s = SLAB ? slot_of_thread(a, t_) : t_;
-    const double r = a.ph.r, cut2 = 4.0 * r * r;
+    const double r = a.ph.r, r2 = r * r, cut2 = 4.0 * r2;
     GridDesc g = *a.grid;
     if (!SLAB) g.swap = 0;
-    int n = 0, imin = 0;
+    int n = 0, imin = -1;
     bool ok = true;
     double xi = 0.0, yi = 0.0;
     bool wrapx = false, wrapy = false;            // only cells in the outermost bins can see a periodic image
-    int bx = 0, by = 0;
     if (live) {
+        int bx, by;
         bin_xy(g, a.keys[s], bx, by);
         if (SLAB) live = pass_selects(a, g, s, bx);
-    }
-
-    // ---- gather the neighbours within 2r: the sorted cells, then (face pass of a slab) the late cells ----
-    if (live) {
-        const double2 pi_ = a.xy[s];
-        xi = pi_.x; yi = pi_.y;
-        wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);
-        wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
-        // lines of bins: rows, or columns in a swapped (slab) grid
-        const int npos = g.swap ? g.nby : g.nbx, nline = g.swap ? g.nbx : g.nby, pos = g.swap ? by : bx;
-        const bool per_pos = g.swap ? g.pery : g.perx, per_line = g.swap ? g.perx : g.pery;
-        int rows[3];
-        const int nrow = cell_rows(nline, per_line, g.swap ? bx : by, rows);
-        double dmin = 1e300;
-        for (int tab = 0; tab < (SLAB ? 2 : 1); ++tab) {
-            const int *const bin_start = tab ? a.bin_start_late : a.bin_start;
-            if (!bin_start) break;
-            const int first = tab ? a.n_main : 0;
-            for (int ir = 0; ir < nrow; ++ir) {
-                int c0[2], c1[2];
-                const int nrun = row_runs(npos, per_pos, bin_start, rows[ir], pos, c0, c1);
-                for (int q = 0; q < nrun; ++q) {
+        if (live) {
+            // ---- (1) neighbours within 2r: the sorted cells, then (face pass of a slab) the late cells ----
+            const double2 pi_ = a.xy[s];
+            xi = pi_.x; yi = pi_.y;
+            wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);
+            wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
+            // lines of bins: rows, or columns in a swapped (slab) grid
+            const int npos = g.swap ? g.nby : g.nbx, nline = g.swap ? g.nbx : g.nby, pos = g.swap ? by : bx;
+            const bool per_pos = g.swap ? g.pery : g.perx, per_line = g.swap ? g.perx : g.pery;
+            int rows[3];
+            const int nrow = cell_rows(nline, per_line, g.swap ? bx : by, rows);
+            double dmin = 1e300;
+            for (int tab = 0; tab < (SLAB ? 2 : 1); ++tab) {
+                const int *const bin_start = tab ? a.bin_start_late : a.bin_start;
+                if (!bin_start) break;
+                const int first = tab ? a.n_main : 0;
+                for (int ir = 0; ir < nrow; ++ir) {
+                    int c0[2], c1[2];
+                    const int nrun = row_runs(npos, per_pos, bin_start, rows[ir], pos, c0, c1);
+                    for (int q = 0; q < nrun; ++q) {
 #pragma unroll 4
-                    for (int c = first + c0[q]; c < first + c1[q]; ++c) {
-                        const double2 pc = a.xy[c];
-                        double dx = pc.x - xi, dy = pc.y - yi;
-                        if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
-                        if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
-                        const double d2 = dx * dx + dy * dy;
-                        if (d2 < cut2 && c != s && d2 > 0.0) {
-                            if (n < cmax) {
-                                s_idx[n * HULL_TPB + tid] = c;
-                                if (d2 < dmin) { dmin = d2; imin = n; }
-                                ++n;
-                            } else ok = false;
+                        for (int c = first + c0[q]; c < first + c1[q]; ++c) {
+                            const double2 pc = a.xy[c];
+                            double dx = pc.x - xi, dy = pc.y - yi;
+                            if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
+                            if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
+                            const double d2 = dx * dx + dy * dy;
+                            if (d2 < cut2 && c != s && d2 > 0.0) {
+                                if (n < cmax) {
+                                    si[n * T] = c;
+                                    if (d2 < dmin) { dmin = d2; imin = n; }
+                                    ++n;
+                                } else ok = false;
+                            }
                         }
                     }
                 }
             }
         }
     }
-    // ---- gift wrapping in the dual plane.  List entry c <-> homogeneous dual point (p_c, k_c) with k_c = |p_c|^2
-    //      (twice the true k; the factor cancels in every sign).  Entry n is the ORIGIN of the dual plane, (p, k) =
-    //      ((0,0), 2): the "half-plane at infinity".  It becomes a hull vertex exactly when the neighbours do not
-    //      surround the cell, i.e. when the Voronoi polygon is unbounded; the two polygon edges next to it then run
-    //      off to infinity.
-    //      orient(a, b, c) = sign((p_b k_a - p_a k_b) x (p_c k_a - p_a k_c));  the nearest neighbour is on the hull.
-    //      Two independent running-best chains (even / odd list entries) halve the dependent latency.  The loop is
-    //      compiled twice: warps none of whose cells touches a periodic face skip the minimum-image code. ----
-    unsigned long long hull_lo = 0ull, hull_hi = 0ull;   // 16 x 8-bit list indices (n = the origin)
-    int m = 0;
-    const bool wrap = live && ok && n > 0;
-    const int npair_max = (__reduce_max_sync(FULL_MASK, wrap ? n : 0) + 1) >> 1;
-    auto hull_steps = [&](auto wrap_tag) {
-        constexpr bool W = decltype(wrap_tag)::value;
-        auto disp = [&](int c, double &dx, double &dy) {       // displacement of list entry c (< n)
-            const double2 pc = a.xy[s_idx[c * HULL_TPB + tid]];
-            dx = pc.x - xi; dy = pc.y - yi;
-            if (W) {
-                if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
-                if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
-            }
-        };
-        bool done = !wrap;
-        int cur = imin;
-        while (__any_sync(FULL_MASK, !done)) {
-            double pax = 0.0, pay = 0.0, ka = 2.0;
-            if (!done) {
-                if (m < 8) hull_lo |= (unsigned long long)cur << (8 * m); else hull_hi |= (unsigned long long)cur << (8 * (m - 8));
-                ++m;
-                if (cur < n) { disp(cur, pax, pay); ka = pax * pax + pay * pay; }
-            }
-            int best0 = -1, best1 = -1;
-            double u0x = 0.0, u0y = 0.0, u1x = 0.0, u1y = 0.0;
-            for (int cp = 0; cp < npair_max; ++cp) {
-                const int ca = 2 * cp, cb = 2 * cp + 1;
-                if (!done && ca < n && ca != cur) {
-                    double qx_, qy_; disp(ca, qx_, qy_);
-                    const double kc = qx_ * qx_ + qy_ * qy_;
-                    const double wx = qx_ * ka - pax * kc, wy = qy_ * ka - pay * kc;
-                    if (best0 < 0 || u0x * wy - u0y * wx < 0.0) { best0 = ca; u0x = wx; u0y = wy; }
-                }
-                if (!done && cb < n && cb != cur) {
-                    double qx_, qy_; disp(cb, qx_, qy_);
-                    const double kc = qx_ * qx_ + qy_ * qy_;
-                    const double wx = qx_ * ka - pax * kc, wy = qy_ * ka - pay * kc;
-                    if (best1 < 0 || u1x * wy - u1y * wx < 0.0) { best1 = cb; u1x = wx; u1y = wy; }
-                }
-            }
-            if (!done) {
-                // merge the chains: the overall next hull vertex is the one with every other point on its left
-                int best = best0;
-                double ux = u0x, uy = u0y;
-                if (best0 < 0 || (best1 >= 0 && u0x * u1y - u0y * u1x < 0.0)) { best = best1; ux = u1x; uy = u1y; }
-                // the origin: w = 0 * k_a - p_a * k_O, direction -p_a.  An exact tie means q_a, the origin and the best
-                // neighbour are collinear (e.g. collinear cells): the farther point wins, as in any gift wrapping;
-                // |q_c - q_a| is proportional to |w_c| / k_c.
-                if (cur != n) {
-                    const double wx = -pax, wy = -pay;
-                    bool take = best < 0;
-                    if (!take) {
-                        const double cr = ux * wy - uy * wx;
-                        if (cr < 0.0) take = true;
-                        else if (cr == 0.0) {
-                            double bx_, by_;
-                            disp(best, bx_, by_);
-                            const double kb = bx_ * bx_ + by_ * by_;
-                            take = (wx * wx + wy * wy) * kb * kb > (ux * ux + uy * uy);
-                        }
-                    }
-                    if (take) best = n;
-                }
-                cur = best;
-                if (cur == imin) done = true;
-                else if (m >= KHULL) { ok = false; done = true; }
-            }
-        }
+    __syncwarp();
+    // displacement of the cell in sorted slot `slot`; normal of a polygon edge (2 x the foot point of its bisector)
+    auto disp_of = [&](int slot, double &dx, double &dy) {
+        const double2 pc = a.xy[slot];
+        dx = pc.x - xi; dy = pc.y - yi;
+        if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
+        if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
     };
-    if (__any_sync(FULL_MASK, wrapx || wrapy)) hull_steps(std::true_type{}); else hull_steps(std::false_type{});
+    const double B = 2.0 * r;                     // half side of the bounding square: its sides are bisectors of virtual neighbours at 4r
+    auto normal_of = [&](int lab, double &nx, double &ny) {
+        if (lab < 0) {
+            const int q = LAB_SIDE - lab;         // bottom, right, top, left
+            nx = (q == 1) ? 2.0 * B : ((q == 3) ? -2.0 * B : 0.0);
+            ny = (q == 0) ? -2.0 * B : ((q == 2) ? 2.0 * B : 0.0);
+        } else disp_of(lab, nx, ny);
+    };
 
-    // ---- hand the polygon to k_ring ----
-    if (live) {
-        if (!ok) {   // too many neighbours / hull vertices for the fast path: queue for the large-capacity kernel
-            const int idx = atomicAdd(&a.flags[0], 1);
-            if (idx < OVF_MAX) a.ovf_cells[idx] = s; else atomicAdd(&a.flags[3], 1);
-            a.hull_len[s] = HULL_QUEUED;
-        } else {
-            const int mm = wrap ? m : 0;
-            a.hull_len[s] = (unsigned char)mm;
-            int *hs = a.hull_slot + s;                       // slot-major: edge k at hs[k * stride]
-            for (int k = 0; k < mm; ++k) {
-                const int h = (int)(((k < 8) ? (hull_lo >> (8 * k)) : (hull_hi >> (8 * (k - 8)))) & 0xffull);
-                hs[k * a.stride] = (h < n) ? s_idx[h * HULL_TPB + tid] : -2;   // -2: the edge at infinity
+    // ---- (2) the polygon: edge k (counter-clockwise) runs from vertex k to vertex k+1; sv[k] = vertex k, sl[k] = the sorted
+    //      slot of the neighbour whose bisector carries edge k (LAB_SIDE - q: side q of the bounding square) ----
+    int m = 4;
+    const bool work = live && ok && n > 0;
+    if (work) {
+        sv[0 * T] = make_double2(-B, -B); sv[1 * T] = make_double2(B, -B); sv[2 * T] = make_double2(B, B); sv[3 * T] = make_double2(-B, B);
+        sl[0 * T] = LAB_SIDE; sl[1 * T] = LAB_SIDE - 1; sl[2 * T] = LAB_SIDE - 2; sl[3 * T] = LAB_SIDE - 3;
+    }
+    {
+        const int nloop = __reduce_max_sync(FULL_MASK, work ? n : 0);
+        int cnext = 0;
+        double2 pnext = make_double2(0.0, 0.0);
+        if (work) { cnext = si[0]; pnext = a.xy[cnext]; }
+        for (int ci = 0; ci < nloop; ++ci) {
+            const bool act = work && ok && ci < n;
+            // slot and position of this neighbour (requested one iteration ago); request the next one
+            const int c = cnext;
+            const double2 pc = pnext;
+            if (work && ci + 1 < n) { cnext = si[(ci + 1) * T]; pnext = a.xy[cnext]; }
+            double nx = pc.x - xi, ny = pc.y - yi;
+            if (wrapx) nx = min_image(nx, g.Lx, g.halfLx);
+            if (wrapy) ny = min_image(ny, g.Ly, g.halfLy);
+            const double cc = 0.5 * (nx * nx + ny * ny);
+            // which vertices lie inside the new half-plane?  (bit k; the loop bound is the warp's largest polygon)
+            unsigned in = 0u;
+            const int mloop = __reduce_max_sync(FULL_MASK, act ? m : 0);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                if (k >= mloop) break;
+                const double2 v = sv[k * T];
+                if (fma(nx, v.x, ny * v.y) <= cc) in |= 1u << k;
+            }
+            const unsigned full = (1u << m) - 1u;
+            in &= full;
+            if (act && in != full && in != 0u) {
+                // ea: the edge that leaves the half-plane (vertex ea inside, vertex ea+1 outside); eb: the edge that comes back
+                const unsigned rot = ((in >> 1) | ((in & 1u) << (m - 1))) & full;      // bit k = vertex k+1 inside
+                const int ea = __ffs(in & ~rot) - 1, eb = __ffs(~in & rot & full) - 1;
+                const int lab_a = sl[ea * T], lab_b = sl[eb * T];
+                // P = edge ea ^ new bisector, Q = edge eb ^ new bisector (intersections of the two generating bisectors)
+                double ax, ay, bx_, by_;
+                normal_of(lab_a, ax, ay);
+                normal_of(lab_b, bx_, by_);
+                const double ca = 0.5 * (ax * ax + ay * ay), cb = 0.5 * (bx_ * bx_ + by_ * by_);
+                const double ida = __drcp_rn(ax * ny - ay * nx), idb = __drcp_rn(bx_ * ny - by_ * nx);
+                const double2 Pv = make_double2((ca * ny - cc * ay) * ida, (ax * cc - nx * ca) * ida);
+                const double2 Qv = make_double2((cb * ny - cc * by_) * idb, (bx_ * cc - nx * cb) * idb);
+                int at;                           // P goes to slot `at`, Q to `at + 1`
+                if (ea < eb) {
+                    // vertices ea+1 .. eb are cut off; keep 0 .. ea, then P, Q, then eb+1 .. m-1
+                    const int sh = 2 - (eb - ea);
+                    if (m + sh > KP) ok = false;
+                    else {
+                        if (sh > 0) { for (int k = m - 1; k > eb; --k) { sv[(k + 1) * T] = sv[k * T]; sl[(k + 1) * T] = sl[k * T]; } }
+                        else if (sh < 0) { for (int k = eb + 1; k < m; ++k) { sv[(k + sh) * T] = sv[k * T]; sl[(k + sh) * T] = sl[k * T]; } }
+                        m += sh;
+                    }
+                    at = ea + 1;
+                } else {
+                    // the cut-off run wraps around the end of the list: keep eb+1 .. ea (moved to the front), then P, Q
+                    const int s0 = eb + 1, cnt = ea - eb;
+                    if (cnt + 2 > KP) ok = false;
+                    else for (int k = 0; k < cnt; ++k) { sv[k * T] = sv[(k + s0) * T]; sl[k * T] = sl[(k + s0) * T]; }
+                    m = cnt + 2;                  // <= the old m
+                    at = cnt;
+                }
+                if (ok) { sv[at * T] = Pv; sl[at * T] = c; sv[(at + 1) * T] = Qv; sl[(at + 1) * T] = lab_b; }
             }
         }
+    }
+
+    const bool poly_ok = work && ok;
+    // ---- (3) ring, clockwise from the edge of the nearest neighbour: edge k is walked from the start of its
+    //      counter-clockwise successor (V1) to its own start (V2)  (finite_voronoi.py:363-459) ----
+    const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
+    double2 *const rh = a.ring_h + (live ? s : 0);
+    int *const rn = a.ring_nbr + (live ? s : 0);
+    int2 *const ak = a.arc_key + (live ? s : 0);
+    double4 *const ap = a.arc_pts + (live ? s : 0);
+    const size_t ros = a.stride;
+    int E = 0, z = 0, na = 0;
+    double A = 0.0, P = 0.0;
+    double x0 = 0.0, y0 = 0.0;                   // first ring entry
+    int nbr0 = ARC;
+    double xp = 0.0, yp = 0.0;                   // previous ring entry
+    int nbr_p = ARC, arc_from = ARC;             // its leaving edge; the contact edge that ended where the pending arc starts
+    // connect the previous entry to (x, y), the start of the edge with neighbour nb
+    auto close_prev = [&](double x, double y, int nb) {
+        if (nbr_p != ARC) {
+            const double sx = xp - x, sy = yp - y;
+            const double l2 = sx * sx + sy * sy;
+            P += l2 > 0.0 ? l2 * rsqrt(l2) : 0.0;
+            A += -0.5 * (xp * y - yp * x);
+            ++z;
+        } else if (na < ARC_MAX) {               // the arc that started at (xp, yp) ends here
+            ak[na * ros] = make_int2(arc_from, nb);
+            ap[na * ros] = make_double4(xp, yp, x, y);
+            ++na;
+        } else ok = false;                       // more arcs than the fast path stores
+    };
+    // new ring entry at (x, y); nb = neighbour across the edge leaving it (ARC: an arc starts here, at the end of the
+    // contact edge with neighbour `edge`)
+    auto emit = [&](double x, double y, int nb, int edge) {
+        if (E >= RS) { ok = false; return; }
+        if (E > 0) close_prev(x, y, nb); else { x0 = x; y0 = y; nbr0 = nb; }
+        rh[E * ros] = make_double2(x, y);
+        rn[E * ros] = nb;
+        if (nb == ARC) arc_from = edge;
+        xp = x; yp = y; nbr_p = nb; ++E;
+    };
+    {
+        const int mw = (work && ok) ? m : 0;
+        const int mloop = __reduce_max_sync(FULL_MASK, mw);
+        // the edge of the nearest neighbour (always a Voronoi neighbour)
+        const int smin = (mw && imin >= 0) ? si[imin * T] : -1;
+        int k = 0;
+#pragma unroll
+        for (int q = 0; q < KP; ++q) {
+            if (q >= mloop) break;
+            if (q < mw && sl[q * T] == smin) k = q;
+        }
+        double2 V1 = make_double2(0.0, 0.0);
+        if (mw) V1 = sv[((k + 1 == mw) ? 0 : k + 1) * T];
+        for (int st = 0; st < mloop; ++st) {
+            if (st < mw) {
+                const double2 V2 = sv[k * T];
+                const int j = sl[k * T];
+                if (j >= 0 && ok) {                        // a real neighbour (the sides of the square emit nothing)
+                    double pcx, pcy;
+                    disp_of(j, pcx, pcy);
+                    const bool in1 = V1.x * V1.x + V1.y * V1.y <= r2;
+                    // first entry of the edge: its inner start vertex (d1 <= r) or the point where it enters the disk (never
+                    // both); second: the point where it leaves the disk.  An edge between two inner vertices has neither.
+                    bool has1 = in1, has2 = false;
+                    double x1 = V1.x, y1 = V1.y, x2 = 0.0, y2 = 0.0;
+                    const double d2c = 0.25 * (pcx * pcx + pcy * pcy);               // |C|^2, C = p/2
+                    if (d2c < r2 && !(in1 && V2.x * V2.x + V2.y * V2.y <= r2)) {      // the bisector crosses the circle
+                        const double inv = 0.5 * rsqrt(d2c);
+                        const double ux = pcy * inv, uy = -pcx * inv;                  // clockwise unit vector along the edge
+                        const double t1 = V1.x * ux + V1.y * uy, t2 = V2.x * ux + V2.y * uy;
+                        const double tr = sqrt(r2 - d2c);
+                        if (-tr < t2 && -tr > t1) { has1 = true; x1 = 0.5 * pcx - tr * ux; y1 = 0.5 * pcy - tr * uy; }    // entry point
+                        if (tr < t2 && tr > t1) { has2 = true; x2 = 0.5 * pcx + tr * ux; y2 = 0.5 * pcy + tr * uy; }      // exit point
+                    }
+                    if (has1) emit(x1, y1, j, j);
+                    if (has2) emit(x2, y2, ARC, j);
+                }
+                V1 = V2;
+                k = (k == 0) ? mw - 1 : k - 1;
+            }
+        }
+    }
+    if (live && ok && E >= 2) close_prev(x0, y0, nbr0);   // closing edge: last entry -> first entry
+    const bool ringed = live && ok && E >= 2;
+    if (live && !ok) {   // too many neighbours / polygon edges / ring entries / arcs for the fast path: queue for the large-capacity kernel
+        const int idx = atomicAdd(&a.flags[0], 1);
+        if (idx < OVF_MAX) {
+            a.ovf_cells[idx] = s;
+            // only the ring outgrew the fast path: hand the polygon over, the slow path need not clip again
+            const int mm = poly_ok ? m : 0;
+            a.ovf_m[idx] = mm;
+            for (int k = 0; k < mm; ++k) { const int lab = sl[k * T]; a.ovf_hull[(size_t)idx * KPOLY_SLOW + k] = lab >= 0 ? lab : -2; }
+        } else atomicAdd(&a.flags[3], 1);
+        a.ring_len[s] = 0; a.n_arc[s] = 0;
+    }
+
+    // ---- arcs: the lanes of a warp evaluate their q-th arc together (cell_geom.pyx:454-469) ----
+    double Larc = 0.0;
+    {
+        const int nq = ringed ? na : 0;
+        const int aloop = __reduce_max_sync(FULL_MASK, nq);
+        for (int q = 0; q < aloop; ++q) {
+            if (q < nq) {
+                const double4 c = ap[q * ros];            // (v1, v2) = (start, end)
+                double ang = atan2(c.z * c.y - c.w * c.x, c.x * c.z + c.y * c.w);   // angle(v1) - angle(v2)
+                if (ang < 0.0) ang += TWO_PI;
+                Larc += r * ang;
+                A += 0.5 * r2 * ang;
+            }
+        }
+    }
+    P += Larc;
+    if (live && ok) {
+        int zz = z;
+        if (!ringed) {                           // isolated cell (cell_geom.pyx:402-406)
+            A = PI * r2; P = TWO_PI * r; Larc = TWO_PI * r; zz = 0;
+            a.ring_len[s] = 0; a.n_arc[s] = 0;
+        } else {
+            a.ring_len[s] = (unsigned char)E;
+            a.n_arc[s] = (unsigned char)na;
+            if (E > 12) atomicMax(&a.flags[2], E);
+        }
+        a.area[s] = A; a.perim[s] = P; a.arcl[s] = Larc; a.coord[s] = zz;
+        CellRec q;
+        q.x = xi; q.y = yi;
+        q.cA = 2.0 * a.ph.KA * (A - a.a0[s]);
+        q.cP = 2.0 * a.ph.KP * (P - a.ph.P0);
+        a.rec[s] = q;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K2b: ring, measures and per-vertex gradients from the polygon found by k_hull.  One thread per cell, no shared
-// memory, no per-thread arrays.
+// ring and measures of a queued cell from its polygon (hull[k * hstride], k < m_pool: neighbour slots counter-clockwise,
+// < 0 for edges at infinity), streamed into slot `pool_idx` of the overflow pool; at most RS_SLOW entries, returns false
+// when even that is too short.  Vertices are rebuilt as the intersections of consecutive bisectors.
 // ------------------------------------------------------------------------------------------------------
-#ifndef RING_MIN_BLOCKS
-#define RING_MIN_BLOCKS 6
-#endif
-// POOL = false: the fast path, every lane of the warp calls it (warp-uniform loop bounds), records slot-major, at most
-// RS entries; a longer ring queues the cell.  POOL = true: one queued cell per thread (k_geometry_slow), records into
-// slot `pool_idx` of the overflow pool, at most RING_POOL_FAST entries; returns false when even that is too short.
-constexpr int RING_POOL_FAST = 32;               // bounded by the 32-bit arc mask
 template <bool POOL, bool SLAB>
-__device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const bool live_in, const int pool_idx) {
+__device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const bool live_in, const int pool_idx,
+                                          const int *hull, const size_t hstride, const int m_pool) {
     bool live = live_in;
     const double r = a.ph.r, B4 = 4.0 * r;
     GridDesc g = *a.grid;
@@ -455,7 +433,8 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
     bool wrapx = false, wrapy = false;
     int m = 0;
     bool ok = true;
-    const int *hs = a.hull_slot + (live ? s : 0);      // slot-major: edge k at hs[k * a.stride]
+    const int *hs = hull;                                            // edge k at hs[k * hst]
+    const size_t hst = hstride;
     if (live) {
         int bx, by;
         bin_xy(g, a.keys[s], bx, by);
@@ -465,14 +444,13 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
             xi = pi_.x; yi = pi_.y;
             wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);
             wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
-            m = a.hull_len[s];
+            m = m_pool;
         }
     }
-    const bool queued = (m == HULL_QUEUED);
-    if (queued) m = 0;
+    const bool queued = false;
     // displacement of polygon edge k's neighbour
     auto disp = [&](int k, double &dx, double &dy, int &slot) {
-        slot = hs[k * a.stride];
+        slot = hs[k * hst];
         if (slot >= 0) {
             const double2 pc = a.xy[slot];
             dx = pc.x - xi; dy = pc.y - yi;
@@ -481,20 +459,16 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
         } else { dx = 0.0; dy = 0.0; }
     };
 
-    // ---- ring, streamed.  The polygon edges are the hull vertices h_0..h_{m-1} (counter-clockwise); the ring is
-    //      clockwise, so edge k is walked from vertex k+1 to vertex k for k = m-1 .. 0 (finite_voronoi.py:363-459).
-    //      Ring records are written as they are produced; their gx/gy slots double as scratch (1/length of a
-    //      straight edge, or the (cross, dot) of an arc's end points) until the last pass overwrites them, so the
-    //      kernel keeps no per-thread arrays at all. ----
+    // ---- ring, streamed.  The polygon edges are e_0..e_{m-1} (counter-clockwise); the ring is clockwise, so edge k
+    //      is walked from vertex k+1 to vertex k for k = m-1 .. 0 (finite_voronoi.py:363-459). ----
     const double r2 = r * r;
     const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
-    // slot-major: entry e at ro[e * ros]; inside the pool the records of a cell are contiguous (RingShared and RingSelf
-    // have the same layout)
-    RingOwn *const ro = POOL ? a.ovf_ro + (size_t)pool_idx * RS_SLOW : a.ro + s;
-    RingSelf *const self = POOL ? reinterpret_cast<RingSelf *>(a.ovf_rs + (size_t)pool_idx * RS_SLOW) : a.self + s;
+    double2 *const rh = POOL ? a.ovf_ring_h + (size_t)pool_idx * RS_SLOW : a.ring_h + s;
+    int *const rn = POOL ? a.ovf_ring_nbr + (size_t)pool_idx * RS_SLOW : a.ring_nbr + s;
+    int2 *const ak = POOL ? a.ovf_arc_key + (size_t)pool_idx * ARC_SLOW : a.arc_key + s;
+    double4 *const ap = POOL ? a.ovf_arc_pts + (size_t)pool_idx * ARC_SLOW : a.arc_pts + s;
     const size_t ros = POOL ? 1 : a.stride;
-    int *const key = a.ring_key + (size_t)s * RS;   // the compact key row k_force scans (fast path only)
-    constexpr int ECAP = POOL ? RING_POOL_FAST : RS;
+    constexpr int ECAP = POOL ? RS_SLOW : RS, ACAP = POOL ? ARC_SLOW : ARC_MAX;
     const int mm = m;
     const int mloop = POOL ? mm : __reduce_max_sync(FULL_MASK, mm);
     // Junction between the counter-clockwise consecutive polygon edges A (slot ja, displacement a) and B (jb, b):
@@ -514,101 +488,116 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
             if (jb >= 0) { const double f = B4 * rsqrt(bx_ * bx_ + by_ * by_); sbx = 0.5 * bx_ + f * by_; sby = 0.5 * by_ - f * bx_; } // C_B - 4r ccw(B)
         }
     };
-    int E = 0, z = 0;
-    unsigned arcmask = 0u;                       // bit e set: ring entry e starts an arc
+    int E = 0, z = 0, na = 0;
     double A = 0.0, P = 0.0;
     double x0 = 0.0, y0 = 0.0;                   // first ring entry
-    double xp = 0.0, yp = 0.0;                   // previous ring entry (its record is written when the next one arrives)
-    int nbr_p = ARC;
-    // connect the previous entry to (x, y): measure the edge, then write the previous entry's shared record
-    auto close_prev = [&](double x, double y) {
-        RingSelf o; o.nbr = nbr_p; o.type = (nbr_p != ARC) ? 1 : 0; o.w = 0.0;
+    int nbr0 = ARC;
+    double xp = 0.0, yp = 0.0;                   // previous ring entry
+    int nbr_p = ARC, arc_from = ARC;             // its leaving edge; the contact edge that ended where the pending arc starts
+    // connect the previous entry to (x, y), the start of the edge with neighbour nb
+    auto close_prev = [&](double x, double y, int nb) {
         if (nbr_p != ARC) {
             const double sx = xp - x, sy = yp - y;
             const double l2 = sx * sx + sy * sy;
-            const double il = l2 > 0.0 ? rsqrt(l2) : 0.0;
-            P += l2 * il;
+            P += l2 > 0.0 ? l2 * rsqrt(l2) : 0.0;
             A += -0.5 * (xp * y - yp * x);
-            o.gx = il; o.gy = 0.0;
             ++z;
-        } else {
-            o.gx = x * yp - y * xp;              // v2 x v1
-            o.gy = xp * x + yp * y;              // v1 . v2
-        }
-        self[(E - 1) * ros] = o;
-        if (!POOL) key[E - 1] = nbr_p;
+        } else if (na < ACAP) {                  // the arc that started at (xp, yp) ends here
+            ak[na * ros] = make_int2(arc_from, nb);
+            ap[na * ros] = make_double4(xp, yp, x, y);
+            ++na;
+        } else ok = false;                       // more arcs than the fast path stores: the cell goes to the pool
     };
-    auto emit = [&](double x, double y, double ex, double ey, int nb) {
+    // new ring entry at (x, y); nb = neighbour across the edge leaving it (ARC: an arc starts here, at the end of the
+    // contact edge with neighbour `edge`)
+    auto emit = [&](double x, double y, int nb, int edge) {
         if (E >= ECAP) { ok = false; return; }
-        if (E > 0) close_prev(x, y); else { x0 = x; y0 = y; }
-        RingOwn q; q.hx = x; q.hy = y; q.px = ex; q.py = ey;
-        ro[E * ros] = q;
-        if (nb == ARC) arcmask |= 1u << E;
+        if (E > 0) close_prev(x, y, nb); else { x0 = x; y0 = y; nbr0 = nb; }
+        rh[E * ros] = make_double2(x, y);
+        rn[E * ros] = nb;
+        if (nb == ARC) arc_from = edge;
         xp = x; yp = y; nbr_p = nb; ++E;
     };
-    for (int k = 0; k < mm; ++k) {               // pull the neighbours' positions towards L1 before the dependent walk
-        const int sl = hs[k * a.stride];
-        if (sl >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.xy + sl));
-    }
     {
+        // the walk visits the edges m-1, then m-2, ..., 0 and needs the PREVIOUS polygon edge of each: slot indices are
+        // requested two iterations ahead, positions one iteration ahead, so neither load sits on the critical path
+        auto load_slot = [&](int k) { return hs[k * hst]; };
+        auto load_pos = [&](int slot) { return slot >= 0 ? a.xy[slot] : make_double2(0.0, 0.0); };
+        auto rel = [&](int slot, double2 pc, double &dx, double &dy) {
+            if (slot >= 0) {
+                dx = pc.x - xi; dy = pc.y - yi;
+                if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
+                if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
+            } else { dx = 0.0; dy = 0.0; }
+        };
         double pcx = 0.0, pcy = 0.0, pnx = 0.0, pny = 0.0, V1x = 0.0, V1y = 0.0;
         int jc = -2, jn = -2;
+        int slA = -2, slB = -2;                   // previous edge of iteration kk / kk + 1
+        double2 poA = make_double2(0.0, 0.0);
         if (mm > 0) {
             double tx, ty;
             disp(mm - 1, pcx, pcy, jc);
             disp(0, pnx, pny, jn);
+            slA = load_slot(mm > 1 ? mm - 2 : 0);
+            slB = load_slot(mm > 2 ? mm - 3 : mm - 1);
+            poA = load_pos(slA);
             junction(jc, pcx, pcy, jn, pnx, pny, V1x, V1y, tx, ty);   // end of edge m-1 (junction with edge 0)
         }
         for (int kk = 0; kk < mloop; ++kk) {
             if (kk < mm) {
-                const int k = mm - 1 - kk;
                 double ppx, ppy, V2x, V2y, Enx, Eny;
-                int jp;
-                disp(k == 0 ? mm - 1 : k - 1, ppx, ppy, jp);
+                const int jp = slA;
+                rel(slA, poA, ppx, ppy);
+                {   // edge index of the previous edge two iterations on: k - 1 with k = mm - 1 - (kk + 2)
+                    int kn = mm - 4 - kk; if (kn < 0) kn += mm; if (kn < 0) kn += mm; if (kn < 0) kn += mm;
+                    const int slC = (kk + 2 < mm) ? load_slot(kn) : -2;
+                    poA = load_pos(slB);
+                    slA = slB; slB = slC;
+                }
                 junction(jp, ppx, ppy, jc, pcx, pcy, Enx, Eny, V2x, V2y);   // end of edge k-1, start of edge k
                 if (jc >= 0 && ok) {                       // a real neighbour (virtual edges emit nothing)
                     const int j = jc;
-                    if (V1x * V1x + V1y * V1y <= r2) emit(V1x, V1y, pcx, pcy, j);      // inner start vertex, d1 <= r
+                    const bool in1 = V1x * V1x + V1y * V1y <= r2;
+                    // first entry of the edge: its inner start vertex (d1 <= r) or the point where it enters the disk (never
+                    // both); second: the point where it leaves the disk.  An edge between two inner vertices has neither.
+                    bool has1 = in1, has2 = false;
+                    double x1 = V1x, y1 = V1y, x2 = 0.0, y2 = 0.0;
                     const double d2c = 0.25 * (pcx * pcx + pcy * pcy);               // |C|^2, C = p/2
-                    if (d2c < r2) {                        // the bisector crosses the disk
+                    if (d2c < r2 && !(in1 && V2x * V2x + V2y * V2y <= r2)) {          // the bisector crosses the circle
                         const double inv = 0.5 * rsqrt(d2c);
                         const double ux = pcy * inv, uy = -pcx * inv;                  // clockwise unit vector along the edge
                         const double t1 = V1x * ux + V1y * uy, t2 = V2x * ux + V2y * uy;
                         const double tr = sqrt(r2 - d2c);
-                        if (-tr < t2 && -tr > t1) emit(0.5 * pcx - tr * ux, 0.5 * pcy - tr * uy, pcx, pcy, j);   // entry point
-                        if (tr < t2 && tr > t1) emit(0.5 * pcx + tr * ux, 0.5 * pcy + tr * uy, pcx, pcy, ARC);  // exit point
+                        if (-tr < t2 && -tr > t1) { has1 = true; x1 = 0.5 * pcx - tr * ux; y1 = 0.5 * pcy - tr * uy; }    // entry point
+                        if (tr < t2 && tr > t1) { has2 = true; x2 = 0.5 * pcx + tr * ux; y2 = 0.5 * pcy + tr * uy; }      // exit point
                     }
+                    if (has1) emit(x1, y1, j, j);
+                    if (has2) emit(x2, y2, ARC, j);
                 }
                 pcx = ppx; pcy = ppy; jc = jp; V1x = Enx; V1y = Eny;
             }
         }
     }
+    if (live && ok && !queued && E >= 2) close_prev(x0, y0, nbr0);   // closing edge: last entry -> first entry
     const bool ringed = live && ok && !queued && E >= 2;
-    if (ringed) close_prev(x0, y0);              // closing edge: last entry -> first entry
 
-    if (POOL && !ok) return false;               // the caller falls back to the clipping path
+    if (POOL && !ok) return false;               // even the pool is too short: the caller reports it
     if (!POOL && live && !ok) {                  // ring longer than the stride: queue the cell for the large-capacity kernel
         const int idx = atomicAdd(&a.flags[0], 1);
         if (idx < OVF_MAX) a.ovf_cells[idx] = s; else atomicAdd(&a.flags[3], 1);
-        a.ring_len[s] = 0;
+        a.ring_len[s] = 0; a.n_arc[s] = 0;
     }
-    if (live && queued) a.ring_len[s] = 0;       // k_geometry_slow fills everything in
-    if (live && ok && !queued && E < 2) {                   // isolated cell (cell_geom.pyx:402-406)
-        a.area[s] = PI * r2; a.perim[s] = TWO_PI * r; a.arcl[s] = TWO_PI * r; a.coord[s] = 0;
-        a.ring_len[s] = 0;
-    }
+    if (live && queued) { a.ring_len[s] = 0; a.n_arc[s] = 0; }   // k_geometry_slow fills everything in
 
     // ---- arcs: the lanes of a warp evaluate their q-th arc together (cell_geom.pyx:454-469) ----
     double Larc = 0.0;
     {
-        unsigned rem = ringed ? arcmask : 0u;
-        const int aloop = POOL ? __popc(rem) : __reduce_max_sync(FULL_MASK, __popc(rem));
+        const int nq = ringed ? na : 0;
+        const int aloop = POOL ? nq : __reduce_max_sync(FULL_MASK, nq);
         for (int q = 0; q < aloop; ++q) {
-            if (rem) {
-                const int e = __ffs(rem) - 1;
-                rem &= rem - 1;
-                const RingSelf sc = self[e * ros];
-                double ang = atan2(sc.gx, sc.gy);         // angle(v1) - angle(v2)
+            if (q < nq) {
+                const double4 c = ap[q * ros];            // (v1, v2) = (start, end)
+                double ang = atan2(c.z * c.y - c.w * c.x, c.x * c.z + c.y * c.w);   // angle(v1) - angle(v2)
                 if (ang < 0.0) ang += TWO_PI;
                 Larc += r * ang;
                 A += 0.5 * r2 * ang;
@@ -616,69 +605,34 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
         }
     }
     P += Larc;
-    double cA = 0.0, cP = 0.0, cL = 0.0;
-    if (ringed) {
-        a.area[s] = A; a.perim[s] = P; a.arcl[s] = Larc; a.coord[s] = z;
-        if (POOL) { a.ring_len[s] = RING_IN_POOL; a.ovf_index[s] = pool_idx; a.ovf_len[pool_idx] = E; }
-        else a.ring_len[s] = (unsigned char)E;
-        if (E > 12) atomicMax(&a.flags[2], E);
-        cA = 2.0 * a.ph.KA * (A - a.a0[s]);
-        cP = 2.0 * a.ph.KP * (P - a.ph.P0);
-        cL = cP + a.ph.Lambda;
-    }
-
-    // ---- per-vertex gradients of this cell (cell_geom.pyx:478-539), streamed over the ring records ----
-    {
-        const int EE = ringed ? E : 0;
-        const int Eloop = POOL ? EE : __reduce_max_sync(FULL_MASK, EE);
-        // software pipeline: the record of entry e+2 (vertex position, 1/length scratch) is requested while vertex e is
-        // being processed; entry e's scratch is only overwritten after its last use
-        double hpx = 0.0, hpy = 0.0, hcx = 0.0, hcy = 0.0, hnx = 0.0, hny = 0.0, ilp = 0.0, ilc = 0.0, iln = 0.0;
-        auto load_h = [&](int e, double &x, double &y) { const double2 v = *reinterpret_cast<const double2 *>(&ro[e * ros]); x = v.x; y = v.y; };
-        auto load_il = [&](int e) { return ((arcmask >> e) & 1u) ? 0.0 : self[e * ros].gx; };
-        if (EE > 0) {
-            const int e1 = (1 == EE) ? 0 : 1;
-            load_h(EE - 1, hpx, hpy); load_h(0, hcx, hcy); load_h(e1, hnx, hny);
-            ilp = load_il(EE - 1); ilc = load_il(0); iln = load_il(e1);
+    if (live && ok && !queued) {
+        int zz = z;
+        if (!ringed) {                           // isolated cell (cell_geom.pyx:402-406)
+            A = PI * r2; P = TWO_PI * r; Larc = TWO_PI * r; zz = 0;
+            a.ring_len[s] = 0; a.n_arc[s] = 0;
+        } else {
+            if (POOL) { a.ring_len[s] = RING_IN_POOL; a.ovf_index[s] = pool_idx; a.ovf_len[pool_idx] = E; }
+            else a.ring_len[s] = (unsigned char)E;
+            a.n_arc[s] = (unsigned char)na;
+            if (E > 12) atomicMax(&a.flags[2], E);
         }
-        for (int e = 0; e < Eloop; ++e) {
-            if (e < EE) {
-                const int e0 = (e == 0) ? EE - 1 : e - 1;
-                int e3 = e + 2; if (e3 >= EE) e3 -= EE; if (e3 >= EE) e3 -= EE;
-                double hqx, hqy;
-                load_h(e3, hqx, hqy);
-                const double ilq = load_il(e3);
-                const bool arc_c = (arcmask >> e) & 1u, arc_p = (arcmask >> e0) & 1u;
-                // u(e) = (v1 - v2)/|v1 - v2| for straight edges, 0 for arcs;  dP/dv1 = u(e) - u(e-1);  dA/dv1 = 0.5 (perp(v0) - perp(v2))
-                const double uex = (hcx - hnx) * ilc, uey = (hcy - hny) * ilc;
-                const double upx = (hpx - hcx) * ilp, upy = (hpy - hcy) * ilp;
-                const double gx = cA * 0.5 * (hpy - hny) + cP * (uex - upx);
-                const double gy = cA * 0.5 * (hnx - hpx) + cP * (uey - upy);
-                double w = 0.0;
-                if (arc_c)       // an arc starts here: da = +0.5 r^2 (1 - cos D), dl = +r
-                    w = cA * 0.5 * (r2 - (hcx * hnx + hcy * hny)) + cL * r;
-                else if (arc_p)  // an arc ends here
-                    w = -(cA * 0.5 * (r2 - (hpx * hcx + hpy * hcy)) + cL * r);
-                // final record (nbr / type were written when the entry was closed)
-                double *dst = reinterpret_cast<double *>(&self[e * ros]);
-                dst[0] = gx; dst[1] = gy; dst[2] = w;
-                hpx = hcx; hpy = hcy; hcx = hnx; hcy = hny; hnx = hqx; hny = hqy; ilp = ilc; ilc = iln; iln = ilq;
-            }
-        }
+        a.area[s] = A; a.perim[s] = P; a.arcl[s] = Larc; a.coord[s] = zz;
+        CellRec q;
+        q.x = xi; q.y = yi;
+        q.cA = 2.0 * a.ph.KA * (A - a.a0[s]);
+        q.cP = 2.0 * a.ph.KP * (P - a.ph.P0);
+        a.rec[s] = q;
     }
     return true;
 }
 
-template <bool SLAB>
-__global__ void __launch_bounds__(HULL_TPB, RING_MIN_BLOCKS) k_ring(GeomArgs a) {
-    const int t = blockIdx.x * HULL_TPB + threadIdx.x;
-    ring_cell<false, SLAB>(a, SLAB ? slot_of_thread(a, t) : t, t < a.n, 0);
-}
-
 // ------------------------------------------------------------------------------------------------------
-// slow path: the (few) queued cells, one thread each, in-place clipping with large local arrays
+// slow path: the (few) queued cells, one thread each
 // ------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void geom_cell_slow(const GeomArgs &a, const int s, const int pool_idx) {
+// polygon of cell s by in-place clipping of a bounding square with large local arrays -> ovf_hull of pool slot
+// `pool_idx` (neighbour slots counter-clockwise, -2 for the sides of the square); returns the edge count, -1 when the
+// polygon outgrows KPOLY_SLOW
+__device__ __noinline__ int clip_cell_slow(const GeomArgs &a, const int s, const int pool_idx) {
     constexpr int K = KPOLY_SLOW;
     const double r = a.ph.r, cut2 = 4.0 * r * r;
     const double xi = a.xy[s].x, yi = a.xy[s].y;
@@ -720,15 +674,27 @@ __device__ __noinline__ void geom_cell_slow(const GeomArgs &a, const int s, cons
             }
         }
     }
-    finish_cell<K, RS_SLOW, true>(a, s, pool_idx, true, ok, vx, vy, px, py, lab, m);
+    if (!ok) return -1;
+    int *out = a.ovf_hull + (size_t)pool_idx * KPOLY_SLOW;
+    for (int k = 0; k < m; ++k) out[k] = lab[k];
+    return m;
 }
 
 __global__ void __launch_bounds__(64) k_geometry_slow(GeomArgs a) {
     const int cnt = min(a.flags[0], OVF_MAX);
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x) {
         const int s = a.ovf_cells[idx];
-        // queued by k_ring (its polygon is fine, only the ring outgrew the stride): emit the ring again, into the pool;
-        // queued by k_hull, or a ring beyond RING_POOL_FAST: clip from scratch
-        if (a.hull_len[s] == HULL_QUEUED || !ring_cell<true, true>(a, s, true, idx)) geom_cell_slow(a, s, idx);
+        const int m0 = a.ovf_m[idx];
+        const int m = m0 > 0 ? m0 : clip_cell_slow(a, s, idx);
+        const bool done = m >= 0 && ring_cell<true, true>(a, s, true, idx, a.ovf_hull + (size_t)idx * KPOLY_SLOW, 1, m);
+        if (!done) {   // exceeded even the slow-path capacity: the host reports AFV_ERR_CAPACITY; the cell counts as isolated
+            atomicAdd(&a.flags[3], 1);
+            const double r = a.ph.r, PI = 3.14159265358979323846;
+            const double A = PI * r * r, P = 2.0 * PI * r;
+            a.ring_len[s] = 0; a.n_arc[s] = 0;
+            a.area[s] = A; a.perim[s] = P; a.arcl[s] = P; a.coord[s] = 0;
+            CellRec q; q.x = a.xy[s].x; q.y = a.xy[s].y; q.cA = 2.0 * a.ph.KA * (A - a.a0[s]); q.cP = 2.0 * a.ph.KP * (P - a.ph.P0);
+            a.rec[s] = q;
+        }
     }
 }

@@ -114,19 +114,36 @@ __global__ void k_bin_start(const unsigned *__restrict__ keys_sorted, int n, con
 #include "afv_geometry.cuh"
 
 // ------------------------------------------------------------------------------------------------------
-// K3: force gather (+ fused active-Langevin update).  One thread per cell walks its own ring; for every
-// contact edge it finds the edge back to itself in the neighbour's ring (<= RS keys) and reads the
-// neighbour's two records at the ends of the shared edge.  No atomics; summation order is the ring order.
+// K3: force gather (+ fused active-Langevin update).  One thread per owned cell walks its own ring (slot-major,
+// coalesced) and gathers ONE 32-byte record (position, cA = 2KA(A-A0), cP = 2KP(P-P0)) per contact neighbour.
+//
+// The reference assembles F_i = -sum_h (dE/dh)(dh/dr_i) with dE/dh = sum over the (<= 3) cells c around vertex h of
+// cA_c dA_c/dh + cP_c dP_c/dh (cell_geom.pyx:478-518, finite_voronoi.py:537-634).  dA_c/dh, dP_c/dh involve c's two
+// ring neighbours of h, one of which cell i does not see (the far end b of the edge between the two OTHER cells).
+// For an inner vertex h = circumcentre(i, a, b) that end is not needed: dh/dr_i is parallel to the bisector of (a, b),
+// which carries h and b, so   cross(b, dh) = cross(h, dh)   and   d|h - b| = -(d^ . dh)   with d^ the unit vector
+// along that bisector pointing away from cell i.  Everything else -- the far ends of i's own two edges, the three
+// positions -- cell i holds.  Outer vertices (circle-circle intersections) keep the reference's regularised Jacobian
+// literally (finite_voronoi.py:653-746), so there the neighbour's arc end IS needed: it comes from the neighbour's
+// arc table (<= 1.1 look-ups per cell at rho l^2 = 1, none in a confluent tissue).
+// No atomics; the summation order is the ring order, which starts at the nearest neighbour: results do not depend on
+// the sort order.
 // ------------------------------------------------------------------------------------------------------
 struct ForceArgs {
-    const RingOwn *ro;             // slot-major
-    const RingSelf *self;          // slot-major; also what the neighbours gather
+    const double2 *ring_h;         // slot-major
+    const int *ring_nbr;
     size_t stride;
     const unsigned char *ring_len;
-    const int *ring_key;
+    const CellRec *rec;
+    const unsigned char *n_arc;
+    const int2 *arc_key;
+    const double4 *arc_pts;
     const int *ovf_index, *ovf_len;
-    const RingShared *ovf_rs;
-    const RingOwn *ovf_ro;
+    const double2 *ovf_ring_h;
+    const int *ovf_ring_nbr;
+    const int2 *ovf_arc_key;
+    const double4 *ovf_arc_pts;
+    const GridDesc *grid;
     const unsigned char *owned;
     const int64_t *gid;
     int n;
@@ -150,137 +167,188 @@ __device__ __forceinline__ unsigned xch_lists(double x, unsigned char own, doubl
     return (x < lo ? 1u : 0u) | ((x >= lo && x < lo + halo) ? 2u : 0u) | (x >= hi ? 4u : 0u) | ((x >= hi - halo && x < hi) ? 8u : 0u);
 }
 
-struct NbrRec { double gx, gy; const double *pw; };   // the arc weight is fetched only at outer vertices
-
-__device__ __forceinline__ bool lookup_edge(const ForceArgs &a, int j, int self, NbrRec &at_start, NbrRec &at_end) {
-    // edge (j -> self) in j's ring runs from slot t to slot t+1; seen from `self` the same edge runs the other
-    // way, so j's slot t is the END of self's edge and j's slot t+1 its START.
-    // The 16 keys of j's ring are one 64-byte row: independent 16-byte loads, then register compares; rings of
-    // <= 8 entries (the common case) need only the first half.
-    const int4 *kj = reinterpret_cast<const int4 *>(a.ring_key + (size_t)j * RS);
-    int Ej = a.ring_len[j];                       // independent of the key loads: all are in flight together
-    const int4 k0 = kj[0], k1 = kj[1];
-    int t = -1;
-    if (Ej != RING_IN_POOL) {
-        unsigned match = (k0.x == self ? 1u : 0u) | (k0.y == self ? 2u : 0u) | (k0.z == self ? 4u : 0u) | (k0.w == self ? 8u : 0u) |
-                         (k1.x == self ? 16u : 0u) | (k1.y == self ? 32u : 0u) | (k1.z == self ? 64u : 0u) | (k1.w == self ? 128u : 0u);
-        if (Ej > 8) {
-            const int4 k2 = kj[2], k3 = kj[3];
-            match |= (k2.x == self ? 1u : 0u) << 8 | (k2.y == self ? 1u : 0u) << 9 | (k2.z == self ? 1u : 0u) << 10 | (k2.w == self ? 1u : 0u) << 11 |
-                     (k3.x == self ? 1u : 0u) << 12 | (k3.y == self ? 1u : 0u) << 13 | (k3.z == self ? 1u : 0u) << 14 | (k3.w == self ? 1u : 0u) << 15;
-        }
-        match &= (1u << Ej) - 1u;                 // slots beyond the ring hold stale keys
-        t = __ffs(match) - 1;
-        if (t >= 0) {
-            const int t1 = (t + 1 == Ej) ? 0 : t + 1;
-            const RingSelf *re = a.self + (size_t)t * a.stride + j, *rb = a.self + (size_t)t1 * a.stride + j;
-            const double2 ge = *reinterpret_cast<const double2 *>(re), gs = *reinterpret_cast<const double2 *>(rb);
-            at_end.gx = ge.x; at_end.gy = ge.y; at_end.pw = &re->w;
-            at_start.gx = gs.x; at_start.gy = gs.y; at_start.pw = &rb->w;
-            return true;
-        }
-    } else {   // pooled ring: generic scan over its per-cell records
+// far end (relative to cell j) of j's arc that STARTS where j's contact edge with `self` ends (starts_there) or that
+// ENDS where j's contact edge with `self` starts (!starts_there)
+__device__ __forceinline__ bool arc_far_end(const ForceArgs &a, int j, int self, bool starts_there, double &qx, double &qy) {
+    int na = a.n_arc[j];
+    const int2 *ak = a.arc_key + j;
+    const double4 *ap = a.arc_pts + j;
+    size_t st = a.stride;
+    if (a.ring_len[j] == RING_IN_POOL) {
         const int pi = a.ovf_index[j];
-        Ej = a.ovf_len[pi];
-        const RingShared *rj = a.ovf_rs + (size_t)pi * RS_SLOW;
-        for (int q = 0; q < Ej; ++q) {
-            const int2 kt = *reinterpret_cast<const int2 *>(&rj[q].nbr);
-            if (kt.x == self && kt.y == 1) { t = q; break; }
-        }
-        if (t >= 0) {
-            const int t1 = (t + 1 == Ej) ? 0 : t + 1;
-            const double2 ge = *reinterpret_cast<const double2 *>(&rj[t]), gs = *reinterpret_cast<const double2 *>(&rj[t1]);
-            at_end.gx = ge.x; at_end.gy = ge.y; at_end.pw = &rj[t].w;
-            at_start.gx = gs.x; at_start.gy = gs.y; at_start.pw = &rj[t1].w;
+        ak = a.ovf_arc_key + (size_t)pi * ARC_SLOW; ap = a.ovf_arc_pts + (size_t)pi * ARC_SLOW; st = 1;
+    }
+    for (int q = 0; q < na; ++q) {
+        const int2 k = ak[q * st];
+        if ((starts_there ? k.x : k.y) == self) {
+            const double4 c = ap[q * st];
+            qx = starts_there ? c.z : c.x; qy = starts_there ? c.w : c.y;
             return true;
         }
     }
-    at_start.gx = at_start.gy = 0.0; at_start.pw = nullptr;
-    at_end.gx = at_end.gy = 0.0; at_end.pw = nullptr;
+    qx = qy = 0.0;
     return false;
 }
 
 #ifndef FORCE_MIN_BLOCKS
-#define FORCE_MIN_BLOCKS 1
+#define FORCE_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(128, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.n) return;
-    if (a.owned[s] != CELL_OWNED) { a.fx[s] = 0.0; a.fy[s] = 0.0; return; }
-    int E = a.ring_len[s];
+    const bool live = s < a.n && a.owned[s] == CELL_OWNED;
+    if (s < a.n && !live) { a.fx[s] = 0.0; a.fy[s] = 0.0; }
+    int E = live ? a.ring_len[s] : 0;
     const double r = a.ph.r, r2 = r * r;
     double dEx = 0.0, dEy = 0.0;
-    if (E >= 2) {
-        // own ring: slot-major private records (coalesced across the warp); pooled rings are per-cell arrays
-        const RingOwn *ro = a.ro + s;
-        const RingSelf *self = a.self + s;
-        const RingShared *prs = nullptr;
-        size_t ros = a.stride;
-        if (E == RING_IN_POOL) {
-            const int pi = a.ovf_index[s];
-            E = a.ovf_len[pi]; prs = a.ovf_rs + (size_t)pi * RS_SLOW; ro = a.ovf_ro + (size_t)pi * RS_SLOW; ros = 1;
-        }
-        auto own_rec = [&](int e) {
-            RingShared q;
-            if (prs) q = prs[e];
-            else { const RingSelf f = self[e * ros]; q.nbr = f.nbr; q.type = f.type; q.gx = f.gx; q.gy = f.gy; q.w = f.w; }
-            return q;
-        };
-        int misses = 0;
-        // contribution of the last edge's neighbour to vertex 0
-        RingShared prev = own_rec(E - 1);
-        RingOwn prev_o = ro[(E - 1) * ros];
-        NbrRec pend = {0.0, 0.0, nullptr}, tmp;
-        if (prev.type == 1) misses += !lookup_edge(a, prev.nbr, s, tmp, pend);
-        for (int e = 0; e < E; ++e) {
-            const RingShared cur = own_rec(e);
-            const RingOwn own = ro[e * ros];
-            NbrRec cs = {0.0, 0.0, nullptr}, ce = {0.0, 0.0, nullptr};
-            if (cur.type == 1) misses += !lookup_edge(a, cur.nbr, s, cs, ce);
-            const double Gx = cur.gx + pend.gx + cs.gx, Gy = cur.gy + pend.gy + cs.gy;
-            const double hx = own.hx, hy = own.hy;
-            if (prev.type == 1 && cur.type == 1) {
-                // inner vertex = circumcentre(0, pa, pb): dh = eps (h . dr_i) / (pa . eps), eps = perp(pb - pa)
-                const double pax = prev_o.px, pay = prev_o.py, pbx = own.px, pby = own.py;
-                const double epx = -(pby - pay), epy = pbx - pax;
-                const double coef = (Gx * epx + Gy * epy) / (pax * epx + pay * epy);
-                dEx += coef * hx; dEy += coef * hy;
-            } else if (prev.type != cur.type) {
-                // outer vertex on the bisector with j (finite_voronoi.py:653-746)
-                const bool entry = (cur.type == 1);
-                const double pjx = entry ? own.px : prev_o.px, pjy = entry ? own.py : prev_o.py;
-                const double *pwj = entry ? cs.pw : pend.pw;
-                const double Wj = pwj ? *pwj : 0.0, Wi = cur.w;
-                const double rho2 = pjx * pjx + pjy * pjy, rho = sqrt(rho2);
-                const double root = sqrt(fmax(4.0 * r2 - rho2, 0.0));
-                const double cr = pjx * hy - pjy * hx;
-                const double sg = (cr > 0.0) ? 1.0 : ((cr < 0.0) ? -1.0 : 0.0);
-                const double k1 = 2.0 * r2 / (fmax(root, a.ph.delta) * rho2 * rho);
-                const double k2 = root / (2.0 * rho);
-                // T_x = dx_terms, T_y = dy_terms of the reference with r_IJ = -p_j
-                const double Txx = -k1 * pjx * pjy,       Txy = k1 * pjx * pjx - k2;
-                const double Tyx = -k1 * pjy * pjy + k2,  Tyy = k1 * pjx * pjy;
-                // dh/dx_i = (1/2 + s Txx, s Txy), dh/dy_i = (s Tyx, 1/2 + s Tyy); dh/dr_j = e - dh/dr_i
-                const double hxi_x = 0.5 + sg * Txx, hxi_y = sg * Txy, hyi_x = sg * Tyx, hyi_y = 0.5 + sg * Tyy;
-                const double hxj_x = 0.5 - sg * Txx, hxj_y = -sg * Txy, hyj_x = -sg * Tyx, hyj_y = 0.5 - sg * Tyy;
-                dEx += Gx * hxi_x + Gy * hxi_y;
-                dEy += Gx * hyi_x + Gy * hyi_y;
-                // arc angles: theta_i of h about i, theta_j of h about j
-                const double ujx = hx - pjx, ujy = hy - pjy;
-                const double iui = 1.0 / (hx * hx + hy * hy), iuj = 1.0 / (ujx * ujx + ujy * ujy);
-                const double upix = -hy * iui, upiy = hx * iui, upjx = -ujy * iuj, upjy = ujx * iuj;
-                const double dti_x = -(hxj_x * upix + hxj_y * upiy), dti_y = -(hyj_x * upix + hyj_y * upiy);
-                const double dtj_x = hxi_x * upjx + hxi_y * upjy, dtj_y = hyi_x * upjx + hyi_y * upjy;
-                dEx += Wi * dti_x + Wj * dtj_x;
-                dEy += Wi * dti_y + Wj * dtj_y;
-            }
-            pend = ce; prev = cur; prev_o = own;
-        }
-        if (misses) atomicAdd(&a.flags[1], misses);
+    const double2 *rh = a.ring_h + (live ? s : 0);
+    const int *rn = a.ring_nbr + (live ? s : 0);
+    size_t ros = a.stride;
+    bool pooled = false;
+    if (E == RING_IN_POOL) {
+        const int pi = a.ovf_index[s];
+        E = a.ovf_len[pi]; rh = a.ovf_ring_h + (size_t)pi * RS_SLOW; rn = a.ovf_ring_nbr + (size_t)pi * RS_SLOW; ros = 1; pooled = true;
     }
+    if (E < 2) E = 0;
+    const GridDesc g = *a.grid;
+    CellRec me = {0.0, 0.0, 0.0, 0.0};
+    if (live) me = a.rec[s];
+    const double cAi = me.cA, cPi = me.cP, cLi = me.cP + a.ph.Lambda;
+    // contact neighbour across an edge: displacement (minimum image; a no-op for |d| <= L/2, so the bits are those
+    // k_hull / k_measure worked with) and energy prefactors
+    struct Nb { double px, py, cA, cP; };
+    auto fetch = [&](int j) {
+        const double4 v = *reinterpret_cast<const double4 *>(a.rec + j);
+        Nb o;
+        o.px = v.x - me.x; o.py = v.y - me.y;
+        if (g.perx) o.px = min_image(o.px, g.Lx, g.halfLx);
+        if (g.pery) o.py = min_image(o.py, g.Ly, g.halfLy);
+        o.cA = v.z; o.cP = v.w;
+        return o;
+    };
+    auto inv_len = [](double ax, double ay, double bx, double by) {
+        const double sx = ax - bx, sy = ay - by, l2 = sx * sx + sy * sy;
+        return l2 > 0.0 ? rsqrt(l2) : 0.0;
+    };
+    int misses = 0;
+    // outer vertex at ring entry e, between entries (hp, np_) and (hn, .): the contact edge with j = bj starts (entry) or
+    // ends (!entry) here; il = 1 / its length  (finite_voronoi.py:653-746)
+    auto outer_vertex = [&](bool entry, int j, const Nb &bj, double il, double2 hp, double2 hc, double2 hn) {
+        const double hx = hc.x, hy = hc.y;
+        const double fxe = entry ? hn.x : hp.x, fye = entry ? hn.y : hp.y;     // far end of the contact edge
+        const double oxe = entry ? hp.x : hn.x, oye = entry ? hp.y : hn.y;     // other end of i's arc
+        const double pjx = bj.px, pjy = bj.py;
+        double qx, qy;                            // other end of j's arc at h, relative to j
+        misses += !arc_far_end(a, j, s, entry, qx, qy);
+        const double ujx = hx - pjx, ujy = hy - pjy;                           // h relative to j
+        const double Qx = qx + pjx, Qy = qy + pjy;                             // ... relative to i
+        // unit vector from the far end of the contact edge towards h: dP/dh of both cells along the edge
+        const double tx = (hx - fxe) * il, ty = (hy - fye) * il;
+        // polygon parts (cell_geom.pyx:478-518): dA/dv1 = 0.5 (y0 - y2, x2 - x0) with (v0, v2) the ring neighbours of
+        // h -- for i: (hp, hn); for j: (far end, Q) when the edge arrives at h in j's ring (entry), (Q, far end) else
+        const double sgn = entry ? 1.0 : -1.0;
+        const double Gx = cAi * 0.5 * (hp.y - hn.y) + bj.cA * 0.5 * sgn * (fye - Qy) + (cPi + bj.cP) * tx;
+        const double Gy = cAi * 0.5 * (hn.x - hp.x) + bj.cA * 0.5 * sgn * (Qx - fxe) + (cPi + bj.cP) * ty;
+        // arc-end weights (cell_geom.pyx:521-539): +-(cA/2 (r^2 - v1 . v2) + (cP + Lambda) r), + where the arc starts
+        const double wi = cAi * 0.5 * (r2 - (hx * oxe + hy * oye)) + cLi * r;
+        const double wj = bj.cA * 0.5 * (r2 - (ujx * qx + ujy * qy)) + (bj.cP + a.ph.Lambda) * r;
+        const double Wi = entry ? -wi : wi, Wj = entry ? wj : -wj;
+        const double rho2 = pjx * pjx + pjy * pjy, irho = rsqrt(rho2);
+        const double root = sqrt(fmax(4.0 * r2 - rho2, 0.0));
+        const double cr = pjx * hy - pjy * hx;
+        const double sg = (cr > 0.0) ? 1.0 : ((cr < 0.0) ? -1.0 : 0.0);
+        const double k1 = 2.0 * r2 * irho * irho * irho / fmax(root, a.ph.delta);
+        const double k2 = 0.5 * root * irho;
+        // T_x = dx_terms, T_y = dy_terms of the reference with r_IJ = -p_j
+        const double Txx = -k1 * pjx * pjy,       Txy = k1 * pjx * pjx - k2;
+        const double Tyx = -k1 * pjy * pjy + k2,  Tyy = k1 * pjx * pjy;
+        // dh/dx_i = (1/2 + s Txx, s Txy), dh/dy_i = (s Tyx, 1/2 + s Tyy); dh/dr_j = e - dh/dr_i
+        const double hxi_x = 0.5 + sg * Txx, hxi_y = sg * Txy, hyi_x = sg * Tyx, hyi_y = 0.5 + sg * Tyy;
+        const double hxj_x = 0.5 - sg * Txx, hxj_y = -sg * Txy, hyj_x = -sg * Tyx, hyj_y = 0.5 - sg * Tyy;
+        dEx += Gx * hxi_x + Gy * hxi_y;
+        dEy += Gx * hyi_x + Gy * hyi_y;
+        // arc angles: theta_i of h about i, theta_j of h about j
+        const double iui = 1.0 / (hx * hx + hy * hy), iuj = 1.0 / (ujx * ujx + ujy * ujy);
+        const double upix = -hy * iui, upiy = hx * iui, upjx = -ujy * iuj, upjy = ujx * iuj;
+        const double dti_x = -(hxj_x * upix + hxj_y * upiy), dti_y = -(hyj_x * upix + hyj_y * upiy);
+        const double dtj_x = hxi_x * upjx + hxi_y * upjy, dtj_y = hyi_x * upjx + hyi_y * upjy;
+        dEx += Wi * dti_x + Wj * dtj_x;
+        dEy += Wi * dti_y + Wj * dtj_y;
+    };
+    // ---- pass 1, all lanes of the warp in step over their rings: inner vertices; outer vertices (rarer, and a long
+    //      code path) are only noted down -- 4 bits each -- and done together afterwards ----
+    unsigned long long outer = 0ull;
+    int n_outer = 0;
+    {
+        // rolling window over entries e-1, e, e+1 (vertex, neighbour across the leaving edge and its record); what
+        // entry e+2 needs is requested one iteration ahead, so no load sits on the critical path of the loop
+        double2 hp = make_double2(0.0, 0.0), hc = hp, hn = hp;
+        int np_ = ARC, nc = ARC, nn = ARC;
+        Nb bp = {0.0, 0.0, 0.0, 0.0}, bc = bp;
+        double ilp = 0.0;
+        if (E) {
+            const int e1 = (1 == E) ? 0 : 1;
+            hp = rh[(size_t)(E - 1) * ros]; hc = rh[0]; hn = rh[(size_t)e1 * ros];
+            np_ = rn[(size_t)(E - 1) * ros]; nc = rn[0]; nn = rn[(size_t)e1 * ros];
+            if (np_ != ARC) { bp = fetch(np_); ilp = inv_len(hp.x, hp.y, hc.x, hc.y); }
+            if (nc != ARC) bc = fetch(nc);
+        }
+        const int Eloop = __reduce_max_sync(FULL_MASK, E);
+        for (int e = 0; e < Eloop; ++e) {
+            if (e < E) {
+                int e2 = e + 2; if (e2 >= E) e2 -= E;
+                const double2 h2 = rh[(size_t)e2 * ros];
+                const int n2 = rn[(size_t)e2 * ros];
+                Nb bn = {0.0, 0.0, 0.0, 0.0};
+                if (nn != ARC) bn = fetch(nn);
+                const double ilc = (nc != ARC) ? inv_len(hc.x, hc.y, hn.x, hn.y) : 0.0;
+                const double hx = hc.x, hy = hc.y;
+                if (np_ != ARC && nc != ARC) {
+                    // inner vertex h = circumcentre(0, pa, pb): dh = eps (h . dr_i) / (pa . eps), eps = perp(pb - pa)
+                    const double epx = -(bc.py - bp.py), epy = bc.px - bp.px;
+                    const double den = bp.px * epx + bp.py * epy;
+                    // sum_c cA_c dA_c/dh . eps  with the unseen far end replaced by h (see above)
+                    const double Sx = cAi * (hp.x - hn.x) + bp.cA * (hx - hp.x) + bc.cA * (hn.x - hx);
+                    const double Sy = cAi * (hp.y - hn.y) + bp.cA * (hy - hp.y) + bc.cA * (hn.y - hy);
+                    // unit vectors from the far ends of i's two edges towards h
+                    const double eax = (hx - hp.x) * ilp, eay = (hy - hp.y) * ilp;
+                    const double ebx = (hx - hn.x) * ilc, eby = (hy - hn.y) * ilc;
+                    const double e2n = epx * epx + epy * epy;
+                    const double elen = e2n * rsqrt(e2n);
+                    const double Ge = -0.5 * (Sx * epy - Sy * epx) + (cPi + bp.cP) * (eax * epx + eay * epy) + (cPi + bc.cP) * (ebx * epx + eby * epy);
+                    // edge (a, b) leaves h away from cell i: its unit vector is sign(den) eps / |eps|
+                    const double coef = (Ge - (bp.cP + bc.cP) * (den > 0.0 ? elen : -elen)) / den;
+                    dEx += coef * hx; dEy += coef * hy;
+                } else if ((np_ != ARC) != (nc != ARC)) {
+                    if (!pooled) { outer |= (unsigned long long)e << (4 * n_outer); ++n_outer; }
+                    else { const bool entry = (nc != ARC); outer_vertex(entry, entry ? nc : np_, entry ? bc : bp, entry ? ilc : ilp, hp, hc, hn); }
+                }
+                hp = hc; hc = hn; hn = h2; np_ = nc; nc = nn; nn = n2; bp = bc; bc = bn; ilp = ilc;
+            }
+        }
+    }
+    // ---- pass 2: the q-th outer vertex of every lane ----
+    {
+        const int qloop = __reduce_max_sync(FULL_MASK, n_outer);
+        for (int q = 0; q < qloop; ++q) {
+            if (q < n_outer) {
+                const int e = (int)((outer >> (4 * q)) & 15ull);
+                const int e0 = (e == 0) ? E - 1 : e - 1, e1 = (e + 1 == E) ? 0 : e + 1;
+                const double2 hp = rh[(size_t)e0 * ros], hc = rh[(size_t)e * ros], hn = rh[(size_t)e1 * ros];
+                const int nc = rn[(size_t)e * ros];
+                const bool entry = (nc != ARC);
+                const int j = entry ? nc : rn[(size_t)e0 * ros];
+                const Nb bj = fetch(j);
+                const double il = entry ? inv_len(hc.x, hc.y, hn.x, hn.y) : inv_len(hp.x, hp.y, hc.x, hc.y);
+                outer_vertex(entry, j, bj, il, hp, hc, hn);
+            }
+        }
+    }
+    if (misses) atomicAdd(&a.flags[1], misses);
+    if (!live) return;
     const double Fx = -dEx, Fy = -dEy;
     a.fx[s] = Fx; a.fy[s] = Fy;
-    if (a.do_step) {
+    // a step whose geometry exceeded every capacity does not move the cells: the state stays the one the error is about
+    if (a.do_step && a.flags[3] == 0) {
         const double th = a.theta[s];
         double sn, cs_;
         sincos(th, &sn, &cs_);
@@ -333,37 +401,34 @@ __global__ void k_gather_by_gid(const double *__restrict__ src, const int64_t *_
 
 // read-only view of all rings (regular fixed-stride storage + overflow pool)
 struct RingView {
-    const RingSelf *self;
-    const RingOwn *ro;
+    const double2 *ring_h;
+    const int *ring_nbr;
     const unsigned char *ring_len;
     const int *ovf_index, *ovf_len;
-    const RingShared *ovf_rs;
-    const RingOwn *ovf_ro;
-    size_t stride;   // RingOwn is slot-major outside the pool
-    // prs != nullptr: pooled ring with per-cell records; else entry e's nbr/type live in self[e * stride + s]
-    __device__ __forceinline__ int get(int s, const RingShared *&prs, const RingOwn *&pro, size_t &ros) const {
+    const double2 *ovf_ring_h;
+    const int *ovf_ring_nbr;
+    size_t stride;
+    // entry e of the ring: vertex at h[e * ros], neighbour slot (ARC = arc) at nb[e * ros]
+    __device__ __forceinline__ int get(int s, const double2 *&h, const int *&nb, size_t &ros) const {
         int E = ring_len[s];
-        prs = nullptr; pro = ro + s; ros = stride;
-        if (E == RING_IN_POOL) { const int pi = ovf_index[s]; E = ovf_len[pi]; prs = ovf_rs + (size_t)pi * RS_SLOW; pro = ovf_ro + (size_t)pi * RS_SLOW; ros = 1; }
+        h = ring_h + s; nb = ring_nbr + s; ros = stride;
+        if (E == RING_IN_POOL) { const int pi = ovf_index[s]; E = ovf_len[pi]; h = ovf_ring_h + (size_t)pi * RS_SLOW; nb = ovf_ring_nbr + (size_t)pi * RS_SLOW; ros = 1; }
         return E;
-    }
-    __device__ __forceinline__ int2 nbr_type(int s, int e, const RingShared *prs) const {
-        return prs ? *reinterpret_cast<const int2 *>(&prs[e].nbr) : *reinterpret_cast<const int2 *>(&self[(size_t)e * stride + s].nbr);
     }
 };
 
-// connections: count and emit pairs (gid_i < gid_j) from the rings
+// connections: count and emit pairs (gid_i < gid_j) from the rings (contact <=> straight ring edge)
 __global__ void k_conn_count(RingView rv, const int64_t *__restrict__ gid, const unsigned char *__restrict__ owned, int n, int *__restrict__ cnt) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     int c = 0;
-    if (owned[s]) {
-        const RingShared *rs; const RingOwn *ro; size_t ros;
-        const int E = rv.get(s, rs, ro, ros);
+    if (owned[s] == CELL_OWNED) {
+        const double2 *h; const int *nb; size_t ros;
+        const int E = rv.get(s, h, nb, ros);
         const int64_t gi = gid[s];
         for (int e = 0; e < E; ++e) {
-            const int2 q = rv.nbr_type(s, e, rs);
-            if (q.y == 1 && gi < gid[q.x]) ++c;
+            const int j = nb[e * ros];
+            if (j != ARC && gi < gid[j]) ++c;
         }
     }
     cnt[s] = c;
@@ -371,15 +436,15 @@ __global__ void k_conn_count(RingView rv, const int64_t *__restrict__ gid, const
 __global__ void k_conn_emit(RingView rv, const int64_t *__restrict__ gid, const unsigned char *__restrict__ owned, int n,
                             const int *__restrict__ off, int64_t *__restrict__ pairs) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n || !owned[s]) return;
-    const RingShared *rs; const RingOwn *ro; size_t ros;
-    const int E = rv.get(s, rs, ro, ros);
+    if (s >= n || owned[s] != CELL_OWNED) return;
+    const double2 *h; const int *nb; size_t ros;
+    const int E = rv.get(s, h, nb, ros);
     const int64_t gi = gid[s];
     int o = off[s];
     for (int e = 0; e < E; ++e) {
-        const int2 q = rv.nbr_type(s, e, rs);
-        if (q.y == 1) {
-            const int64_t gj = gid[q.x];
+        const int j = nb[e * ros];
+        if (j != ARC) {
+            const int64_t gj = gid[j];
             if (gi < gj) { pairs[2 * (size_t)o] = gi; pairs[2 * (size_t)o + 1] = gj; ++o; }
         }
     }
@@ -389,21 +454,21 @@ __global__ void k_conn_emit(RingView rv, const int64_t *__restrict__ gid, const 
 __global__ void k_ring_len_by_gid(RingView rv, const int64_t *__restrict__ gid, int n, int *__restrict__ len_out) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const RingShared *rs; const RingOwn *ro; size_t ros;
-    len_out[gid[s]] = rv.get(s, rs, ro, ros);
+    const double2 *h; const int *nb; size_t ros;
+    len_out[gid[s]] = rv.get(s, h, nb, ros);
 }
 __global__ void k_ring_emit(RingView rv, const int64_t *__restrict__ gid, const double2 *__restrict__ xy, int n,
                             const int *__restrict__ off_by_gid, signed char *__restrict__ types, double *__restrict__ vxy) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const RingShared *rs; const RingOwn *ro; size_t ros;
-    const int E = rv.get(s, rs, ro, ros);
+    const double2 *h; const int *nb; size_t ros;
+    const int E = rv.get(s, h, nb, ros);
     const int o = off_by_gid[gid[s]];
     const double xi = xy[s].x, yi = xy[s].y;
     for (int e = 0; e < E; ++e) {
-        types[o + e] = (signed char)rv.nbr_type(s, e, rs).y;
-        const RingOwn q = ro[e * ros];
-        vxy[2 * (size_t)(o + e)] = xi + q.hx; vxy[2 * (size_t)(o + e) + 1] = yi + q.hy;
+        types[o + e] = (signed char)(nb[e * ros] != ARC ? 1 : 0);
+        const double2 q = h[e * ros];
+        vxy[2 * (size_t)(o + e)] = xi + q.x; vxy[2 * (size_t)(o + e) + 1] = yi + q.y;
     }
 }
 

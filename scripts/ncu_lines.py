@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Summarise an ncu report per CUDA source line: python scripts/ncu_lines.py report.ncu-rep [top]"""
+"""Summarise an ncu report per CUDA source line: python scripts/ncu_lines.py report.ncu-rep [top] [samp|instr]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+key = 4 if (len(sys.argv) > 3 and sys.argv[3] == "instr") else 3
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 hdr = None; fname = ""; out = []
@@ -16,5 +17,5 @@ for r in rows:
             pass
 ts = sum(o[3] for o in out); ti = sum(o[4] for o in out); tt = sum(o[5] for o in out)
 print(f"samples {ts:.0f}  warp-instr {ti:.3g}  thread-instr {tt:.3g}  avg threads/instr {tt/ti:.2f}")
-for o in sorted(out, key=lambda o: -o[3])[:top]:
+for o in sorted(out, key=lambda o: -o[key])[:top]:
     print(f"{o[0][:16]:16s}{o[1]:5d} samp {100*o[3]/ts:5.1f}% instr {100*o[4]/ti:5.1f}% thr/instr {o[5]/max(o[4],1):5.1f} | {o[2][:100]}")
