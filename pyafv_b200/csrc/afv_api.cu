@@ -76,6 +76,10 @@ struct AfvContext {
     int2 *arc_key = nullptr;      // slot-major arcs (afv_device.cuh)
     double4 *arc_pts = nullptr;
     CellRec *rec = nullptr;       // per cell: position + energy prefactors, gathered by the neighbours in k_force
+    DevBuf nb_list;               // slot-major neighbour lists, nb_rows rows of `cap` slots
+    int nb_rows = 0;
+    unsigned char *nb_cnt = nullptr;
+    int *nb_min = nullptr;
     int *flags = nullptr;         // device: [0] slow-path cells, [1] lookup misses, [2] max ring length, [3] hard overflows
     int *ovf_cells = nullptr, *ovf_index = nullptr, *ovf_len = nullptr, *ovf_hull = nullptr, *ovf_m = nullptr, *ovf_ring_nbr = nullptr;
     double2 *ovf_ring_h = nullptr;
@@ -152,6 +156,8 @@ void free_all(AfvHandle h) {
     cudaFree(h->ring_h); h->ring_h = nullptr; cudaFree(h->ring_nbr); h->ring_nbr = nullptr;
     cudaFree(h->arc_key); h->arc_key = nullptr; cudaFree(h->arc_pts); h->arc_pts = nullptr;
     cudaFree(h->n_arc); h->n_arc = nullptr; cudaFree(h->rec); h->rec = nullptr;
+    cudaFree(h->nb_cnt); h->nb_cnt = nullptr; cudaFree(h->nb_min); h->nb_min = nullptr;
+    cudaFree(h->nb_list.p); h->nb_list.p = nullptr; h->nb_list.bytes = 0; h->nb_rows = 0;
     cudaFree(h->ovf_index); h->ovf_index = nullptr;
     cudaFree(h->bin_start_late); h->bin_start_late = nullptr;
     h->keys = h->keys_sorted = nullptr; h->iota = h->perm = h->bin_start = nullptr; h->cub_tmp = nullptr;
@@ -212,6 +218,8 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     if ((rc = dev_alloc(h, &h->ring_len, cap))) return rc;
     if ((rc = dev_alloc(h, &h->n_arc, cap))) return rc;
     if ((rc = dev_alloc(h, &h->rec, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->nb_cnt, cap))) return rc;
+    if ((rc = dev_alloc(h, &h->nb_min, cap))) return rc;
     if ((rc = dev_alloc(h, &h->ring_h, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->ring_nbr, (size_t)cap * RS))) return rc;
     if ((rc = dev_alloc(h, &h->arc_key, (size_t)cap * ARC_MAX))) return rc;
@@ -381,13 +389,26 @@ int stage_geometry(AfvHandle h, GeomPass gp = GeomPass()) {
         h->cmax_hint = std::max(h->cmax_hint, std::min(CMAX_HARD, std::max(24, (int)(1.8 * mean) + 12)));
     }
     int cmax = h->cmax_hint;
-    const size_t smem = geom_smem_bytes(cmax);
     cudaStream_t st = gp.stream ? gp.stream : h->stream;
     if (n > 0 && gp.fast) {
-        StageTimer t(h, 1, st);
-        if (h->late_mode) k_geom<true><<<nblk(n, GEOM_TPB), GEOM_TPB, smem, st>>>(a, cmax);
-        else k_geom<false><<<nblk(n, GEOM_TPB), GEOM_TPB, smem, st>>>(a, cmax);
-        h->launches += 1;
+        if (h->nb_rows < cmax) {   // the neighbour lists grow with the candidate capacity (the other stream of a slab may still read them)
+            CK(cudaDeviceSynchronize());
+            int rc = ensure_buf(h, h->nb_list, (size_t)cmax * (size_t)h->cap * sizeof(int));
+            if (rc) return rc;
+            h->nb_rows = cmax;
+        }
+        a.nb_list = (int *)h->nb_list.p; a.nb_cnt = h->nb_cnt; a.nb_min = h->nb_min;
+        {
+            StageTimer t(h, 1, st);
+            if (h->late_mode) k_nbrs<true><<<nblk(n, 128), 128, 0, st>>>(a, cmax);
+            else k_nbrs<false><<<nblk(n, 128), 128, 0, st>>>(a, cmax);
+        }
+        {
+            StageTimer t(h, 2, st);
+            if (h->late_mode) k_clip<true><<<nblk(n, GEOM_TPB), GEOM_TPB, clip_smem_bytes(), st>>>(a);
+            else k_clip<false><<<nblk(n, GEOM_TPB), GEOM_TPB, clip_smem_bytes(), st>>>(a);
+        }
+        h->launches += 2;
     }
     if (gp.slow) {
         StageTimer t(h, 5, st);
@@ -531,8 +552,6 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
         g_create_error = "cudaMalloc failed"; afv_destroy(h); return AFV_ERR_CUDA;
     }
     cudaMemsetAsync(h->flags, 0, 8 * sizeof(int), h->stream);
-    cudaFuncSetAttribute(k_geom<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geom_smem_bytes(CMAX_HARD));
-    cudaFuncSetAttribute(k_geom<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geom_smem_bytes(CMAX_HARD));
 
     *out = h;
     return AFV_OK;

@@ -1,8 +1,8 @@
 // K2: geometry of the finite-Voronoi cells.  Included by afv_kernels.cuh inside namespace afv.
 //
-// k_geom (fast path): one thread per cell.  The neighbours within 2r are gathered once into shared memory, the Voronoi
-// polygon is the bounding square clipped by their bisector half-planes (a linked list of edges in shared memory, the
-// links in a register), and the ring is walked right away, exactly as the reference defines it
+// k_nbrs: neighbour lists (all cells within 2r, from the 3 x 3 bins).  k_clip (fast path): one thread per cell; the
+// Voronoi polygon is a bounding square clipped by the neighbours' bisector half-planes (edges in shared-memory slots,
+// their order in a register), and the ring is walked right away, exactly as the reference defines it
 // (finite_voronoi.py:363-459), with area / perimeter / arc length (cell_geom.pyx:432-475) accumulated on the fly.
 // What it leaves behind for the force gather is small: the ring (vertex + neighbour slot, 20 B per entry), the arcs,
 // and ONE 32-byte record per cell with the energy prefactors 2KA(A-A0), 2KP(P-P0) -- no per-vertex gradient records.
@@ -27,6 +27,9 @@ struct GeomArgs {
     double4 *arc_pts;          // [ARC_MAX * stride]
     unsigned char *n_arc;      // [n]
     CellRec *rec;              // [n] what the neighbours gather in k_force
+    int *nb_list;              // [cmax * stride] slot-major neighbour lists (k_nbrs -> k_clip)
+    unsigned char *nb_cnt;     // [n] entries; NB_OVERFLOW when the list was too short
+    int *nb_min;               // [n] sorted slot of the nearest neighbour (-1: none within 2r)
     double *area, *perim, *arcl;
     int *coord;
     int *flags;                // [0] cells sent to the slow path, [1] lookup misses, [2] max ring length, [3] hard overflows
@@ -112,94 +115,164 @@ __device__ __forceinline__ int cell_rows(const int nline, const bool per, int li
 // ------------------------------------------------------------------------------------------------------
 // fast path
 // ------------------------------------------------------------------------------------------------------
-constexpr int GEOM_TPB = 64;
-constexpr int KP = 14;           // polygon edges on the fast path (<= 16: the links are 4-bit)
-constexpr int CMAX_HARD = 128;   // upper bound of the per-cell candidate list (the launch picks cmax <= this); < 252 (8-bit labels)
+constexpr int GEOM_TPB = 128;
+constexpr int KP = 14;           // polygon edges on the fast path (<= 16: the order of the slots is a sequence of 4-bit ids)
+constexpr int CMAX_HARD = 128;   // upper bound of the per-cell neighbour list (the launch picks cmax <= this)
+constexpr int NB_OVERFLOW = 255; // nb_cnt: more neighbours within 2r than the list holds
 constexpr int LAB_SIDE = -2;     // polygon-edge labels LAB_SIDE - q: side q of the bounding square (labels >= 0: sorted slots)
 
-inline size_t geom_smem_bytes(int cmax) { return (size_t)GEOM_TPB * ((size_t)cmax * sizeof(int) + (size_t)KP * (sizeof(double2) + sizeof(int))); }
-
-#ifndef GEOM_MIN_BLOCKS
-#define GEOM_MIN_BLOCKS 8
-#endif
-// One thread per cell, everything between the candidate gather and the ring on chip:
-// (1) gather: the sorted slots of all neighbours within 2r, from the 3 bin rows (<= 2 contiguous runs each), into a
-//     per-thread list in shared memory ([entry][thread], conflict free);
-// (2) polygon: a bounding square (half side 2r) clipped by the bisector half-plane of every listed neighbour.  The
-//     polygon (vertex + edge label per slot, <= KP slots, counter-clockwise) lives in shared memory.  Per neighbour one
-//     unrolled pass evaluates every vertex against the half-plane (one 16-byte shared load + 2 FMAs each) into a bit
-//     mask; the edges that leave / re-enter the half-plane follow from two bit operations, the (<= 2) new vertices are
-//     the intersections of the two generating bisectors (a vertex is a function of its generating triple only,
-//     independent of the order of the cuts), and the list is patched in place;
-// (3) ring + measures: the walk of k_geometry_slow's ring_cell, but with the vertices at hand: clockwise, starting at
-//     the edge of the nearest neighbour (so that every sum is taken in an order the geometry defines, not the sort).
-// Cells with more than cmax neighbours, KP polygon edges, RS ring entries or ARC_MAX arcs are queued for
-// k_geometry_slow.
+// ------------------------------------------------------------------------------------------------------
+// K2a: neighbour lists.  One thread per cell: the sorted slots of all cells within 2r, from the 3 bin rows (<= 2
+// contiguous runs each), slot-major (entry e of cell s at nb_list[e * stride + s]) so that k_clip, whose lanes walk their
+// lists in step, reads them coalesced.  Also the nearest neighbour (where the ring of the cell will start).
 // SLAB = false: one box, every cell, rows of bins contiguous (the single-GPU path, nothing of the slab machinery is
 // compiled in).  SLAB = true: an x-slab -- columns contiguous, pass filters, the late cells' bin table.
+// ------------------------------------------------------------------------------------------------------
 template <bool SLAB>
-__global__ void __launch_bounds__(GEOM_TPB, GEOM_MIN_BLOCKS) k_geom(GeomArgs a, const int cmax) {
-    extern __shared__ double2 s_mem[];
-    const int tid = threadIdx.x;
-    double2 *const sv = s_mem + tid;                                                       // [KP][TPB] start vertex of edge k
-    int *const sl = reinterpret_cast<int *>(s_mem + KP * GEOM_TPB) + tid;                  // [KP][TPB] label: sorted slot of the neighbour, or LAB_SIDE - q
-    int *const si = reinterpret_cast<int *>(s_mem + KP * GEOM_TPB) + KP * GEOM_TPB + tid;  // [cmax][TPB] sorted slots of the neighbours
-    constexpr int T = GEOM_TPB;
-    const int t_ = blockIdx.x * GEOM_TPB + tid;
-    bool live = t_ < a.n;
+__global__ void __launch_bounds__(128) k_nbrs(GeomArgs a, const int cmax) {
+    const int t_ = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_ >= a.n) return;
     const int s = SLAB ? slot_of_thread(a, t_) : t_;
-    const double r = a.ph.r, r2 = r * r, cut2 = 4.0 * r2;
     GridDesc g = *a.grid;
     if (!SLAB) g.swap = 0;
-    int n = 0, imin = -1;
+    int bx, by;
+    bin_xy(g, a.keys[s], bx, by);
+    if (SLAB && !pass_selects(a, g, s, bx)) return;
+    const double r = a.ph.r, cut2 = 4.0 * r * r;
+    const double2 pi_ = a.xy[s];
+    const double xi = pi_.x, yi = pi_.y;
+    const bool wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);   // only cells in the outermost bins can see a periodic image
+    const bool wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
+    // lines of bins: rows, or columns in a swapped (slab) grid
+    const int npos = g.swap ? g.nby : g.nbx, nline = g.swap ? g.nbx : g.nby, pos = g.swap ? by : bx;
+    const bool per_pos = g.swap ? g.pery : g.perx, per_line = g.swap ? g.perx : g.pery;
+    int rows[3];
+    const int nrow = cell_rows(nline, per_line, g.swap ? bx : by, rows);
+    int *const list = a.nb_list + s;
+    int n = 0, smin = -1;
     bool ok = true;
-    double xi = 0.0, yi = 0.0;
-    bool wrapx = false, wrapy = false;            // only cells in the outermost bins can see a periodic image
-    if (live) {
-        int bx, by;
-        bin_xy(g, a.keys[s], bx, by);
-        if (SLAB) live = pass_selects(a, g, s, bx);
-        if (live) {
-            // ---- (1) neighbours within 2r: the sorted cells, then (face pass of a slab) the late cells ----
-            const double2 pi_ = a.xy[s];
-            xi = pi_.x; yi = pi_.y;
-            wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);
-            wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
-            // lines of bins: rows, or columns in a swapped (slab) grid
-            const int npos = g.swap ? g.nby : g.nbx, nline = g.swap ? g.nbx : g.nby, pos = g.swap ? by : bx;
-            const bool per_pos = g.swap ? g.pery : g.perx, per_line = g.swap ? g.perx : g.pery;
-            int rows[3];
-            const int nrow = cell_rows(nline, per_line, g.swap ? bx : by, rows);
-            double dmin = 1e300;
-            for (int tab = 0; tab < (SLAB ? 2 : 1); ++tab) {
-                const int *const bin_start = tab ? a.bin_start_late : a.bin_start;
-                if (!bin_start) break;
-                const int first = tab ? a.n_main : 0;
-                for (int ir = 0; ir < nrow; ++ir) {
-                    int c0[2], c1[2];
-                    const int nrun = row_runs(npos, per_pos, bin_start, rows[ir], pos, c0, c1);
-                    for (int q = 0; q < nrun; ++q) {
+    double dmin = 1e300;
+    for (int tab = 0; tab < (SLAB ? 2 : 1); ++tab) {     // the sorted cells, then (face pass of a slab) the late cells
+        const int *const bin_start = tab ? a.bin_start_late : a.bin_start;
+        if (!bin_start) break;
+        const int first = tab ? a.n_main : 0;
+        for (int ir = 0; ir < nrow; ++ir) {
+            int c0[2], c1[2];
+            const int nrun = row_runs(npos, per_pos, bin_start, rows[ir], pos, c0, c1);
+            for (int q = 0; q < nrun; ++q) {
 #pragma unroll 4
-                        for (int c = first + c0[q]; c < first + c1[q]; ++c) {
-                            const double2 pc = a.xy[c];
-                            double dx = pc.x - xi, dy = pc.y - yi;
-                            if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
-                            if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
-                            const double d2 = dx * dx + dy * dy;
-                            if (d2 < cut2 && c != s && d2 > 0.0) {
-                                if (n < cmax) {
-                                    si[n * T] = c;
-                                    if (d2 < dmin) { dmin = d2; imin = n; }
-                                    ++n;
-                                } else ok = false;
-                            }
-                        }
+                for (int c = first + c0[q]; c < first + c1[q]; ++c) {
+                    const double2 pc = a.xy[c];
+                    double dx = pc.x - xi, dy = pc.y - yi;
+                    if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
+                    if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
+                    const double d2 = dx * dx + dy * dy;
+                    if (d2 < cut2 && c != s && d2 > 0.0) {
+                        if (n < cmax) {
+                            list[(size_t)n * a.stride] = c;
+                            if (d2 < dmin) { dmin = d2; smin = c; }
+                            ++n;
+                        } else ok = false;
                     }
                 }
             }
         }
     }
-    __syncwarp();
+    a.nb_cnt[s] = ok ? (unsigned char)n : (unsigned char)NB_OVERFLOW;
+    a.nb_min[s] = smin;
+}
+
+// intersection of the bisectors of two neighbours at displacements a and b, (a, b) in counter-clockwise order of the
+// polygon edges they carry (a x b > 0)
+__device__ __forceinline__ double2 bisector_junction(double ax, double ay, double bx, double by) {
+    // explicit roundings: the compiler must not contract the two inlined copies of this expression differently
+    const double ca = __dmul_rn(0.5, __fma_rn(ax, ax, __dmul_rn(ay, ay))), cb = __dmul_rn(0.5, __fma_rn(bx, bx, __dmul_rn(by, by)));
+    const double idet = __drcp_rn(__fma_rn(ax, by, -__dmul_rn(ay, bx)));
+    return make_double2(__dmul_rn(__fma_rn(ca, by, -__dmul_rn(cb, ay)), idet), __dmul_rn(__fma_rn(ax, cb, -__dmul_rn(bx, ca)), idet));
+}
+
+inline size_t clip_smem_bytes() { return (size_t)GEOM_TPB * ((size_t)KP * (sizeof(double2) + sizeof(int)) + sizeof(int)) + (CMAX_HARD + 2) * sizeof(int); }
+
+#ifndef CLIP_MIN_BLOCKS
+#define CLIP_MIN_BLOCKS 6
+#endif
+// ------------------------------------------------------------------------------------------------------
+// K2b: polygon, ring and measures.  One thread per cell, everything between the neighbour list and the ring on chip:
+// (1) polygon: a bounding square (half side 2r) clipped by the bisector half-plane of every listed neighbour.  The
+//     edges live in fixed SLOTS of shared memory (start vertex + label, [slot][thread], conflict free); their counter-
+//     clockwise ORDER is a sequence of 4-bit slot ids in one 64-bit register.  Per neighbour one unrolled pass
+//     evaluates every vertex against the half-plane (one 16-byte shared load + 2 FMAs each) into a bit mask; the
+//     edges that leave / re-enter the half-plane follow from two bit operations, the two new vertices are the
+//     intersections of the generating bisectors (a vertex is a function of its generating triple only, whatever the
+//     order of the cuts), and the cut itself is a rotate-mask-insert of the order register: no data moves.
+// (2) ring + measures: clockwise from the edge of the nearest neighbour (so that every sum is taken in an order the
+//     geometry defines, not the sort), with the vertices at hand; exactly the reference's ring
+//     (finite_voronoi.py:363-459) and measures (cell_geom.pyx:432-475).
+// Cells with more than cmax neighbours, KP polygon edges, RS ring entries or ARC_MAX arcs are queued for
+// k_geometry_slow.
+// ------------------------------------------------------------------------------------------------------
+template <bool SLAB>
+__global__ void __launch_bounds__(GEOM_TPB, CLIP_MIN_BLOCKS) k_clip(GeomArgs a) {
+    extern __shared__ double2 s_mem[];
+    const int tid = threadIdx.x;
+    constexpr int T = GEOM_TPB;
+    double2 *const sv = s_mem + tid;                                       // [KP][T] start vertex of the edge in slot k
+    int *const sl = reinterpret_cast<int *>(s_mem + KP * T) + tid;         // [KP][T] its label: sorted slot of the neighbour, or LAB_SIDE - q
+    // The cells of the block are dealt to its threads by decreasing list length, so that the lanes of a warp run (nearly)
+    // the same number of clips: the loop bounds below are warp maxima.  All of the block's cells share their
+    // neighbourhood, so the locality of the loads does not change.
+    // (A counting sort on the list length; which thread takes which cell of a tie is arbitrary and changes no result.)
+    int *const s_deal = reinterpret_cast<int *>(s_mem + KP * T) + KP * T;  // [T] rank -> thread index in slot order
+    int *const s_hist = s_deal + T;                                        // [CMAX_HARD + 2] cells per list length, then start ranks
+    int t_;
+    {
+        const int t0 = blockIdx.x * GEOM_TPB + tid;
+        int key = CMAX_HARD + 1;                                           // threads without a cell rank last
+        // (cells this pass does not select may carry a stale count: any value 0 .. 255)
+        if (t0 < a.n) { const int c = a.nb_cnt[SLAB ? slot_of_thread(a, t0) : t0]; key = (c > CMAX_HARD) ? CMAX_HARD : CMAX_HARD - c; }
+        for (int j = tid; j < CMAX_HARD + 2; j += T) s_hist[j] = 0;
+        __syncthreads();
+        atomicAdd(&s_hist[key], 1);
+        __syncthreads();
+        if (tid < 32) {   // exclusive scan of the CMAX_HARD + 2 counters by one warp
+            int carry = 0;
+            for (int base = 0; base < CMAX_HARD + 2; base += 32) {
+                const int j = base + tid;
+                const int v = (j < CMAX_HARD + 2) ? s_hist[j] : 0;
+                int x = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL_MASK, x, d); if (tid >= d) x += y; }
+                if (j < CMAX_HARD + 2) s_hist[j] = carry + x - v;
+                carry += __shfl_sync(FULL_MASK, x, 31);
+            }
+        }
+        __syncthreads();
+        s_deal[atomicAdd(&s_hist[key], 1)] = tid;
+        __syncthreads();
+        t_ = blockIdx.x * GEOM_TPB + s_deal[tid];
+    }
+    bool live = t_ < a.n;
+    const int s = SLAB ? slot_of_thread(a, t_) : t_;
+    const double r = a.ph.r, r2 = r * r;
+    GridDesc g = *a.grid;
+    if (!SLAB) g.swap = 0;
+    int n = 0, smin = -1;
+    bool ok = true;
+    double xi = 0.0, yi = 0.0;
+    bool wrapx = false, wrapy = false;
+    if (live) {
+        int bx, by;
+        bin_xy(g, a.keys[s], bx, by);
+        if (SLAB) live = pass_selects(a, g, s, bx);
+        if (live) {
+            const double2 pi_ = a.xy[s];
+            xi = pi_.x; yi = pi_.y;
+            wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);
+            wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
+            n = a.nb_cnt[s]; smin = a.nb_min[s];
+            if (n == NB_OVERFLOW) { ok = false; n = 0; }
+        }
+    }
     // displacement of the cell in sorted slot `slot`; normal of a polygon edge (2 x the foot point of its bisector)
     auto disp_of = [&](int slot, double &dx, double &dy) {
         const double2 pc = a.xy[slot];
@@ -216,9 +289,13 @@ __global__ void __launch_bounds__(GEOM_TPB, GEOM_MIN_BLOCKS) k_geom(GeomArgs a, 
         } else disp_of(lab, nx, ny);
     };
 
-    // ---- (2) the polygon: edge k (counter-clockwise) runs from vertex k to vertex k+1; sv[k] = vertex k, sl[k] = the sorted
-    //      slot of the neighbour whose bisector carries edge k (LAB_SIDE - q: side q of the bounding square) ----
+    // ---- (1) the polygon.  Edge at position p of the order (counter-clockwise) runs from its start vertex to the start
+    //      vertex of the edge at position p+1. ----
+    // `ord` is a permutation of all KP slot ids, 4 bits each: positions 0 .. m-1 are the edges of the polygon in order,
+    // the positions behind them the free slots.
+    unsigned long long ord = 0xfedcba9876543210ull;
     int m = 4;
+#define NIB(w, p) ((int)(((w) >> (4 * (p))) & 15ull))
     const bool work = live && ok && n > 0;
     if (work) {
         sv[0 * T] = make_double2(-B, -B); sv[1 * T] = make_double2(B, -B); sv[2 * T] = make_double2(B, B); sv[3 * T] = make_double2(-B, B);
@@ -226,69 +303,65 @@ __global__ void __launch_bounds__(GEOM_TPB, GEOM_MIN_BLOCKS) k_geom(GeomArgs a, 
     }
     {
         const int nloop = __reduce_max_sync(FULL_MASK, work ? n : 0);
-        int cnext = 0;
-        double2 pnext = make_double2(0.0, 0.0);
-        if (work) { cnext = si[0]; pnext = a.xy[cnext]; }
+        const int *const list = a.nb_list + (live ? s : 0);
+        // neighbour slots are requested two iterations ahead, their positions one iteration ahead
+        int c1 = 0, c2 = 0;
+        double2 p1 = make_double2(0.0, 0.0);
+        if (work) { c1 = list[0]; if (n > 1) c2 = list[a.stride]; p1 = a.xy[c1]; }
         for (int ci = 0; ci < nloop; ++ci) {
             const bool act = work && ok && ci < n;
-            // slot and position of this neighbour (requested one iteration ago); request the next one
-            const int c = cnext;
-            const double2 pc = pnext;
-            if (work && ci + 1 < n) { cnext = si[(ci + 1) * T]; pnext = a.xy[cnext]; }
+            const int c = c1;
+            const double2 pc = p1;
+            c1 = c2;
+            if (work && ci + 1 < n) p1 = a.xy[c1];
+            if (work && ci + 2 < n) c2 = list[(size_t)(ci + 2) * a.stride];
             double nx = pc.x - xi, ny = pc.y - yi;
             if (wrapx) nx = min_image(nx, g.Lx, g.halfLx);
             if (wrapy) ny = min_image(ny, g.Ly, g.halfLy);
             const double cc = 0.5 * (nx * nx + ny * ny);
-            // which vertices lie inside the new half-plane?  (bit k; the loop bound is the warp's largest polygon)
+            // which vertices lie inside the new half-plane?  (bit p; the loop bound is the warp's largest polygon)
             unsigned in = 0u;
             const int mloop = __reduce_max_sync(FULL_MASK, act ? m : 0);
 #pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                if (k >= mloop) break;
-                const double2 v = sv[k * T];
-                if (fma(nx, v.x, ny * v.y) <= cc) in |= 1u << k;
+            for (int p = 0; p < KP; ++p) {
+                if (p >= mloop) break;
+                const double2 v = sv[NIB(ord, p) * T];
+                if (fma(nx, v.x, ny * v.y) <= cc) in |= 1u << p;
             }
             const unsigned full = (1u << m) - 1u;
             in &= full;
             if (act && in != full && in != 0u) {
-                // ea: the edge that leaves the half-plane (vertex ea inside, vertex ea+1 outside); eb: the edge that comes back
-                const unsigned rot = ((in >> 1) | ((in & 1u) << (m - 1))) & full;      // bit k = vertex k+1 inside
+                // ea: the edge that leaves the half-plane (its start inside, its end outside); eb: the edge that comes back
+                const unsigned rot = ((in >> 1) | ((in & 1u) << (m - 1))) & full;      // bit p = vertex p+1 inside
                 const int ea = __ffs(in & ~rot) - 1, eb = __ffs(~in & rot & full) - 1;
-                const int lab_a = sl[ea * T], lab_b = sl[eb * T];
+                const int sa = NIB(ord, ea), sb = NIB(ord, eb);
                 // P = edge ea ^ new bisector, Q = edge eb ^ new bisector (intersections of the two generating bisectors)
+                // Both with the same expression, arguments in counter-clockwise order of the two edges: the bits of a vertex
+                // depend on its generating pair only, not on which of the two was clipped first.
                 double ax, ay, bx_, by_;
-                normal_of(lab_a, ax, ay);
-                normal_of(lab_b, bx_, by_);
-                const double ca = 0.5 * (ax * ax + ay * ay), cb = 0.5 * (bx_ * bx_ + by_ * by_);
-                const double ida = __drcp_rn(ax * ny - ay * nx), idb = __drcp_rn(bx_ * ny - by_ * nx);
-                const double2 Pv = make_double2((ca * ny - cc * ay) * ida, (ax * cc - nx * ca) * ida);
-                const double2 Qv = make_double2((cb * ny - cc * by_) * idb, (bx_ * cc - nx * cb) * idb);
-                int at;                           // P goes to slot `at`, Q to `at + 1`
-                if (ea < eb) {
-                    // vertices ea+1 .. eb are cut off; keep 0 .. ea, then P, Q, then eb+1 .. m-1
-                    const int sh = 2 - (eb - ea);
-                    if (m + sh > KP) ok = false;
-                    else {
-                        if (sh > 0) { for (int k = m - 1; k > eb; --k) { sv[(k + 1) * T] = sv[k * T]; sl[(k + 1) * T] = sl[k * T]; } }
-                        else if (sh < 0) { for (int k = eb + 1; k < m; ++k) { sv[(k + sh) * T] = sv[k * T]; sl[(k + sh) * T] = sl[k * T]; } }
-                        m += sh;
-                    }
-                    at = ea + 1;
-                } else {
-                    // the cut-off run wraps around the end of the list: keep eb+1 .. ea (moved to the front), then P, Q
-                    const int s0 = eb + 1, cnt = ea - eb;
-                    if (cnt + 2 > KP) ok = false;
-                    else for (int k = 0; k < cnt; ++k) { sv[k * T] = sv[(k + s0) * T]; sl[k * T] = sl[(k + s0) * T]; }
-                    m = cnt + 2;                  // <= the old m
-                    at = cnt;
+                normal_of(sl[sa * T], ax, ay);
+                normal_of(sl[sb * T], bx_, by_);
+                const double2 Pv = bisector_junction(ax, ay, nx, ny);
+                const double2 Qv = bisector_junction(nx, ny, bx_, by_);
+                // Rotate the first m positions so that eb comes first.  Then the edges at 1 .. t stay (t = where ea went), those
+                // at t+1 .. m-1 lie entirely outside, the new edge follows t, and edge eb (position 0) starts at Q.  The
+                // slot at position t+1 -- the first one that fell free, or, when only one vertex was cut off (t+1 = m), the
+                // first slot of the free tail -- takes the new edge, and everything behind it is free: the rotation IS the cut.
+                int t = ea - eb; if (t < 0) t += m;
+                if (t + 2 > KP) ok = false;       // more than KP edges
+                else {
+                    const unsigned long long mmask = (1ull << (4 * m)) - 1ull, low = ord & mmask;
+                    ord = (ord & ~mmask) | (((low >> (4 * eb)) | (low << (4 * (m - eb)))) & mmask);
+                    const int ns = NIB(ord, t + 1);
+                    m = t + 2;
+                    sv[ns * T] = Pv; sl[ns * T] = c; sv[sb * T] = Qv;
                 }
-                if (ok) { sv[at * T] = Pv; sl[at * T] = c; sv[(at + 1) * T] = Qv; sl[(at + 1) * T] = lab_b; }
             }
         }
     }
-
     const bool poly_ok = work && ok;
-    // ---- (3) ring, clockwise from the edge of the nearest neighbour: edge k is walked from the start of its
+
+    // ---- (2) ring, clockwise from the edge of the nearest neighbour: an edge is walked from the start of its
     //      counter-clockwise successor (V1) to its own start (V2)  (finite_voronoi.py:363-459) ----
     const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
     double2 *const rh = a.ring_h + (live ? s : 0);
@@ -327,25 +400,36 @@ __global__ void __launch_bounds__(GEOM_TPB, GEOM_MIN_BLOCKS) k_geom(GeomArgs a, 
         xp = x; yp = y; nbr_p = nb; ++E;
     };
     {
-        const int mw = (work && ok) ? m : 0;
+        const int mw = poly_ok ? m : 0;
         const int mloop = __reduce_max_sync(FULL_MASK, mw);
-        // the edge of the nearest neighbour (always a Voronoi neighbour)
-        const int smin = (mw && imin >= 0) ? si[imin * T] : -1;
-        int k = 0;
+        // position of the nearest neighbour's edge (it is always a Voronoi neighbour)
+        int p = 0;
 #pragma unroll
         for (int q = 0; q < KP; ++q) {
             if (q >= mloop) break;
-            if (q < mw && sl[q * T] == smin) k = q;
+            if (q < mw && sl[NIB(ord, q) * T] == smin) p = q;
         }
         double2 V1 = make_double2(0.0, 0.0);
-        if (mw) V1 = sv[((k + 1 == mw) ? 0 : k + 1) * T];
+        // label and neighbour position of the edge at position p are requested one iteration ahead
+        int jn = LAB_SIDE;
+        double2 pn = make_double2(0.0, 0.0);
+        if (mw) {
+            V1 = sv[NIB(ord, (p + 1 == mw) ? 0 : p + 1) * T];
+            jn = sl[NIB(ord, p) * T];
+            if (jn >= 0) pn = a.xy[jn];
+        }
         for (int st = 0; st < mloop; ++st) {
             if (st < mw) {
+                const int k = NIB(ord, p);
                 const double2 V2 = sv[k * T];
-                const int j = sl[k * T];
+                const int j = jn;
+                const double2 pj = pn;
+                p = (p == 0) ? mw - 1 : p - 1;
+                if (st + 1 < mw) { jn = sl[NIB(ord, p) * T]; if (jn >= 0) pn = a.xy[jn]; }
                 if (j >= 0 && ok) {                        // a real neighbour (the sides of the square emit nothing)
-                    double pcx, pcy;
-                    disp_of(j, pcx, pcy);
+                    double pcx = pj.x - xi, pcy = pj.y - yi;
+                    if (wrapx) pcx = min_image(pcx, g.Lx, g.halfLx);
+                    if (wrapy) pcy = min_image(pcy, g.Ly, g.halfLy);
                     const bool in1 = V1.x * V1.x + V1.y * V1.y <= r2;
                     // first entry of the edge: its inner start vertex (d1 <= r) or the point where it enters the disk (never
                     // both); second: the point where it leaves the disk.  An edge between two inner vertices has neither.
@@ -364,7 +448,6 @@ __global__ void __launch_bounds__(GEOM_TPB, GEOM_MIN_BLOCKS) k_geom(GeomArgs a, 
                     if (has2) emit(x2, y2, ARC, j);
                 }
                 V1 = V2;
-                k = (k == 0) ? mw - 1 : k - 1;
             }
         }
     }
@@ -377,10 +460,11 @@ __global__ void __launch_bounds__(GEOM_TPB, GEOM_MIN_BLOCKS) k_geom(GeomArgs a, 
             // only the ring outgrew the fast path: hand the polygon over, the slow path need not clip again
             const int mm = poly_ok ? m : 0;
             a.ovf_m[idx] = mm;
-            for (int k = 0; k < mm; ++k) { const int lab = sl[k * T]; a.ovf_hull[(size_t)idx * KPOLY_SLOW + k] = lab >= 0 ? lab : -2; }
+            for (int q = 0; q < mm; ++q) { const int lab = sl[NIB(ord, q) * T]; a.ovf_hull[(size_t)idx * KPOLY_SLOW + q] = lab >= 0 ? lab : -2; }
         } else atomicAdd(&a.flags[3], 1);
         a.ring_len[s] = 0; a.n_arc[s] = 0;
     }
+#undef NIB
 
     // ---- arcs: the lanes of a warp evaluate their q-th arc together (cell_geom.pyx:454-469) ----
     double Larc = 0.0;

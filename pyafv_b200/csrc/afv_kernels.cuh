@@ -191,7 +191,7 @@ __device__ __forceinline__ bool arc_far_end(const ForceArgs &a, int j, int self,
 }
 
 #ifndef FORCE_MIN_BLOCKS
-#define FORCE_MIN_BLOCKS 4
+#define FORCE_MIN_BLOCKS 6
 #endif
 __global__ void __launch_bounds__(128, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -209,6 +209,11 @@ __global__ void __launch_bounds__(128, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
         E = a.ovf_len[pi]; rh = a.ovf_ring_h + (size_t)pi * RS_SLOW; rn = a.ovf_ring_nbr + (size_t)pi * RS_SLOW; ros = 1; pooled = true;
     }
     if (E < 2) E = 0;
+    // the whole ring is requested up front: the walk below then finds it in L1 instead of paying one DRAM round trip per entry
+    for (int e = 0; e < E; ++e) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rh + (size_t)e * ros));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rn + (size_t)e * ros));
+    }
     const GridDesc g = *a.grid;
     CellRec me = {0.0, 0.0, 0.0, 0.0};
     if (live) me = a.rec[s];
