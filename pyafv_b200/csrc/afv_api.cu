@@ -299,7 +299,7 @@ void periodic_grid(AfvHandle h, GridDesc &g) {
     g.nbx = nbx; g.nby = nby; g.perx = h->slab ? 0 : 1; g.pery = 1;
     // late-cell stepping of an x-slab: columns contiguous, so that the face columns are the two ends of the sorted order
     g.swap = (h->slab && h->late_mode) ? 1 : 0;
-    g.pad_ = 0;
+    g.mix = h->slab ? 1 : 0;
 }
 
 int upload_grid_periodic(AfvHandle h) {
@@ -390,14 +390,15 @@ int stage_geometry(AfvHandle h, GeomPass gp = GeomPass()) {
     }
     int cmax = h->cmax_hint;
     cudaStream_t st = gp.stream ? gp.stream : h->stream;
+    a.nb_list = (int *)h->nb_list.p; a.nb_cnt = h->nb_cnt; a.nb_min = h->nb_min;
     if (n > 0 && gp.fast) {
         if (h->nb_rows < cmax) {   // the neighbour lists grow with the candidate capacity (the other stream of a slab may still read them)
             CK(cudaDeviceSynchronize());
             int rc = ensure_buf(h, h->nb_list, (size_t)cmax * (size_t)h->cap * sizeof(int));
             if (rc) return rc;
             h->nb_rows = cmax;
+            a.nb_list = (int *)h->nb_list.p;
         }
-        a.nb_list = (int *)h->nb_list.p; a.nb_cnt = h->nb_cnt; a.nb_min = h->nb_min;
         {
             StageTimer t(h, 1, st);
             if (h->late_mode) k_nbrs<true><<<nblk(n, 128), 128, 0, st>>>(a, cmax);
@@ -434,7 +435,7 @@ int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, doub
     a.ph = phys_dev(h->prm); a.fx = h->fx; a.fy = h->fy; a.flags = h->flags;
     a.do_step = do_step ? 1 : 0; a.xy = h->xy[c]; a.theta = h->th[c];
     a.dt = dt; a.mu = mu; a.v0 = v0; a.noise_amp = std::sqrt(2.0 * Dr * dt); a.seed = seed; a.step = step;
-    a.noise = noise_row; a.Lx = h->slab ? 0.0 : h->L; a.Ly = h->L;
+    a.noise = noise_row; a.Lx = h->L; a.Ly = h->L;   // a slab keeps the box's own coordinates, wrapped like the single-GPU run
     k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
     h->launches += 1;
     CK(cudaGetLastError());

@@ -24,10 +24,11 @@ struct GridDesc {
     double Lx, halfLx;    // periodic period in x (used when perx)
     double Ly, halfLy;    // periodic period in y (used when pery)
     int nbx, nby;
-    int perx, pery;       // periodic wrap of the bin grid / minimum image per direction
+    int perx, pery;       // periodic wrap of the bin grid per direction (and minimum image for the cells in its outermost bins)
     int swap;             // 0: key = by * nbx + bx (rows contiguous); 1: key = bx * nby + by (columns contiguous: x-slabs, whose face
                           // columns then are the two ends of the sorted order)
-    int pad_;
+    int mix;              // x-slab of a periodic box: the bin grid is open in x, but positions are the box's own (wrapped into
+                          // [0, Lx)), so bins are taken from the wrapped offset to x0 and EVERY displacement gets the minimum image in x
 };
 
 __device__ __forceinline__ unsigned bin_key(const GridDesc &g, int bx, int by) {
@@ -61,6 +62,13 @@ struct __align__(16) CellRec {
 // boundary pieces than that goes to the pool like a cell with a long ring).
 constexpr int ARC_MAX = 4;
 constexpr int ARC_SLOW = RS_SLOW / 2;
+
+// bin column of x (clamped)
+__device__ __forceinline__ int bin_col(const GridDesc &g, double x) {
+    double xr = x - g.x0;
+    if (g.mix) xr -= g.Lx * floor(xr / g.Lx);
+    return min(max((int)floor(xr * g.inv_bx), 0), g.nbx - 1);
+}
 
 __device__ __forceinline__ double min_image(double d, double L, double halfL) {
     if (d > halfL) d -= L;

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(128) k_nbrs(GeomArgs a, const int cmax) {
     const double r = a.ph.r, cut2 = 4.0 * r * r;
     const double2 pi_ = a.xy[s];
     const double xi = pi_.x, yi = pi_.y;
-    const bool wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);   // only cells in the outermost bins can see a periodic image
+    const bool wrapx = g.mix || (g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3));   // only cells in the outermost bins can see a periodic image
     const bool wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
     // lines of bins: rows, or columns in a swapped (slab) grid
     const int npos = g.swap ? g.nby : g.nbx, nline = g.swap ? g.nbx : g.nby, pos = g.swap ? by : bx;
@@ -168,11 +168,9 @@ __global__ void __launch_bounds__(128) k_nbrs(GeomArgs a, const int cmax) {
                     if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
                     const double d2 = dx * dx + dy * dy;
                     if (d2 < cut2 && c != s && d2 > 0.0) {
-                        if (n < cmax) {
-                            list[(size_t)n * a.stride] = c;
-                            if (d2 < dmin) { dmin = d2; smin = c; }
-                            ++n;
-                        } else ok = false;
+                        if (d2 < dmin) { dmin = d2; smin = c; }
+                        if (n < cmax) { list[(size_t)n * a.stride] = c; ++n; }
+                        else ok = false;
                     }
                 }
             }
@@ -267,7 +265,7 @@ __global__ void __launch_bounds__(GEOM_TPB, CLIP_MIN_BLOCKS) k_clip(GeomArgs a) 
         if (live) {
             const double2 pi_ = a.xy[s];
             xi = pi_.x; yi = pi_.y;
-            wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);
+            wrapx = g.mix || (g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3));
             wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
             n = a.nb_cnt[s]; smin = a.nb_min[s];
             if (n == NB_OVERFLOW) { ok = false; n = 0; }
@@ -526,15 +524,23 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
         if (live) {
             const double2 pi_ = a.xy[s];
             xi = pi_.x; yi = pi_.y;
-            wrapx = g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3);
+            wrapx = g.mix || (g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3));
             wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
             m = m_pool;
         }
     }
     const bool queued = false;
+    // the walk starts at the edge of the nearest neighbour, like k_clip's: edge index k of the walk is entry k + rot of the
+    // polygon (so that the sums are taken in the same order whichever path a cell takes)
+    int rot = 0;
+    if (live && m > 0) {
+        const int smin = a.nb_min[s];
+        for (int k = 0; k < m; ++k) if (hs[k * hst] == smin) rot = (k + 1 == m) ? 0 : k + 1;
+    }
+    auto hidx = [&](int k) { int q = k + rot; if (q >= m) q -= m; return hs[q * hst]; };
     // displacement of polygon edge k's neighbour
     auto disp = [&](int k, double &dx, double &dy, int &slot) {
-        slot = hs[k * hst];
+        slot = hidx(k);
         if (slot >= 0) {
             const double2 pc = a.xy[slot];
             dx = pc.x - xi; dy = pc.y - yi;
@@ -562,10 +568,8 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
     auto junction = [&](int ja, double ax, double ay, int jb, double bx_, double by_, double &eax, double &eay, double &sbx, double &sby) {
         const double det = ax * by_ - ay * bx_;
         if (ja >= 0 && jb >= 0 && det > 0.0) {
-            const double ca = 0.5 * (ax * ax + ay * ay), cb = 0.5 * (bx_ * bx_ + by_ * by_);
-            const double idet = __drcp_rn(det);
-            eax = sbx = (ca * by_ - cb * ay) * idet;
-            eay = sby = (ax * cb - bx_ * ca) * idet;
+            const double2 v = bisector_junction(ax, ay, bx_, by_);
+            eax = sbx = v.x; eay = sby = v.y;
         } else {
             eax = eay = sbx = sby = 0.0;
             if (ja >= 0) { const double f = B4 * rsqrt(ax * ax + ay * ay); eax = 0.5 * ax - f * ay; eay = 0.5 * ay + f * ax; }      // C_A + 4r ccw(A)
@@ -605,7 +609,7 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
     {
         // the walk visits the edges m-1, then m-2, ..., 0 and needs the PREVIOUS polygon edge of each: slot indices are
         // requested two iterations ahead, positions one iteration ahead, so neither load sits on the critical path
-        auto load_slot = [&](int k) { return hs[k * hst]; };
+        auto load_slot = [&](int k) { return hidx(k); };
         auto load_pos = [&](int slot) { return slot >= 0 ? a.xy[slot] : make_double2(0.0, 0.0); };
         auto rel = [&](int slot, double2 pc, double &dx, double &dy) {
             if (slot >= 0) {
@@ -749,7 +753,7 @@ __device__ __noinline__ int clip_cell_slow(const GeomArgs &a, const int s, const
                     if (c == s) continue;
                     const double2 pc = a.xy[c];
                     double dx = pc.x - xi, dy = pc.y - yi;
-                    if (g.perx) dx = min_image(dx, g.Lx, g.halfLx);
+                    if (g.perx || g.mix) dx = min_image(dx, g.Lx, g.halfLx);
                     if (g.pery) dy = min_image(dy, g.Ly, g.halfLy);
                     const double d2 = dx * dx + dy * dy;
                     if (d2 >= cut2 || d2 == 0.0) continue;

@@ -65,7 +65,7 @@ __global__ void k_bbox_final(const double *__restrict__ part, int nblocks, doubl
         int nbx = (int)fx, nby = (int)fy;
         double bsx = fmax(cut, sx / (double)nbx), bsy = fmax(cut, sy / (double)nby);
         g->x0 = xmin; g->y0 = ymin; g->inv_bx = 1.0 / bsx; g->inv_by = 1.0 / bsy;
-        g->Lx = g->Ly = 0.0; g->halfLx = g->halfLy = 0.0; g->nbx = nbx; g->nby = nby; g->perx = 0; g->pery = 0; g->swap = 0; g->pad_ = 0;
+        g->Lx = g->Ly = 0.0; g->halfLx = g->halfLy = 0.0; g->nbx = nbx; g->nby = nby; g->perx = 0; g->pery = 0; g->swap = 0; g->mix = 0;
     }
 }
 
@@ -81,8 +81,8 @@ __global__ void k_bin_keys(const double2 *__restrict__ xy, const unsigned char *
     if (owned[i] == CELL_DEAD) { keys[i] = dead_key; return; }
     const GridDesc g = *gp;
     const double2 q = xy[i];
-    int bx = (int)floor((q.x - g.x0) * g.inv_bx), by = (int)floor((q.y - g.y0) * g.inv_by);
-    bx = min(max(bx, 0), g.nbx - 1);
+    const int bx = bin_col(g, q.x);
+    int by = (int)floor((q.y - g.y0) * g.inv_by);
     by = min(max(by, 0), g.nby - 1);
     keys[i] = bin_key(g, bx, by);
 }
@@ -161,10 +161,18 @@ struct ForceArgs {
     double Lx, Ly;                 // periodic wrap of the updated positions per direction (0 = none)
 };
 
-// exchange lists of an owned cell at x (bit q set = member of list q, see k_exchange_count)
-__device__ __forceinline__ unsigned xch_lists(double x, unsigned char own, double lo, double hi, double halo) {
+// offset of x to the lower face `lo` of the slab; with a box period L > 0 the positions are the box's own (wrapped into
+// [0, L)) and the offset is the minimum image
+__device__ __forceinline__ double slab_offset(double x, double lo, double L) {
+    double d = x - lo;
+    if (L > 0.0) { if (d >= 0.5 * L) d -= L; else if (d < -0.5 * L) d += L; }
+    return d;
+}
+// exchange lists of an owned cell at offset xr = slab_offset(x) in a slab of width W (bit q set = member of list q, see
+// k_exchange_count)
+__device__ __forceinline__ unsigned xch_lists(double xr, unsigned char own, double W, double halo) {
     if (own != CELL_OWNED) return 0u;
-    return (x < lo ? 1u : 0u) | ((x >= lo && x < lo + halo) ? 2u : 0u) | (x >= hi ? 4u : 0u) | ((x >= hi - halo && x < hi) ? 8u : 0u);
+    return (xr < 0.0 ? 1u : 0u) | ((xr >= 0.0 && xr < halo) ? 2u : 0u) | (xr >= W ? 4u : 0u) | ((xr >= W - halo && xr < W) ? 8u : 0u);
 }
 
 // far end (relative to cell j) of j's arc that STARTS where j's contact edge with `self` ends (starts_there) or that
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(128, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
         const double4 v = *reinterpret_cast<const double4 *>(a.rec + j);
         Nb o;
         o.px = v.x - me.x; o.py = v.y - me.y;
-        if (g.perx) o.px = min_image(o.px, g.Lx, g.halfLx);
+        if (g.perx || g.mix) o.px = min_image(o.px, g.Lx, g.halfLx);
         if (g.pery) o.py = min_image(o.py, g.Ly, g.halfLy);
         o.cA = v.z; o.cP = v.w;
         return o;
@@ -522,9 +530,9 @@ __global__ void k_pack_message(const int *__restrict__ idx, const int *__restric
 constexpr int XCH_TPB = 256;
 // pass 1: members of every list per block
 __global__ void __launch_bounds__(XCH_TPB) k_exchange_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n,
-                                                            double lo, double hi, double halo, int *__restrict__ blk_cnt) {
+                                                            double lo, double hi, double halo, double L, int *__restrict__ blk_cnt) {
     const int i = blockIdx.x * XCH_TPB + threadIdx.x;
-    const unsigned m = (i < n) ? xch_lists(xy[i].x, owned[i], lo, hi, halo) : 0u;
+    const unsigned m = (i < n) ? xch_lists(slab_offset(xy[i].x, lo, L), owned[i], hi - lo, halo) : 0u;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int c = __syncthreads_count((m >> q) & 1u);
@@ -583,7 +591,7 @@ __global__ void __launch_bounds__(1024) k_exchange_scan(const int *__restrict__ 
 __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__restrict__ xy, const double *__restrict__ th,
                                                            const double *__restrict__ a0, const int64_t *__restrict__ gid,
                                                            unsigned char *__restrict__ owned, int n,
-                                                           double lo, double hi, double halo, double shift_left, double shift_right,
+                                                           double lo, double hi, double halo, double L, double shift_left, double shift_right,
                                                            double deep_lo, double deep_hi, const int *__restrict__ blk_off,
                                                            const int *__restrict__ totals, int cap, double *__restrict__ msg_left,
                                                            double *__restrict__ msg_right) {
@@ -593,7 +601,8 @@ __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__rest
     double2 p = make_double2(0.0, 0.0);
     unsigned char own = CELL_DEAD;
     unsigned m = 0u;
-    if (i < n) { p = xy[i]; own = owned[i]; m = xch_lists(p.x, own, lo, hi, halo); }
+    double xr = 0.0;
+    if (i < n) { p = xy[i]; own = owned[i]; xr = slab_offset(p.x, lo, L); m = xch_lists(xr, own, hi - lo, halo); }
     int rank_in_warp[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -608,8 +617,8 @@ __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__rest
     }
     if (!m) return;
     // transfers that land beyond the receiver's face columns (header slot 2): its face pass then covers every cell
-    if ((m & 1u) && p.x < deep_lo) atomicAdd(&msg_left[2], 1.0);
-    if ((m & 4u) && p.x >= deep_hi) atomicAdd(&msg_right[2], 1.0);
+    if ((m & 1u) && xr < deep_lo - lo) atomicAdd(&msg_left[2], 1.0);
+    if ((m & 4u) && xr >= deep_hi - lo) atomicAdd(&msg_right[2], 1.0);
     const double tv = th[i], av = a0[i], gv = (double)gid[i];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -656,8 +665,8 @@ __global__ void k_late_keys(const double *__restrict__ in_left, const double *__
     if (i >= nl + nr) return;
     const double *q = (i < nl ? in_left + 5 * (size_t)(i + 1) : in_right + 5 * (size_t)(i - nl + 1));
     const GridDesc g = *gp;
-    int bx = (int)floor((q[0] - g.x0) * g.inv_bx), by = (int)floor((q[1] - g.y0) * g.inv_by);
-    bx = min(max(bx, 0), g.nbx - 1);
+    const int bx = bin_col(g, q[0]);
+    int by = (int)floor((q[1] - g.y0) * g.inv_by);
     by = min(max(by, 0), g.nby - 1);
     keys[i] = bin_key(g, bx, by);
 }

@@ -6,7 +6,8 @@ pickling them to workers every step, every rank keeps its x-slab resident on its
 
 1. a halo: the owned cells within ``halo_width`` (default 4.01 l, the reference's default at
    ``parallel_voronoi.py:485`` -- forces need a 4 l dependence range, ``_connectutil.py:19``) of each slab face go
-   to the neighbouring rank, shifted by +-L across the periodic box face;
+   to the neighbouring rank, in the box's own coordinates (displacements are minimum images on every rank, so the
+   operands -- and therefore the results, bit for bit -- are those of the single-GPU run);
 2. ownership transfers: cells that crossed a face during the previous update change owner (the old owner keeps a
    halo copy for this step -- the cell is still within the halo of the face it crossed).
 
@@ -151,7 +152,12 @@ def loopback_exchange(outboxes: list[tuple[torch.Tensor, torch.Tensor]]) -> list
 # the exchange logic (device agnostic)
 # ------------------------------------------------------------------------------------------------------
 class SlabGeometry:
-    """x-slab ``rank`` of ``world`` equal slabs of the periodic square ``[0, L)^2``."""
+    """x-slab ``rank`` of ``world`` equal slabs of the periodic square ``[0, L)^2``.
+
+    Every rank keeps the box's own coordinates (wrapped into ``[0, L)``, exactly like the single-GPU run); offsets to the
+    slab faces and displacements between cells are minimum images.  Nothing is shifted across the box face, so every rank
+    forms a displacement from the same two operands as the single-GPU run: results do not depend on the number of GPUs.
+    """
 
     def __init__(self, L: float, rank: int, world: int, r: float, halo_width: float | None = None):
         self.L, self.rank, self.world, self.r = float(L), int(rank), int(world), float(r)
@@ -160,11 +166,17 @@ class SlabGeometry:
         self.halo = float(4.01 * r if halo_width is None else halo_width)
         if world > 1 and self.W < self.halo:
             raise ValueError(f"slab width {self.W:g} is smaller than the halo width {self.halo:g}: use fewer GPUs")
-        # across the periodic box face the neighbour's coordinates are shifted by one period
-        self.shift_to_left = self.L if rank == 0 else 0.0            # what WE add when sending to the left rank
-        self.shift_to_right = -self.L if rank == world - 1 else 0.0
         pad = 0.5 * r
+        if world > 1 and self.W + 2.0 * (self.halo + pad) > self.L:
+            # (with two slabs both neighbours are the same rank: its two halo strips must not overlap)
+            raise ValueError(f"slab + halo ({self.W + 2 * (self.halo + pad):g}) does not fit the box ({self.L:g}): use fewer GPUs")
+        self.shift_to_left = self.shift_to_right = 0.0     # messages carry the box's own coordinates
         self.grid_x0, self.grid_x1 = self.lo - self.halo - pad, self.hi + self.halo + pad
+
+    def offset(self, x):
+        """Minimum-image offset of x to the lower face of the slab (what the exchange kernels classify cells by)."""
+        d = np.asarray(x, dtype=np.float64) - self.lo
+        return d - self.L * np.floor(d / self.L + 0.5) if self.world > 1 else d
 
 
 def halo_capacity(n_owned: int, geo: SlabGeometry) -> int:

@@ -31,10 +31,12 @@ def test_sharded_build_equals_single(world, dens):
     sh = LoopbackShardedSimulator(pts, theta, phys, L, world, A0=A0)
     b = sh.build()
     assert np.array_equal(b["gids"], np.arange(len(pts)))
-    for k in ("forces", "areas", "perimeters", "arclens"):
-        scale = max(1.0, np.abs(a[k]).max())
-        assert np.abs(a[k] - b[k]).max() <= 1e-9 * scale, k
-    assert np.array_equal(a["coord_nums"], b["coord_nums"])
+    # the result must not depend on the number of GPUs -- bit for bit.  Every rank holds the box's own
+    # coordinates, displacements are minimum images of the same operands, vertices and sums are taken in an order the
+    # geometry defines (not the sort), so the slabs reproduce the single handle exactly.
+    assert np.array_equal(b["pts"], pts)
+    for k in ("forces", "areas", "perimeters", "arclens", "coord_nums"):
+        assert np.array_equal(a[k], b[k]), (k, np.abs(a[k] - b[k]).max())
     ref.close(); sh.close()
 
 
@@ -54,10 +56,8 @@ def test_sharded_trajectory_equals_single():
         s._step_index = 200                                    # same position in the noise stream as the reference run
     sh.step(0.01, 1.0, 2.4, 0.3, seed=5, n_steps=30)
     b = sh.build()
-    d = b["pts"] - ref.pts
-    d -= L * np.round(d / L)
-    assert np.abs(d).max() <= 1e-8
-    assert np.abs(b["theta"] - ref.theta).max() <= 1e-10
+    assert np.array_equal(b["pts"], ref.pts)                   # bit-identical trajectories, whatever the number of slabs
+    assert np.array_equal(b["theta"], ref.theta)
     assert sum(s.n_owned for s in sh.ranks) == len(pts)
     ref.close(); sh.close()
 
@@ -84,19 +84,12 @@ def test_late_cell_exchange_equals_plain(world):
             assert all(st["late_steps"] == 40 and st["late_cells"] > 0 for st in stats)
         out.append((mid, sh.build()))
         sh.close()
-    # the two runs order the cells of a bin differently, so near-degenerate orientation tests may fall the other way
-    # (edges of length ~1e-16) and this violent dynamics amplifies that: most cells stay bit-identical, the rest
-    # agrees to ~1e-8; a missed halo cell or transfer would show up as an O(1) difference
+    # the two runs meet the neighbours of a cell in different orders (row-major against column-major bins, late cells
+    # behind the sorted ones); nothing may depend on that: the trajectories are bit-identical even though this violent
+    # dynamics would amplify a last-bit difference to O(1) within the 40 steps
     for a, b in zip(out[0], out[1]):
-        assert np.array_equal(a["gids"], b["gids"])
-        d = a["pts"] - b["pts"]
-        d -= L * np.round(d / L)
-        assert np.abs(d).max() <= 1e-7
-        for k in ("theta", "forces", "areas", "perimeters", "arclens"):
-            scale = max(1.0, np.abs(a[k]).max())
-            assert np.abs(a[k] - b[k]).max() <= 1e-6 * scale, k
-            assert np.mean(a[k] == b[k]) > 0.9, k
-        assert np.mean(a["coord_nums"] == b["coord_nums"]) > 0.999
+        for k in ("gids", "pts", "theta", "forces", "areas", "perimeters", "arclens", "coord_nums"):
+            assert np.array_equal(a[k], b[k]), (k, np.abs(a[k] - b[k]).max())
 
 
 def test_late_cells_beyond_the_face_columns_trigger_the_full_face_pass():
@@ -140,8 +133,5 @@ def test_late_cell_exchange_follows_single_gpu():
     sh.step(0.01, 1.0, 2.4, 0.3, seed=5, n_steps=30)
     assert all(s.overlapped_steps == 30 for s in sh.ranks)
     b = sh.build()
-    d = b["pts"] - ref.pts
-    d -= L * np.round(d / L)
-    assert np.abs(d).max() <= 1e-8
-    assert np.abs(b["theta"] - ref.theta).max() <= 1e-10
+    assert np.array_equal(b["pts"], ref.pts) and np.array_equal(b["theta"], ref.theta)
     ref.close(); sh.close()

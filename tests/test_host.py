@@ -61,15 +61,19 @@ def test_backend_module_names():
     assert backend._BACKEND_NAME == "cuda" and backend._IMPORT_ERROR is None
 
 
-def test_slab_geometry_shifts():
+def test_slab_geometry():
     from pyafv_b200.sharded import SlabGeometry
     g0, g3 = SlabGeometry(100.0, 0, 4, 1.0), SlabGeometry(100.0, 3, 4, 1.0)
     assert (g0.lo, g0.hi, g3.lo, g3.hi) == (0.0, 25.0, 75.0, 100.0)
-    assert g0.shift_to_left == 100.0 and g0.shift_to_right == 0.0
-    assert g3.shift_to_left == 0.0 and g3.shift_to_right == -100.0
+    # nothing is shifted across the box face: offsets to the slab are minimum images of the box's own coordinates
+    assert g0.shift_to_left == 0.0 and g3.shift_to_right == 0.0
+    assert np.allclose(g0.offset([99.5, 0.5, 26.0]), [-0.5, 0.5, 26.0])
+    assert np.allclose(g3.offset([0.5, 74.0, 99.0]), [25.5, -1.0, 24.0])
     assert g0.halo == pytest.approx(4.01)
     with pytest.raises(ValueError):
         SlabGeometry(10.0, 0, 4, 1.0)
+    with pytest.raises(ValueError):
+        SlabGeometry(17.0, 0, 2, 1.0)       # two slabs: the two halo strips of the one neighbour would overlap
 
 
 def test_tile_pbc_matches_reference_semantics():

@@ -1,6 +1,6 @@
 """CPU, world_size 2 and 3 over gloo: the halo / migration exchange logic of pyafv_b200.sharded with a numpy
 cell store standing in for the GPU handle.  Checks, against brute force on the gathered global state, that after
-the halo exchange every rank holds exactly the cells within the halo width of its slab (in its own unwrapped
+the halo exchange every rank holds exactly the cells within the halo width of its slab (in the box's own, wrapped
 coordinates), and that migration keeps every cell owned by exactly one rank, the right one."""
 from __future__ import annotations
 
@@ -43,11 +43,11 @@ class NumpyCellStore:
     # the message format of afv_pack_exchange / afv_finish_exchange: (cap+1, ROW), header [n_transfer, n_halo, 0, 0, 0]
     def pack_exchange(self, geo, cap):
         self.drop_halo()                              # copies of the previous exchange are retired by the pack pass
-        x = self.rows[:, 0]
-        self._slab = (geo.lo, geo.hi)
+        x = geo.offset(self.rows[:, 0])               # minimum-image offset to the lower face (k_exchange_count / _pack)
+        self._geo = geo
         out = []
-        for mig, halo, shift in (((x < geo.lo), (x >= geo.lo) & (x < geo.lo + geo.halo), geo.shift_to_left),
-                                 ((x >= geo.hi), (x >= geo.hi - geo.halo) & (x < geo.hi), geo.shift_to_right)):
+        for mig, halo, shift in (((x < 0), (x >= 0) & (x < geo.halo), geo.shift_to_left),
+                                 ((x >= geo.W), (x >= geo.W - geo.halo) & (x < geo.W), geo.shift_to_right)):
             a, b = self.rows[self.owned & mig].copy(), self.rows[self.owned & halo].copy()
             assert len(a) + len(b) <= cap
             msg = np.zeros((cap + 1, ROW))
@@ -59,9 +59,8 @@ class NumpyCellStore:
         return out
 
     def finish_exchange(self, from_left, from_right, cap):
-        lo, hi = self._slab
-        x = self.rows[:, 0]
-        self.owned &= (x >= lo) & (x < hi)           # transferred cells stay as halo copies
+        x = self._geo.offset(self.rows[:, 0])
+        self.owned &= (x >= 0) & (x < self._geo.W)   # transferred cells stay as halo copies
         for m in (from_left, from_right):
             na, nb = int(m[0, 0]), int(m[0, 1])
             self.append(m[1:1 + na].clone(), False)
@@ -93,31 +92,22 @@ def _worker(rank, world, port, L, N, halo, q):
             counts = torch.tensor([len(ids)])
             dist.all_reduce(counts)
             assert int(counts) == N
-            # halo: every cell of another rank within the halo width of the slab, in this rank's unwrapped frame
-            want = {}
-            for i in range(N):
-                if geo.lo <= xs[i] < geo.hi:
-                    continue
-                for sh in (-L, 0.0, L):
-                    x = xs[i] + sh
-                    if (geo.lo - halo <= x < geo.lo) or (geo.hi <= x < geo.hi + halo):
-                        want.setdefault(i, []).append(x)
+            # halo: every cell of another rank within the halo width of the slab (minimum-image offsets), held once, in the
+            # box's own coordinates
+            off = geo.offset(xs)
+            want = set(np.flatnonzero(((off >= -halo) & (off < 0)) | ((off >= geo.W) & (off < geo.W + halo))).tolist())
             got = {}
             for g, x in zip(store.rows[~store.owned, 4], store.rows[~store.owned, 0]):
                 got.setdefault(int(g), []).append(float(x))
-            assert set(want) <= set(got), (rank, it, sorted(set(want) - set(got))[:5])
-            for i in want:                                      # (copies of transferred cells may sit a little deeper)
-                for x in want[i]:
-                    assert min(abs(x - y) for y in got[i]) < 1e-9
-            for i in got:                                       # nothing but genuine images of other ranks' cells
-                for y in got[i]:
-                    assert min(abs(y - (xs[i] + sh)) for sh in (-L, 0.0, L)) < 1e-9 and not (geo.lo <= y < geo.hi)
+            assert want <= set(got), (rank, it, sorted(want - set(got))[:5])
+            for i in got:                                       # nothing but the other ranks' cells, once each, unshifted
+                assert len(got[i]) == 1 and abs(got[i][0] - xs[i]) < 1e-9 and not (geo.lo <= xs[i] < geo.hi), (rank, it, i, got[i])
             if it % 2:                                          # explicit drop and drop-by-the-next-pack both occur
                 store.drop_halo()
             # ---- "dynamics": a deterministic drift that pushes cells across faces (< halo width) ----
             drift = 0.9 * np.sin(np.arange(N) + it)
             ids = store.rows[:, 4].astype(int)
-            store.rows[:, 0] += drift[ids]                          # local, un-wrapped like the GPU step leaves it
+            store.rows[:, 0] = np.mod(store.rows[:, 0] + drift[ids], L)   # wrapped into the box, as the GPU step leaves it
             pts[:, 0] = np.mod(pts[:, 0] + drift, L)
         q.put((rank, "ok"))
     except Exception as e:   # surface the failure to the parent
