@@ -187,17 +187,17 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
         if ((rc = dev_alloc(h, &h->gid[k], cap))) break;
         if ((rc = dev_alloc(h, &h->owned[k], cap))) break;
     }
+    cudaError_t ce = cudaSuccess;
     if (rc == AFV_OK && keep > 0 && oxy) {
         h->cur = 0;
-        cudaMemcpyAsync(h->xy[0], oxy, keep * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream);
-        cudaMemcpyAsync(h->th[0], ot, keep * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
-        cudaMemcpyAsync(h->a0[0], oa, keep * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
-        cudaMemcpyAsync(h->gid[0], og, keep * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream);
-        cudaMemcpyAsync(h->owned[0], oo, keep, cudaMemcpyDeviceToDevice, h->stream);
-        cudaStreamSynchronize(h->stream);
+        auto cp = [&](void *dst, const void *src, size_t bytes) { if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, h->stream); };
+        cp(h->xy[0], oxy, keep * sizeof(double2)); cp(h->th[0], ot, keep * sizeof(double)); cp(h->a0[0], oa, keep * sizeof(double));
+        cp(h->gid[0], og, keep * sizeof(int64_t)); cp(h->owned[0], oo, keep);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
     }
     cudaFree(oxy); cudaFree(ot); cudaFree(oa); cudaFree(og); cudaFree(oo);
-    if (rc) return rc;
+    if (rc == AFV_OK && ce != cudaSuccess) { h->err = std::string("reserve: ") + cudaGetErrorString(ce); rc = AFV_ERR_CUDA; }
+    if (rc) { h->n = h->n_owned = h->n_dead = 0; h->built = false; return rc; }   // the old state is gone: the handle is empty, not stale
     // bins: up to 2 per cell, power of two so that the sort width is fixed
     int bits = 6;
     while (((int64_t)1 << bits) < 2 * cap && bits < 31) ++bits;
@@ -614,6 +614,10 @@ int afv_set_positions(AfvHandle h, const double *xy_host, int64_t N) {
         CK(cudaMemcpyAsync(h->xy[h->cur], xy_host, (size_t)N * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
         k_init_cells<<<nblk(n, 256), 256, 0, h->stream>>>(n, h->gid[h->cur], h->owned[h->cur]);
         h->launches += 1;
+        if (h->L > 0.0 && !h->slab) {   // cells outside the box would miss their neighbours across the other face
+            k_wrap_box<<<nblk(n, 256), 256, 0, h->stream>>>(h->xy[h->cur], n, h->L);
+            h->launches += 1;
+        }
     }
     h->n = N; h->n_owned = N; h->n_dead = 0; h->gid_is_perm = true; h->built = false;
     CK(cudaGetLastError());

@@ -161,12 +161,13 @@ struct ForceArgs {
     double Lx, Ly;                 // periodic wrap of the updated positions per direction (0 = none)
 };
 
-// offset of x to the lower face `lo` of the slab; with a box period L > 0 the positions are the box's own (wrapped into
-// [0, L)) and the offset is the minimum image
-__device__ __forceinline__ double slab_offset(double x, double lo, double L) {
-    double d = x - lo;
+// offset of x to the lower face `lo` of a slab of width W; with a box period L > 0 the positions are the box's own
+// (wrapped into [0, L)) and the offset is the one whose distance to the slab CENTRE is the minimum image (so that "left
+// of the slab" and "right of the slab" stay apart even when the slab is half the box)
+__device__ __forceinline__ double slab_offset(double x, double lo, double W, double L) {
+    double d = x - (lo + 0.5 * W);
     if (L > 0.0) { if (d >= 0.5 * L) d -= L; else if (d < -0.5 * L) d += L; }
-    return d;
+    return d + 0.5 * W;
 }
 // exchange lists of an owned cell at offset xr = slab_offset(x) in a slab of width W (bit q set = member of list q, see
 // k_exchange_count)
@@ -394,6 +395,16 @@ __global__ void k_unsort_xy(const double2 *__restrict__ src, const int64_t *__re
     if (s < n) out[gid[s]] = src[s];
 }
 
+// positions of a periodic box into [0, L): the caller's host loop may leave them outside (pts += ...; update_positions(pts))
+__global__ void k_wrap_box(double2 *__restrict__ xy, int n, double L) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double2 q = xy[i];
+    q.x -= L * floor(q.x / L); if (q.x >= L) q.x = 0.0;
+    q.y -= L * floor(q.y / L); if (q.y >= L) q.y = 0.0;
+    xy[i] = q;
+}
+
 __global__ void k_fill(double *p, int n, double v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 // out[gid[s]] = src[s]   (back to the caller's order)
@@ -532,7 +543,7 @@ constexpr int XCH_TPB = 256;
 __global__ void __launch_bounds__(XCH_TPB) k_exchange_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n,
                                                             double lo, double hi, double halo, double L, int *__restrict__ blk_cnt) {
     const int i = blockIdx.x * XCH_TPB + threadIdx.x;
-    const unsigned m = (i < n) ? xch_lists(slab_offset(xy[i].x, lo, L), owned[i], hi - lo, halo) : 0u;
+    const unsigned m = (i < n) ? xch_lists(slab_offset(xy[i].x, lo, hi - lo, L), owned[i], hi - lo, halo) : 0u;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int c = __syncthreads_count((m >> q) & 1u);
@@ -602,7 +613,7 @@ __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__rest
     unsigned char own = CELL_DEAD;
     unsigned m = 0u;
     double xr = 0.0;
-    if (i < n) { p = xy[i]; own = owned[i]; xr = slab_offset(p.x, lo, L); m = xch_lists(xr, own, hi - lo, halo); }
+    if (i < n) { p = xy[i]; own = owned[i]; xr = slab_offset(p.x, lo, hi - lo, L); m = xch_lists(xr, own, hi - lo, halo); }
     int rank_in_warp[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {

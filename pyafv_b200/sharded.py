@@ -175,8 +175,8 @@ class SlabGeometry:
 
     def offset(self, x):
         """Minimum-image offset of x to the lower face of the slab (what the exchange kernels classify cells by)."""
-        d = np.asarray(x, dtype=np.float64) - self.lo
-        return d - self.L * np.floor(d / self.L + 0.5) if self.world > 1 else d
+        d = np.asarray(x, dtype=np.float64) - (self.lo + 0.5 * self.W)     # to the slab centre: left and right stay apart
+        return (d - self.L * np.floor(d / self.L + 0.5) if self.world > 1 else d) + 0.5 * self.W
 
 
 def halo_capacity(n_owned: int, geo: SlabGeometry) -> int:
