@@ -22,6 +22,11 @@
  *       <- tile_pbc + build + [:N]                     pyafv/_connectutil.py:12-96
  *   afv_set_slab / afv_pack_exchange / afv_finish_exchange / afv_late_step_* / afv_pack_owned (slab sharding)
  *       <- decompose_points / _build_domain / _merge_results   pyafv/parallel_voronoi.py:125-338,351-418,590-633
+ *   afv_cluster_analysis / afv_get_cluster_labels / afv_get_cluster_sizes / afv_components_of_edges
+ *       <- rebuild_connection_matrix / get_cluster_sizes / select_daughter_cluster   pyafv/_connectutil.py:101-172
+ *   afv_get_energy / afv_get_cell_energies / afv_relax
+ *       <- the energy behind the gradient code (finite_voronoi.py:529,746; physical_params.py:160-171) and the
+ *          fixed-dt relaxation loop of examples/relaxation.py:41-45
  */
 #ifndef AFV_B200_H
 #define AFV_B200_H
@@ -122,8 +127,8 @@ int afv_get_diagnostics(AfvHandle h, int64_t out[4]);
 /* when enabled, every stage of build/step is bracketed by CUDA events on the handle's stream */
 int afv_set_profiling(AfvHandle h, int enabled);
 /* accumulated milliseconds and span counts since the last reset, per stage:
- * 0 bin + sort + reorder + bin starts, 1 k_hull, 2 k_ring, 3 k_force (+ update), 4 connections / ring export,
- * 5 k_geometry_slow (queued cells) */
+ * 0 bin + sort + reorder + bin starts, 1 k_nbrs (neighbour lists), 2 k_clip (polygon, ring, measures), 3 k_force
+ * (+ update), 4 connections / ring export, 5 k_geometry_slow (queued cells) */
 #define AFV_N_STAGES 6
 int afv_get_stage_times(AfvHandle h, double ms_out[AFV_N_STAGES], int64_t launches_out[AFV_N_STAGES], int reset);
 /* number of kernel launches issued by this handle since creation */
@@ -142,9 +147,11 @@ int afv_synchronize(AfvHandle h);
  * steps issued since are reported by the next afv_finish_exchange or afv_synchronize, which synchronise anyway.  Not
  * used when afv_step borrows a host noise array. */
 int afv_set_deferred_checks(AfvHandle h, int enabled);
-/* Turn a periodic handle (box_L > 0) into one x-slab of that box: the bin grid covers x in [grid_x0, grid_x1)
- * without wrap (the caller supplies halo cells with x already shifted by +-L where the slab touches the box
- * face), y stays periodic, and afv_step no longer wraps x (cells leaving the slab are migrated by the caller). */
+/* Turn a periodic handle (box_L > 0) into one x-slab of that box: the bin grid covers x in [grid_x0, grid_x1) without
+ * wrap, y stays periodic.  Cells -- owned and halo -- keep the box's own coordinates in [0, L): bins are taken from the
+ * offset to grid_x0 wrapped by L, every displacement is a minimum image, and afv_step wraps x like the single-GPU
+ * run, so that every rank forms a displacement from the same two operands as one GPU would: results do not depend on
+ * the number of slabs, bit for bit.  Cells leaving the slab are migrated by the exchange. */
 int afv_set_slab(AfvHandle h, double grid_x0, double grid_x1);
 /* Replace the device state by (x, y, theta, A0, gid) rows given in DEVICE memory: n_owned owned cells followed
  * by n_halo halo cells (halo cells take part in the geometry but receive no force / update).  rows: (n,5)
@@ -170,8 +177,9 @@ int afv_pack_pair(AfvHandle h, double lo0, double hi0, double shift0, double lo1
 int afv_finish_pair(AfvHandle h, const double *in0_dev, const double *in1_dev, int64_t cap_rows, int is_halo, int remove_packed);
 /* One exchange per step: ownership transfers and halo cells in the same message.  Message = (cap_rows+1, 5): header
  * [n_transfer, n_halo, 0, 0, 0], then the transfer rows, then the halo rows.  afv_pack_exchange selects, for the slab
- * [lo, hi): left message = owned cells with x < lo (transfers) and lo <= x < lo+halo (halo), x + shift_left; right
- * message = x >= hi (transfers) and hi-halo <= x < hi (halo), x + shift_right.  The same pass retires the halo
+ * [lo, hi) and with d = the offset of x to lo (on a slab handle: the minimum image about the slab centre): left
+ * message = owned cells with d < 0 (transfers) and 0 <= d < halo (halo), x + shift_left; right message = d >= hi-lo
+ * (transfers) and hi-lo-halo <= d < hi-lo (halo), x + shift_right (both shifts are 0 for slab handles).  The same pass retires the halo
  * copies of the previous exchange (the next sort drops them; afv_drop_halo is the explicit form) and keeps this rank's
  * transferred cells as halo copies.  afv_finish_exchange (one synchronisation) appends the received rows.
  * Replaces parallel_voronoi.py:125-338 (decompose_points) + :590-633 (_merge_results) for a time loop. */
@@ -204,6 +212,33 @@ int afv_stream_wait(AfvHandle h, void *other_stream);
 /* after afv_build: rows (count,11) of the OWNED cells in device memory:
  * x, y, theta, A0, gid, fx, fy, area, perimeter, arclen, coord_num */
 int afv_pack_owned(AfvHandle h, double *rows_dev_out, int64_t capacity, int64_t *count);
+
+
+/* ---- cluster analysis on the device (the callers of `connections`, pyafv/_connectutil.py:101-172) ------------- */
+/* Connected components of the contact graph of the last build, straight from the rings on the device (no (K,2) list
+ * is built or copied).  Component labels are numbered by ascending smallest cell index, i.e. exactly like
+ * scipy.sparse.csgraph.connected_components numbers them.  Single-GPU handles (afv_set_positions) only. */
+int afv_cluster_analysis(AfvHandle h, int64_t *n_components);
+int afv_get_cluster_labels(AfvHandle h, int64_t *labels_out /* (N,) caller order */);
+int afv_get_cluster_sizes(AfvHandle h, int64_t *sizes_out /* (n_components,) */);
+/* the same for an explicit edge list in host memory (get_cluster_sizes(N, connect)): labels_out (N) and sizes_out (N;
+ * the first *n_components entries are set) may be NULL */
+int afv_components_of_edges(AfvHandle h, int64_t N, const int64_t *pairs_host, int64_t K, int64_t *labels_out, int64_t *sizes_out,
+                            int64_t *n_components);
+
+/* ---- energy and relaxation ------------------------------------------------------------------------------------ */
+/* E = sum_i KA (A_i - A0_i)^2 + KP (P_i - P0)^2 + Lambda L_arc,i of the last build, reduced on the device in a fixed
+ * order (bit-reproducible run to run) */
+int afv_get_energy(AfvHandle h, double *energy_out);
+int afv_get_cell_energies(AfvHandle h, double *out /* (N,) caller order */);
+/* FIRE relaxation (Bitzek et al., PRL 97, 170201) entirely on the device: per iteration build + forces, the three
+ * global sums F.v, |v|^2, |F|^2, the time-step / mixing update and the move, without a host round trip; the host
+ * looks at max|F| every `check_every` iterations.  Stops when max|F| <= f_tol or after max_steps.  dt0: initial time
+ * step, dt_max: largest one.  out[0] iterations done, [1] energy, [2] max|F|, [3] last dt, [4] 1 if converged.
+ * energies_out (may be NULL): energy at every check, at most n_energies entries; *n_checks = number written.
+ * Single-GPU handles only; replaces the fixed-dt loop of examples/relaxation.py:41-45. */
+int afv_relax(AfvHandle h, double dt0, double dt_max, double f_tol, int max_steps, int check_every, double out[5],
+              double *energies_out, int n_energies, int *n_checks);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 SRC = PKG / "csrc" / "afv_api.cu"
-DEPS = [SRC, PKG / "csrc" / "afv_kernels.cuh", PKG / "csrc" / "afv_device.cuh", PKG / "csrc" / "afv_shard.inc", PKG / "csrc" / "afv_geometry.cuh",
+DEPS = [SRC, *sorted((PKG / "csrc").glob("*.cuh")), *sorted((PKG / "csrc").glob("*.inc")),
         PKG.parent / "include" / "afv_b200.h"]
 LIB = PKG / "libafv_b200.so"
 

@@ -22,6 +22,8 @@ SYMBOLS = [
     "afv_get_diagnostics", "afv_set_profiling", "afv_get_stage_times", "afv_launch_count", "afv_host_alloc",
     "afv_host_free", "afv_measure_fp64_peak", "afv_device_ptr", "afv_stream", "afv_synchronize", "afv_set_deferred_checks",
     "afv_set_slab", "afv_set_cells_device", "afv_extract_slab", "afv_drop_halo", "afv_append_cells", "afv_num_owned", "afv_pack_owned", "afv_pack_pair", "afv_finish_pair", "afv_pack_exchange", "afv_finish_exchange", "afv_late_step_begin", "afv_late_finish", "afv_late_step_end", "afv_stream_wait", "afv_get_exchange_stats",
+    "afv_cluster_analysis", "afv_get_cluster_labels", "afv_get_cluster_sizes", "afv_components_of_edges",
+    "afv_get_energy", "afv_get_cell_energies", "afv_relax",
 ]
 
 
@@ -100,6 +102,13 @@ def load() -> C.CDLL:
         "afv_stream_wait": (C.c_int, [H, P]),
         "afv_get_exchange_stats": (C.c_int, [H, P]),
         "afv_pack_owned": (C.c_int, [H, P, I64, C.POINTER(I64)]),
+        "afv_cluster_analysis": (C.c_int, [H, C.POINTER(I64)]),
+        "afv_get_cluster_labels": (C.c_int, [H, P]),
+        "afv_get_cluster_sizes": (C.c_int, [H, P]),
+        "afv_components_of_edges": (C.c_int, [H, I64, P, I64, P, P, C.POINTER(I64)]),
+        "afv_get_energy": (C.c_int, [H, C.POINTER(D)]),
+        "afv_get_cell_energies": (C.c_int, [H, P]),
+        "afv_relax": (C.c_int, [H, D, D, D, C.c_int, C.c_int, P, P, C.c_int, C.POINTER(C.c_int)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

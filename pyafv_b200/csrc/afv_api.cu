@@ -88,6 +88,9 @@ struct AfvContext {
     int h_flags[4] = {0, 0, 0, 0};
     // scratch
     DevBuf scratch_a, scratch_b, noise_buf, conn_buf, ring_types, ring_xy, ring_off;
+    DevBuf cc_parent, cc_flag, cc_rank, cc_labels, cc_sizes, cc_tmp, cc_edges;   // cluster analysis (afv_cluster.inc)
+    int64_t n_clusters = 0;
+    DevBuf sums_partial, fire_state, fire_vel;   // energy / FIRE relaxation (afv_relax.inc)
     int *cnt = nullptr, *off = nullptr;  // per-cell counts / offsets (cap + 1)
     int64_t n_conn = -1, n_ring = -1;
     bool built = false;
@@ -569,7 +572,9 @@ void afv_destroy(AfvHandle h) {
     cudaFree(h->pair_cnt); cudaFree(h->pair_dev); cudaFreeHost(h->pair_host);
     for (cudaEvent_t e : {h->ev_sorted, h->ev_late, h->ev_force, h->ev_pack, h->ev_interior}) if (e) cudaEventDestroy(e);
     for (DevBuf *b : {&h->late_keys, &h->late_keys_sorted, &h->late_perm, &h->late_tmp}) cudaFree(b->p);
-    for (DevBuf *b : {&h->scratch_a, &h->scratch_b, &h->noise_buf, &h->conn_buf, &h->ring_types, &h->ring_xy, &h->ring_off}) cudaFree(b->p);
+    for (DevBuf *b : {&h->scratch_a, &h->scratch_b, &h->noise_buf, &h->conn_buf, &h->ring_types, &h->ring_xy, &h->ring_off,
+                      &h->cc_parent, &h->cc_flag, &h->cc_rank, &h->cc_labels, &h->cc_sizes, &h->cc_tmp, &h->cc_edges,
+                      &h->sums_partial, &h->fire_state, &h->fire_vel}) cudaFree(b->p);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -652,7 +657,7 @@ int afv_set_theta(AfvHandle h, const double *theta_host, int64_t N) {
 
 int afv_build(AfvHandle h, unsigned flags) {
     CHECK_H(h);
-    h->n_conn = -1; h->n_ring = -1;
+    h->n_conn = -1; h->n_ring = -1; h->n_clusters = 0;
     if (h->n == h->n_dead) { h->n = h->n_dead = 0; }   // only stale halo copies left
     h->late_mode = false;
     if (h->n == 0) { h->built = true; h->n_conn = 0; h->n_ring = 0; return AFV_OK; }
@@ -728,7 +733,7 @@ int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t s
     }
     if (!deferred && (rc = check_flags(h))) return rc;   // also synchronises: noise_host is borrowed for the call only
     h->built = true;
-    h->n_conn = -1; h->n_ring = -1;
+    h->n_conn = -1; h->n_ring = -1; h->n_clusters = 0;
     return AFV_OK;
 }
 
@@ -921,5 +926,11 @@ int afv_set_deferred_checks(AfvHandle h, int enabled) {
 
 // ---- slab sharding primitives ----
 #include "afv_shard.inc"
+
+// ---- cluster analysis on the device ----
+#include "afv_cluster.inc"
+
+// ---- energy and FIRE relaxation on the device ----
+#include "afv_relax.inc"
 
 }  // extern "C"

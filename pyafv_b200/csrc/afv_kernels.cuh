@@ -496,6 +496,9 @@ __global__ void k_ring_emit(RingView rv, const int64_t *__restrict__ gid, const 
     }
 }
 
+#include "afv_cluster.cuh"
+#include "afv_relax.cuh"
+
 // ------------------------------------------------------------------------------------------------------
 // slab sharding helpers.  Rows are (n,5) float64: x, y, theta, A0, gid
 // ------------------------------------------------------------------------------------------------------

@@ -190,6 +190,52 @@ class FiniteVoronoiSimulator:
             self._pts_stale = True
 
     # ------------------------------------------------------------------------------------------------
+    def energy(self) -> float:
+        r"""Total energy :math:`E = \sum_i K_A (A_i - A_{0,i})^2 + K_P (P_i - P_0)^2 + \Lambda L_{arc,i}` of the last
+        ``build()`` / ``step()`` geometry, reduced on the device in a fixed order.  This is the energy whose gradient the
+        reference's force code implements (``finite_voronoi.py:529,746``); the reference never evaluates it."""
+        e = C.c_double()
+        self._h.call("afv_get_energy", C.byref(e))
+        return float(e.value)
+
+    def cell_energies(self) -> np.ndarray:
+        """(N,) per-cell energies of the last build (they sum to :meth:`energy`)."""
+        return self._h.fetch("afv_get_cell_energies", (self.N,))
+
+    def relax(self, max_steps: int = 2000, *, dt: float = 0.01, dt_max: float | None = None, f_tol: float = 1e-6,
+              check_every: int = 20) -> dict[str, object]:
+        """Energy minimisation by FIRE (Bitzek et al., PRL 97, 170201) on the device: replaces the fixed-``dt`` Euler loop
+        of ``examples/relaxation.py:41-45``.  Build, forces, the global sums, the adaptive time step and the move of one
+        iteration never leave the GPU; the host looks at ``max|F|`` every ``check_every`` iterations.
+
+        Returns ``steps``, ``energy``, ``fmax``, ``dt`` (last time step), ``converged`` and ``energies`` (the energy at every
+        check).  The geometry left on the device is that of the final positions (``forces`` etc. are current)."""
+        if max_steps < 0:
+            raise ValueError("max_steps must be non-negative")
+        dt_max = 10.0 * dt if dt_max is None else float(dt_max)
+        n_e = max_steps // max(check_every, 1) + 3
+        energies = np.zeros(n_e)
+        out = np.zeros(5)
+        nchk = C.c_int()
+        self._h.call("afv_relax", float(dt), dt_max, float(f_tol), int(max_steps), int(check_every), out.ctypes.data,
+                     energies.ctypes.data, int(n_e), C.byref(nchk))
+        if self.N:
+            self._pts_stale = True
+        return dict(steps=int(out[0]), energy=float(out[1]), fmax=float(out[2]), dt=float(out[3]), converged=bool(out[4]),
+                    energies=energies[: nchk.value].copy())
+
+    def cluster_sizes(self) -> tuple[np.ndarray, int, np.ndarray]:
+        """Connected components of the contact graph of the last build, computed on the device from the rings (no
+        ``connections`` array is built or copied).  Same return value as the reference's
+        ``get_cluster_sizes(N, connections)`` (``_connectutil.py:154-172``): ``(cluster_sizes, n_components, labels)``,
+        labels numbered like ``scipy.sparse.csgraph.connected_components`` numbers them."""
+        nc = C.c_int64()
+        self._h.call("afv_cluster_analysis", C.byref(nc))
+        labels = self._h.fetch("afv_get_cluster_labels", (self.N,), dtype=np.int64)
+        sizes = self._h.fetch("afv_get_cluster_sizes", (nc.value,), dtype=np.int64)
+        return sizes, int(nc.value), labels
+
+    # ------------------------------------------------------------------------------------------------
     def update_positions(self, pts: np.ndarray, A0: float | np.ndarray | None = None) -> None:
         """New cell centres (uploaded immediately: the caller may mutate its array afterwards)."""
         pts = np.asarray(pts, dtype=float)

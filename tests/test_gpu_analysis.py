@@ -1,0 +1,174 @@
+"""GPU: the callers either side of the hot path that SURVEY 8(f) ranks next -- cluster analysis of the contact graph on
+the device (reference: scipy.sparse.csgraph on build()['connections'], pyafv/_connectutil.py:101-172) and the energy /
+FIRE relaxation driver (reference: the fixed-dt loop of examples/relaxation.py:41-45; E is implicit in
+finite_voronoi.py:529,746)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, phys_from
+
+pytestmark = pytest.mark.gpu
+
+
+def _scipy_components(N, conn):
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    i, j = conn[:, 0], conn[:, 1]
+    m = csr_matrix((np.ones(2 * len(conn), dtype=bool), (np.concatenate([i, j]), np.concatenate([j, i]))), shape=(N, N))
+    nc, labels = connected_components(m, directed=False)
+    return nc, labels
+
+
+@pytest.mark.parametrize("case", ["rand_sparse", "pbc_sparse", "rand_dense", "n2_apart", "n1"])
+def test_cluster_analysis_matches_scipy_on_reference_goldens(case):
+    """Components of the REFERENCE's connections (golden) by scipy == device components of our rings == the module-level
+    get_cluster_sizes(N, connections): identical labels, sizes and counts."""
+    import pyafv_b200 as afv
+    g = load_golden(case)
+    pts = g["pts"]
+    N = len(pts)
+    L = float(g["L"]) if "L" in g and float(g["L"]) > 0 else None
+    sim = afv.FiniteVoronoiSimulator(pts, phys_from(g), periodic=L)
+    if "A0" in g:
+        sim.update_preferred_areas(g["A0"])
+    d = sim.build()
+    nc_ref, lab_ref = _scipy_components(N, g["connections"].astype(np.int64).reshape(-1, 2))
+    sizes, nc, labels = sim.cluster_sizes()
+    assert nc == nc_ref and np.array_equal(labels, lab_ref) and np.array_equal(sizes, np.bincount(lab_ref))
+    sizes2, nc2, labels2 = afv.get_cluster_sizes(N, d["connections"])
+    assert nc2 == nc_ref and np.array_equal(labels2, lab_ref) and np.array_equal(sizes2, sizes)
+    assert sizes.dtype == np.int64 and labels.dtype == np.int64 and labels.shape == (N,)
+    sim.close()
+
+
+def test_cluster_analysis_fragmenting_regime_1e6():
+    """BASELINE config[3], fragmenting regime: N = 10^6 at rho l^2 = 0.1 (28 % isolated cells, thousands of clusters)."""
+    import pyafv_b200 as afv
+    N = 1_000_000
+    L = float(np.sqrt(N / 0.1))
+    pts = np.random.default_rng(5).random((N, 2)) * L
+    sim = afv.FiniteVoronoiSimulator(pts, afv.PhysicalParams(), periodic=L)
+    d = sim.build(rings=False)
+    sizes, nc, labels = sim.cluster_sizes()
+    nc_ref, lab_ref = _scipy_components(N, d["connections"])
+    assert nc == nc_ref and np.array_equal(labels, lab_ref)
+    assert np.array_equal(sizes, np.bincount(lab_ref)) and sizes.sum() == N
+    assert (sizes == 1).sum() == (d["coord_nums"] == 0).sum()          # isolated cells are the singleton clusters
+    # a percolating dense tissue is one cluster
+    sim.update_positions(np.random.default_rng(6).random((200_000, 2)) * np.sqrt(200_000))
+    sim2 = afv.FiniteVoronoiSimulator(np.random.default_rng(6).random((200_000, 2)) * np.sqrt(200_000), afv.PhysicalParams(),
+                                      periodic=float(np.sqrt(200_000)))
+    sim2.build(connect=False, rings=False)
+    s2, n2, _ = sim2.cluster_sizes()
+    assert n2 == 1 and s2[0] == 200_000
+    sim.close(); sim2.close()
+
+
+def test_connectivity_helpers_follow_the_reference():
+    import pyafv_b200 as afv
+    conn = np.array([[0, 1], [1, 2], [4, 5], [7, 6], [6, 5]], dtype=np.int64)
+    m = afv.rebuild_connection_matrix(9, conn)
+    assert m.shape == (9, 9) and m.dtype == bool and m.nnz == 10 and (m != m.T).nnz == 0
+    assert np.array_equal(m.getnnz(axis=1), [1, 2, 1, 0, 1, 2, 2, 1, 0])
+    sizes, nc, labels = afv.get_cluster_sizes(9, conn)
+    assert nc == 4 and np.array_equal(labels, [0, 0, 0, 1, 2, 2, 2, 2, 3]) and np.array_equal(sizes, [3, 1, 4, 1])
+    np.random.seed(3)
+    cells, n_sub, local = afv.select_daughter_cluster(9, conn)
+    assert n_sub == len(cells) and set(map(tuple, cells[local].tolist())) <= set(map(tuple, conn.tolist()))
+    assert len(local) == {3: 2, 1: 0, 4: 3}[n_sub]
+    full = np.array([[0, 1], [1, 2]], dtype=np.int64)
+    none, n_all, same = afv.select_daughter_cluster(3, full)            # connected graph: unchanged, like the reference
+    assert none is None and n_all == 3 and same is full
+    with pytest.raises(Exception):
+        afv.get_cluster_sizes(3, np.array([[0, 5]]))
+
+
+def test_energy_is_the_sum_of_its_definition_and_forces_are_its_gradient():
+    """E = sum KA (A - A0)^2 + KP (P - P0)^2 + Lambda L_arc.  With delta = 0 the reference's Jacobian is
+    the exact one, so F = -dE/dr: central differences on the reference's own 100-cell fixture agree to 1e-6."""
+    import pyafv_b200 as afv
+    g = load_golden("varyA0_d0")
+    phys = phys_from(g)
+    assert phys.delta == 0.0
+    pts = g["pts"].copy()
+    sim = afv.FiniteVoronoiSimulator(pts, phys)
+    sim.update_preferred_areas(g["A0"])
+    d = sim.build(connect=False, rings=False)
+    E = sim.energy()
+    e_def = phys.KA * (d["areas"] - g["A0"]) ** 2 + phys.KP * (d["perimeters"] - phys.P0) ** 2 + phys.Lambda * d["arclens"]
+    assert abs(E - e_def.sum()) <= 1e-12 * abs(E)
+    assert np.abs(sim.cell_energies() - e_def).max() <= 1e-12 * e_def.max()
+    assert sim.energy() == E                                        # fixed reduction order: bit-reproducible
+    F = d["forces"]
+    h = 1e-5
+    for k in (0, 17, 42, 63, 99):
+        for ax in (0, 1):
+            q = pts.copy(); q[k, ax] += h
+            sim.update_positions(q, g["A0"]); sim.build(connect=False, rings=False); ep = sim.energy()
+            q[k, ax] -= 2 * h
+            sim.update_positions(q, g["A0"]); sim.build(connect=False, rings=False); em = sim.energy()
+            assert abs(-(ep - em) / (2 * h) - F[k, ax]) <= 1e-6 * max(1.0, np.abs(F).max()), (k, ax)
+    sim.close()
+
+
+def test_fire_relaxation_decreases_the_energy_and_ends_on_the_oracle_forces():
+    import pyafv_b200 as afv
+    from afv_oracle import oracle_build
+    N = 4000
+    L = float(np.sqrt(N / 0.6))
+    rng = np.random.default_rng(8)
+    pts = rng.random((N, 2)) * L
+    A0 = np.pi * (1 + 0.1 * rng.standard_normal(N))
+    phys = afv.PhysicalParams()
+    sim = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
+    sim.update_preferred_areas(A0)
+    sim.step(0.005, 1.0, 0.0, 0.0, n_steps=100)                    # off the violent random start (|F| dt ~ 2 l there)
+    start = sim.pts.copy()
+    sim.build(connect=False, rings=False)
+    e0 = sim.energy()
+    res = sim.relax(1500, dt=0.01, f_tol=1e-7, check_every=25)
+    en = res["energies"]
+    assert len(en) >= 3 and en[0] == e0
+    assert np.all(np.diff(en) <= 1e-9 * abs(e0)), np.diff(en).max()   # the energy never goes up from one check to the next
+    assert res["energy"] < e0 and res["steps"] <= 1500
+    # the state left on the device is consistent: forces of the final positions == the oracle's
+    d = sim.build(connect=False, rings=False)
+    assert abs(sim.energy() - res["energy"]) <= 1e-12 * abs(e0)
+    o = oracle_build(sim.pts, A0=A0, periodic=L)
+    for k in ("forces", "areas", "perimeters", "arclens"):
+        assert np.abs(d[k] - o[k]).max() <= 1e-9 * max(1.0, np.abs(o[k]).max()), k
+    assert abs(np.abs(d["forces"]).max() - res["fmax"] * 1.0) <= max(1e-9, 0.5 * res["fmax"])   # fmax is the Euclidean max |F|
+    # the reference's loop (fixed-dt Euler, examples/relaxation.py:41-45) with the same number of force evaluations is higher
+    sim.update_positions(start, A0)
+    sim.step(0.01, 1.0, 0.0, 0.0, n_steps=res["steps"])
+    sim.build(connect=False, rings=False)
+    assert res["energy"] <= sim.energy() + 1e-9 * abs(e0)
+    sim.close()
+
+
+def test_relax_argument_errors_and_empty_system():
+    import pyafv_b200 as afv
+    from pyafv_b200._lib import AfvError
+    sim = afv.FiniteVoronoiSimulator(np.zeros((0, 2)), afv.PhysicalParams())
+    assert sim.relax(10)["converged"]
+    sim.build()
+    assert sim.cluster_sizes()[1] == 0 and sim.energy() == 0.0
+    sim.close()
+    sim = afv.FiniteVoronoiSimulator(np.array([[0.0, 0.0], [1.2, 0.0]]), afv.PhysicalParams())
+    with pytest.raises(AfvError):
+        sim.relax(10, dt=-1.0)
+    with pytest.raises(AfvError):
+        sim.energy()                                                # no build yet
+    r = sim.relax(2000, dt=0.01, f_tol=1e-9)                         # a doublet relaxes to the minimum of its 1-d energy
+    assert r["converged"] and r["fmax"] <= 1e-9
+    p = sim.pts
+    d = np.linalg.norm(p[0] - p[1])
+    mid, u = 0.5 * (p[0] + p[1]), (p[1] - p[0]) / d
+    e_min = sim.energy()
+    for dd in (d - 1e-3, d + 1e-3):
+        sim.update_positions(np.array([mid - 0.5 * dd * u, mid + 0.5 * dd * u]))
+        sim.build()
+        assert sim.energy() > e_min
+    sim.close()
