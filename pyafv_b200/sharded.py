@@ -226,26 +226,33 @@ class SlabShardedSimulator:
             self._h.call("afv_set_deferred_checks", 1)    # one host synchronisation per step (at the exchange), not two
         self.store = GpuCellStore(self._h, self.device)
         self.comm = comm if comm is not None else (TorchDistComm(rank, world) if world > 1 else None)
+        self._step_index = 0
+        self.overlap = bool(overlap) and world > 1
+        self.overlapped_steps = 0         # steps taken in the overlapped form so far
+        self._xs = None
+        self._inbox = None
+        self.set_cells(pts, theta, A0, gids)
+        if self.overlap:
+            # high priority: its blocks (pack, append, the face pass) are dispatched ahead of the pending blocks of the interior pass
+            self._xs = exchange_stream if exchange_stream is not None else torch.cuda.Stream(self.device, priority=-1)
+
+    def set_cells(self, pts, theta=None, A0=None, gids=None) -> None:
+        """Replace the cells of this rank (all inside its slab): what the constructor does with its arguments."""
         pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
         n = pts.shape[0]
         rows = np.empty((n, ROW))
         rows[:, 0:2] = pts
         rows[:, 2] = 0.0 if theta is None else np.asarray(theta, dtype=np.float64)
-        rows[:, 3] = phys.A0 if A0 is None else np.asarray(A0, dtype=np.float64)
-        rows[:, 4] = (rank * float(2**40) + np.arange(n)) if gids is None else np.asarray(gids, dtype=np.float64)
-        if n and world > 1 and ((pts[:, 0] < self.geo.lo).any() or (pts[:, 0] >= self.geo.hi).any()):
+        rows[:, 3] = self.phys.A0 if A0 is None else np.asarray(A0, dtype=np.float64)
+        rows[:, 4] = (self.rank * float(2**40) + np.arange(n)) if gids is None else np.asarray(gids, dtype=np.float64)
+        if n and self.world > 1 and ((pts[:, 0] < self.geo.lo).any() or (pts[:, 0] >= self.geo.hi).any()):
             raise ValueError("initial cells must lie inside the rank's slab")
+        if self._inbox is not None and self._xs is not None:   # a pending overlapped exchange belongs to the old cells
+            self.store.stream_wait(self._xs.cuda_stream)
         self.store.set_cells(torch.from_numpy(rows).to(self.device), n)
-        self._step_index = 0
         self._cap = None
         self._halo_fresh = False          # the halo copies on the device belong to the current positions
-        self.overlap = bool(overlap) and world > 1
         self._inbox = None                # overlapped form: messages packed for the current positions, on their way, not yet appended
-        self.overlapped_steps = 0         # steps taken in the overlapped form so far
-        self._xs = None
-        if self.overlap:
-            # high priority: its blocks (pack, append, the face pass) are dispatched ahead of the pending blocks of the interior pass
-            self._xs = exchange_stream if exchange_stream is not None else torch.cuda.Stream(self.device, priority=-1)
 
     @property
     def n_owned(self) -> int:
@@ -253,6 +260,15 @@ class SlabShardedSimulator:
 
     def close(self) -> None:
         self._h.close()
+
+    def connections(self) -> np.ndarray:
+        """(K,2) int64 contact pairs (global ids, i < j) found by this rank in its last ``compute_build(connect=True)``: every
+        contact of the system is reported by exactly one rank (the owner of the cell with the smaller id)."""
+        K = C.c_int64()
+        self._h.call("afv_get_num_connections", C.byref(K))
+        conn = np.zeros((K.value, 2), dtype=np.int64)
+        self._h.call("afv_get_connections", conn.ctypes.data)
+        return conn
 
     # -- phases, exposed separately so that a loopback driver can interleave the ranks of one process --------
     def _caps(self):
@@ -313,9 +329,9 @@ class SlabShardedSimulator:
         # retires them (pack_exchange), which costs nothing extra; drop_halo() is the explicit form.
         return self.store.results() if want_results else None
 
-    def compute_build(self) -> torch.Tensor:
+    def compute_build(self, connect: bool = False) -> torch.Tensor:
         from . import _lib
-        self._h.call("afv_build", _lib.BUILD_FORCES)
+        self._h.call("afv_build", _lib.BUILD_FORCES | (_lib.BUILD_CONNECT if connect else 0))
         return self.store.results().clone()
 
     # -- the per-rank drivers (one process per GPU) ---------------------------------------------------------
@@ -389,26 +405,53 @@ def results_dict(res: torch.Tensor) -> dict[str, np.ndarray]:
 # all ranks inside one process (tests, and machines with fewer GPUs than slabs)
 # ------------------------------------------------------------------------------------------------------
 class LoopbackShardedSimulator:
-    """``world`` slabs driven from one process on one device; same phases as the distributed run."""
+    """``world`` slabs driven from ONE process; same phases as the one-process-per-GPU run.
 
-    def __init__(self, pts, theta, phys, L: float, world: int, *, device: int = 0, A0=None, halo_width=None, overlap: bool = False):
+    ``devices`` (default ``[device]``): CUDA ordinals the slabs are dealt to round-robin.  With one device all slabs share
+    it (tests, machines with fewer GPUs than slabs); with several, every slab runs on its own GPU -- the kernels of the
+    ranks are issued back to back and run concurrently, the messages of the exchange are copied device to device.  This
+    is what :class:`pyafv_b200.ParallelFiniteVoronoiSimulator` drives.  (The late-cell overlap needs all slabs on one
+    device here; the one-process-per-GPU form has no such limit.)"""
+
+    def __init__(self, pts, theta, phys, L: float, world: int, *, device: int = 0, A0=None, halo_width=None, overlap: bool = False,
+                 devices=None):
+        self.devices = [int(d) for d in (devices if devices else [device])]
+        self.world, self.L, self.phys = world, float(L), phys
+        self.overlap = bool(overlap) and world > 1 and len(set(self.devices)) == 1
+        self._inbox = None                # overlapped form: messages packed for the current positions, on their way, not yet appended
+        dev0 = torch.device("cuda", self.devices[0])
+        xs = torch.cuda.Stream(dev0, priority=-1) if self.overlap else None   # one exchange stream (single device)
+        self.ranks = []
         pts = np.asarray(pts, dtype=np.float64)
+        parts = self._deal(pts, theta, A0)
+        for rk in range(world):
+            dv = self.devices[rk % len(self.devices)]
+            stream = torch.cuda.current_stream(torch.device("cuda", dv)).cuda_stream   # one stream per device, shared by its ranks
+            p, th, a0, g = parts[rk]
+            self.ranks.append(SlabShardedSimulator(p, th, phys, L, rank=rk, world=world, device=dv, gids=g, A0=a0, halo_width=halo_width,
+                                                   comm=False, stream=stream, overlap=self.overlap, exchange_stream=xs))
+        self.N = pts.shape[0]
+
+    def _deal(self, pts, theta, A0):
+        """(pts, theta, A0, gids) of every slab: ownership by x (right-sided, the last slab takes the upper face)."""
         N = pts.shape[0]
         theta = np.zeros(N) if theta is None else np.asarray(theta, dtype=np.float64)
-        A0 = np.full(N, phys.A0) if A0 is None else np.broadcast_to(np.asarray(A0, dtype=np.float64), (N,))
-        W = L / world
-        owner = np.minimum((pts[:, 0] // W).astype(int), world - 1)
-        self.ranks = []
-        stream = torch.cuda.current_stream(torch.device("cuda", device)).cuda_stream   # one stream for every rank
-        self.overlap = bool(overlap) and world > 1
-        self._inbox = None                # overlapped form: messages packed for the current positions, on their way, not yet appended
-        xs = torch.cuda.Stream(torch.device("cuda", device), priority=-1) if self.overlap else None   # and one exchange stream
-        for rk in range(world):
-            m = owner == rk
-            self.ranks.append(SlabShardedSimulator(pts[m], theta[m], phys, L, rank=rk, world=world, device=device,
-                                                   gids=np.flatnonzero(m), A0=A0[m], halo_width=halo_width, comm=False, stream=stream,
-                                                   overlap=self.overlap, exchange_stream=xs))
-        self.world, self.N = world, N
+        A0 = np.full(N, self.phys.A0) if A0 is None else np.broadcast_to(np.asarray(A0, dtype=np.float64), (N,))
+        W = self.L / self.world
+        faces = np.arange(1, self.world) * W                                # the very numbers SlabGeometry uses for lo / hi
+        owner = np.searchsorted(faces, pts[:, 0], side="right") if N else np.zeros(0, dtype=int)
+        return [(pts[owner == rk], theta[owner == rk], A0[owner == rk], np.flatnonzero(owner == rk)) for rk in range(self.world)]
+
+    def set_cells(self, pts, theta=None, A0=None) -> None:
+        """New positions (and angles / preferred areas) for the whole system: cells are dealt to the slabs again."""
+        pts = np.asarray(pts, dtype=np.float64)
+        for sim, (p, th, a0, g) in zip(self.ranks, self._deal(pts, theta, A0)):
+            sim.set_cells(p, th, a0, g)
+        self.N = pts.shape[0]
+        self._inbox = None
+
+    def _move(self, t: torch.Tensor, sim) -> torch.Tensor:
+        return t if t.device == sim.device else t.to(sim.device, non_blocking=True)
 
     def _refresh_halo(self) -> None:
         if self.world == 1 or all(s._halo_fresh for s in self.ranks):
@@ -418,7 +461,7 @@ class LoopbackShardedSimulator:
                 sim._refresh_halo()
         else:
             for sim, inbox in zip(self.ranks, loopback_exchange([s.exchange_out() for s in self.ranks])):
-                sim.exchange_in(*inbox)
+                sim.exchange_in(self._move(inbox[0], sim), self._move(inbox[1], sim))
 
     def step(self, dt, mu=1.0, v0=0.0, Dr=0.0, *, seed=0, n_steps=1) -> None:
         for _ in range(n_steps):
@@ -440,15 +483,20 @@ class LoopbackShardedSimulator:
             for sim, inbox in zip(self.ranks, loopback_exchange(msgs)):
                 sim._inbox = inbox
 
-    def build(self) -> dict[str, np.ndarray]:
-        """Merged dict in global cell order (the reference's ``_merge_results``)."""
+    def build(self, connect: bool = False) -> dict[str, np.ndarray]:
+        """Merged dict in global cell order (the reference's ``_merge_results``, ``parallel_voronoi.py:590-633``); with
+        ``connect`` also ``connections``: the union of the per-rank contact lists, rows sorted."""
         self._refresh_halo()
-        parts = [results_dict(sim.compute_build()) for sim in self.ranks]
+        res = [sim.compute_build(connect) for sim in self.ranks]             # issued on every device before anything is read back
+        parts = [results_dict(r) for r in res]
         out = {}
         gids = np.concatenate([p["gids"] for p in parts])
         order = np.argsort(gids)
         for k in parts[0]:
             out[k] = np.concatenate([p[k] for p in parts])[order]
+        if connect:
+            conn = np.concatenate([sim.connections() for sim in self.ranks])
+            out["connections"] = conn[np.lexsort((conn[:, 1], conn[:, 0]))] if len(conn) else conn.reshape(0, 2)
         return out
 
     def close(self) -> None:

@@ -105,3 +105,42 @@ def test_parallel_simulator_argument_validation():
         P(np.zeros((3, 2)), afv.PhysicalParams(), grid_shape=(0, 2))
     with pytest.raises(ValueError, match="decomposition_method"):
         P(np.zeros((3, 2)), afv.PhysicalParams(), decomposition_method="fancy")
+
+
+# ---- decompose_points / DomainDecomposition: the reference's own unit tests (tests/test_parallel.py:13-109) ----
+def test_decompose_points_tracks_owned_and_local_ids():
+    pts = np.array([[0.0, 0.0], [0.5, 0.0], [1.0, 0.0], [0.0, 0.5], [0.5, 0.5], [1.0, 1.0]])
+    domains = afv.decompose_points(pts, grid_shape=(2, 2), halo_width=0.1, domain_bounds=((0.0, 1.0), (0.0, 1.0)))
+    owned = np.concatenate([d.local_global_ids[d.owned_local_ids] for d in domains])
+    assert len(domains) == 4 and np.array_equal(np.sort(owned), np.arange(len(pts)))
+    for d in domains:
+        assert np.array_equal(d.local_pts, pts[d.local_global_ids])
+    # right-sided binning with the outermost boundary clipped: (0.5, 0) belongs to the box on its right, (1, 1) to the last box
+    assert [sorted(d.local_global_ids[d.owned_local_ids].tolist()) for d in domains] == [[0], [1, 2], [3], [4, 5]]
+    assert domains[1].halo_x_range == (0.4, 1.1) and domains[2].y_range == (0.5, 1.0) and (domains[3].grid_ix, domains[3].grid_iy) == (1, 1)
+
+
+def test_decompose_points_methods_match_and_halos_are_inclusive():
+    rng = np.random.default_rng(12)
+    pts = rng.random((100, 2)) * np.array([8.0, 5.0])
+    pts[:6] = np.array([[0.0, 0.0], [4.0, 0.0], [8.0, 0.0], [0.0, 5.0], [4.0, 5.0], [8.0, 5.0]])
+    kw = dict(grid_shape=(4, 3), halo_width=0.4, domain_bounds=((0.0, 8.0), (0.0, 5.0)))
+    dense, sx, binned = (afv.decompose_points(pts, method=m, **kw) for m in ("dense", "sorted_x", "binned"))
+    for a, b, c in zip(dense, sx, binned):
+        for d in (b, c):
+            assert np.array_equal(d.local_global_ids, a.local_global_ids) and np.array_equal(d.owned_local_ids, a.owned_local_ids)
+    for d in dense:      # brute force: every point inside the halo box, edges included
+        (x0, x1), (y0, y1) = d.halo_x_range, d.halo_y_range
+        want = np.flatnonzero((pts[:, 0] >= x0) & (pts[:, 0] <= x1) & (pts[:, 1] >= y0) & (pts[:, 1] <= y1))
+        assert np.array_equal(d.local_global_ids, want)
+    with pytest.raises(ValueError):
+        afv.decompose_points(pts, method="fancy")
+    with pytest.raises(ValueError):
+        afv.decompose_points(pts + 10.0, **kw)               # outside domain_bounds
+
+
+def test_decompose_points_one_domain_allows_zero_span_axes():
+    for pts in (np.array([[1.0, 2.0]]), np.array([[0.0, 3.0], [1.0, 3.0]]), np.array([[4.0, 0.0], [4.0, 1.0]])):
+        (d,) = afv.decompose_points(pts, grid_shape=(1, 1), halo_width=0.5)
+        assert np.array_equal(d.local_global_ids, np.arange(len(pts))) and np.array_equal(d.owned_local_ids, np.arange(len(pts)))
+        assert np.array_equal(d.local_pts, pts) and d.halo_x_range == (pts[:, 0].min() - 0.5, pts[:, 0].max() + 0.5)
