@@ -61,7 +61,8 @@ struct AfvContext {
     int cur = 0;
     // cell list
     unsigned *keys = nullptr, *keys_sorted = nullptr;
-    int *iota = nullptr, *perm = nullptr, *bin_start = nullptr;
+    int *iota = nullptr, *perm = nullptr, *bin_start = nullptr, *bin_cnt = nullptr;
+    int *slot_of_gid = nullptr;     // where the caller's cell gid sits in the sorted order (handles filled by afv_set_positions)
     int nbins_cap = 0, key_bits = 0;
     GridDesc *d_grid = nullptr;
     double *bbox_part = nullptr;
@@ -154,6 +155,7 @@ void free_all(AfvHandle h) {
         h->xy[k] = nullptr; h->th[k] = h->a0[k] = nullptr; h->gid[k] = nullptr; h->owned[k] = nullptr;
     }
     cudaFree(h->keys); cudaFree(h->keys_sorted); cudaFree(h->iota); cudaFree(h->perm); cudaFree(h->bin_start);
+    cudaFree(h->bin_cnt); h->bin_cnt = nullptr; cudaFree(h->slot_of_gid); h->slot_of_gid = nullptr;
     cudaFree(h->cub_tmp); cudaFree(h->fx); cudaFree(h->fy); cudaFree(h->area); cudaFree(h->perim); cudaFree(h->arcl);
     cudaFree(h->coord); cudaFree(h->ring_len); cudaFree(h->cnt); cudaFree(h->off);
     cudaFree(h->ring_h); h->ring_h = nullptr; cudaFree(h->ring_nbr); h->ring_nbr = nullptr;
@@ -211,6 +213,8 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     if ((rc = dev_alloc(h, &h->iota, cap))) return rc;
     if ((rc = dev_alloc(h, &h->perm, cap))) return rc;
     if ((rc = dev_alloc(h, &h->bin_start, (size_t)h->nbins_cap + 2))) return rc;
+    if ((rc = dev_alloc(h, &h->bin_cnt, (size_t)h->nbins_cap + 2))) return rc;
+    if ((rc = dev_alloc(h, &h->slot_of_gid, cap))) return rc;
     if ((rc = dev_alloc(h, &h->bin_start_late, (size_t)h->nbins_cap + 2))) return rc;
     if ((rc = dev_alloc(h, &h->fx, cap))) return rc;
     if ((rc = dev_alloc(h, &h->fy, cap))) return rc;
@@ -234,7 +238,7 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     // cub temp storage for the largest sort / scan we issue
     size_t b1 = 0, b2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, b1, h->keys, h->keys_sorted, h->iota, h->perm, (int)cap, 0, h->key_bits, h->stream);
-    cub::DeviceScan::ExclusiveSum(nullptr, b2, h->cnt, h->off, (int)cap + 1, h->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, b2, h->cnt, h->off, std::max((int)cap + 1, h->nbins_cap + 2), h->stream);
     size_t b3 = 0;
     cub::DeviceSelect::Flagged(nullptr, b3, h->iota, h->cnt, h->perm, h->off, (int)cap, h->stream);
     h->cub_tmp_bytes = std::max(std::max(b1, b2), b3) + 256;
@@ -315,7 +319,8 @@ int upload_grid_periodic(AfvHandle h) {
     return AFV_OK;
 }
 
-// bin + sort + reorder + bin starts.  Cells marked dead by the exchange sort behind the live ones and are dropped here.
+// The cell list: counting sort by bin (k_bin_count, exclusive scan, k_bin_scatter).  Cells marked dead by the exchange land
+// behind the live ones and are dropped here.
 int stage_sort(AfvHandle h) {
     StageTimer t(h, 0);
     const int n_all = (int)h->n;
@@ -330,31 +335,23 @@ int stage_sort(AfvHandle h) {
         k_bbox_final<<<1, 32, 0, h->stream>>>(h->bbox_part, nb, h->prm.r, h->nbins_cap, h->d_grid);
         h->launches += 2;
     }
-    // sort width: the bins actually in use when the host knows them (periodic box / slab), else the capacity; dead
-    // cells carry the first key behind the bins
-    int sort_bits = h->key_bits;
-    unsigned dead_key = (1u << h->key_bits) - 1u;
-    if (h->L > 0.0) {
-        dead_key = (unsigned)(h->grid_host.nbx * h->grid_host.nby);
-        sort_bits = 1;
-        while ((1u << sort_bits) <= dead_key) ++sort_bits;
-    }
-    k_bin_keys<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->xy[c], h->owned[c], n_all, h->d_grid, dead_key, h->keys);
+    // bins: those actually in use when the host knows them (periodic box / slab), else the capacity (the grid of an open
+    // system is made on the device); dead cells go to the bin behind the last one
+    int nbins = h->nbins_cap;
+    if (h->L > 0.0) nbins = h->grid_host.nbx * h->grid_host.nby;
+    const unsigned dead_key = (unsigned)nbins;
+    CK(cudaMemsetAsync(h->bin_cnt, 0, (size_t)(nbins + 2) * sizeof(int), h->stream));
+    k_bin_count<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->xy[c], h->owned[c], n_all, h->d_grid, dead_key, h->keys, h->bin_cnt);
     size_t tmp = h->cub_tmp_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->keys, h->keys_sorted, h->iota, h->perm, n_all, 0, sort_bits, h->stream));
-    if (n > 0)
-        k_reorder<<<nblk(n, 256), 256, 0, h->stream>>>(h->perm, n, h->xy[c], h->th[c], h->a0[c], h->gid[c], h->owned[c],
-                                                        h->xy[o], h->th[o], h->a0[o], h->gid[o], h->owned[o]);
+    CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp, tmp, h->bin_cnt, h->bin_start, nbins + 2, h->stream));
+    k_bin_scatter<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->keys, n_all, dead_key, h->bin_start, h->bin_cnt, h->xy[c], h->th[c], h->a0[c],
+                                                            h->gid[c], h->owned[c], h->xy[o], h->th[o], h->a0[o], h->gid[o], h->owned[o],
+                                                            h->keys_sorted, h->gid_is_perm ? h->slot_of_gid : nullptr);
     h->cur = o;
     h->n = n; h->n_dead = 0;
     h->n_main = n; h->n_late = 0; h->late_deep = false;
-    if (h->L > 0.0) {
-        GridDesc g{};
-        periodic_grid(h, g);
-        h->h_flags[3] = g.nbx * g.nby;
-    }
-    k_bin_start<<<nblk(n + 1, 256), 256, 0, h->stream>>>(h->keys_sorted, n, h->d_grid, h->bin_start);
-    h->launches += 4;  // keys, sort (counted once), reorder, bin_start
+    if (h->L > 0.0) h->h_flags[3] = nbins;
+    h->launches += 3;  // count, scan, scatter
     CK(cudaGetLastError());
     return AFV_OK;
 }

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(128) k_nbrs(GeomArgs a, const int cmax) {
     int *const list = a.nb_list + s;
     int n = 0, smin = -1;
     bool ok = true;
-    double dmin = 1e300;
+    double dmin = 1e300, mdx = 0.0, mdy = 0.0;
     for (int tab = 0; tab < (SLAB ? 2 : 1); ++tab) {     // the sorted cells, then (face pass of a slab) the late cells
         const int *const bin_start = tab ? a.bin_start_late : a.bin_start;
         if (!bin_start) break;
@@ -168,7 +168,9 @@ __global__ void __launch_bounds__(128) k_nbrs(GeomArgs a, const int cmax) {
                     if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
                     const double d2 = dx * dx + dy * dy;
                     if (d2 < cut2 && c != s && d2 > 0.0) {
-                        if (d2 < dmin) { dmin = d2; smin = c; }
+                        // nearest neighbour; among equals (lattices) the smallest displacement: the ring start must not
+                        // depend on the order the candidates are met in
+                        if (d2 < dmin || (d2 == dmin && (dx < mdx || (dx == mdx && dy < mdy)))) { dmin = d2; smin = c; mdx = dx; mdy = dy; }
                         if (n < cmax) { list[(size_t)n * a.stride] = c; ++n; }
                         else ok = false;
                     }

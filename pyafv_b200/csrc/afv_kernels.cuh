@@ -70,24 +70,51 @@ __global__ void k_bbox_final(const double *__restrict__ part, int nblocks, doubl
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K1a: bin hash.  key = by * nbx + bx  (row-major so that the 3 bins of a row are contiguous after the sort)
+// K1: the cell list is a COUNTING sort by bin -- three launches: (a) bin key of every cell + histogram, (b) exclusive
+// scan of the histogram = first slot of every bin, (c) scatter of the SoA state into bin order.  key = by * nbx + bx
+// (row-major, so that the 3 bins of a row are one contiguous run of slots).  The order of the cells INSIDE a bin is
+// whatever the atomics make it; nothing downstream depends on it (k_clip's results are a function of the set of
+// neighbours, not of the order they are met in -- test_late_cell_exchange_equals_plain).
+// Cells marked CELL_DEAD (stale halo copies, see k_exchange_pack) get `dead_key`, the bin behind every real one: they
+// land behind the live cells, where the scatter drops them.
 // ------------------------------------------------------------------------------------------------------
-// Cells marked CELL_DEAD (stale halo copies, see k_exchange_pack) get `dead_key`, larger than every bin key: the
-// sort moves them behind the live cells, where the reorder drops them.
-__global__ void k_bin_keys(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, const GridDesc *__restrict__ gp,
-                           unsigned dead_key, unsigned *__restrict__ keys) {
+__global__ void k_bin_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, const GridDesc *__restrict__ gp,
+                            unsigned dead_key, unsigned *__restrict__ keys, int *__restrict__ bin_cnt) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (owned[i] == CELL_DEAD) { keys[i] = dead_key; return; }
-    const GridDesc g = *gp;
-    const double2 q = xy[i];
-    const int bx = bin_col(g, q.x);
-    int by = (int)floor((q.y - g.y0) * g.inv_by);
-    by = min(max(by, 0), g.nby - 1);
-    keys[i] = bin_key(g, bx, by);
+    unsigned key = dead_key;
+    if (owned[i] != CELL_DEAD) {
+        const GridDesc g = *gp;
+        const double2 q = xy[i];
+        const int bx = bin_col(g, q.x);
+        int by = (int)floor((q.y - g.y0) * g.inv_by);
+        by = min(max(by, 0), g.nby - 1);
+        key = bin_key(g, bx, by);
+    }
+    keys[i] = key;
+    atomicAdd(&bin_cnt[key], 1);
 }
 
-// K1b: gather the SoA state into sorted order
+// (c): cell i takes the slot bin_start[key] + (count left in its bin) - 1; the counts are back at zero afterwards.  Dead
+// cells are dropped.  slot_of_gid (may be null): where the caller's cell gid went (fixed-order reductions).
+__global__ void k_bin_scatter(const unsigned *__restrict__ keys, int n, unsigned dead_key, const int *__restrict__ bin_start, int *__restrict__ bin_cnt,
+                              const double2 *__restrict__ xy0, const double *__restrict__ t0, const double *__restrict__ a0,
+                              const int64_t *__restrict__ g0, const unsigned char *__restrict__ o0, double2 *__restrict__ xy1,
+                              double *__restrict__ t1, double *__restrict__ a1, int64_t *__restrict__ g1, unsigned char *__restrict__ o1,
+                              unsigned *__restrict__ keys_sorted, int *__restrict__ slot_of_gid) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned key = keys[i];
+    const int left = atomicSub(&bin_cnt[key], 1);
+    if (key == dead_key) return;
+    const int s = bin_start[key] + left - 1;
+    const int64_t g = g0[i];
+    xy1[s] = xy0[i]; t1[s] = t0[i]; a1[s] = a0[i]; g1[s] = g; o1[s] = o0[i];
+    keys_sorted[s] = key;
+    if (slot_of_gid) slot_of_gid[g] = s;
+}
+
+// gather the SoA state through a permutation (compaction paths)
 __global__ void k_reorder(const int *__restrict__ perm, int n, const double2 *__restrict__ xy0,
                           const double *__restrict__ t0, const double *__restrict__ a0, const int64_t *__restrict__ g0,
                           const unsigned char *__restrict__ o0, double2 *__restrict__ xy1,
@@ -99,17 +126,6 @@ __global__ void k_reorder(const int *__restrict__ perm, int n, const double2 *__
     xy1[s] = xy0[p]; t1[s] = t0[p]; a1[s] = a0[p]; g1[s] = g0[p]; o1[s] = o0[p];
 }
 
-// K1c: first sorted slot of every bin (lower bound), bin_start[nbins] = n.  One thread per sorted slot s in [0, n]:
-// the bins in (key[s-1], key[s]] start at s (every bin is written exactly once; runs of empty bins are short).
-__global__ void k_bin_start(const unsigned *__restrict__ keys_sorted, int n, const GridDesc *__restrict__ gp,
-                            int *__restrict__ bin_start) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > n) return;
-    const int nb = gp->nbx * gp->nby;
-    const int first = (s > 0) ? (int)keys_sorted[s - 1] + 1 : 0;
-    const int last = (s < n) ? (int)keys_sorted[s] : nb;
-    for (int b = first; b <= last; ++b) bin_start[b] = s;
-}
 
 #include "afv_geometry.cuh"
 

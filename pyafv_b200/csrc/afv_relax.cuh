@@ -20,15 +20,18 @@ __global__ void k_cell_energy(const double *__restrict__ area, const double *__r
     if (s < n) e[s] = owned[s] == CELL_OWNED ? cell_energy(ph, area[s], perim[s], arcl[s], a0[s]) : 0.0;
 }
 
-// partial[b * N_SUMS + q]: the five sums over the cells block b visits (grid-stride); vel (indexed by gid) may be null
+// partial[b * N_SUMS + q]: the five sums over the cells block b visits (grid-stride); vel (indexed by gid) may be null.
+// slot_of_gid (may be null): visit the cells in the CALLER's order -- the order inside a bin of the cell list is not
+// reproducible from run to run, the caller's order is, and with it every bit of the sums.
 __global__ void __launch_bounds__(SUMS_TPB) k_sums_partial(const double *__restrict__ fx, const double *__restrict__ fy, const double2 *__restrict__ vel,
                                                            const int64_t *__restrict__ gid, const unsigned char *__restrict__ owned,
                                                            const double *__restrict__ area, const double *__restrict__ perim,
                                                            const double *__restrict__ arcl, const double *__restrict__ a0, int n, PhysDev ph,
-                                                           double *__restrict__ partial) {
+                                                           const int *__restrict__ slot_of_gid, double *__restrict__ partial) {
     __shared__ double sm[N_SUMS][SUMS_TPB];
     double acc[N_SUMS] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int s = blockIdx.x * SUMS_TPB + threadIdx.x; s < n; s += gridDim.x * SUMS_TPB) {
+    for (int i = blockIdx.x * SUMS_TPB + threadIdx.x; i < n; i += gridDim.x * SUMS_TPB) {
+        const int s = slot_of_gid ? slot_of_gid[i] : i;
         if (owned[s] != CELL_OWNED) continue;
         const double Fx = fx[s], Fy = fy[s];
         if (vel) { const double2 v = vel[gid[s]]; acc[0] += Fx * v.x + Fy * v.y; acc[1] += v.x * v.x + v.y * v.y; }
