@@ -115,7 +115,10 @@ __device__ __forceinline__ int cell_rows(const int nline, const bool per, int li
 // ------------------------------------------------------------------------------------------------------
 // fast path
 // ------------------------------------------------------------------------------------------------------
-constexpr int GEOM_TPB = 128;
+#ifndef GEOM_TPB_
+#define GEOM_TPB_ 128
+#endif
+constexpr int GEOM_TPB = GEOM_TPB_;
 constexpr int KP = 14;           // polygon edges on the fast path (<= 16: the order of the slots is a sequence of 4-bit ids)
 constexpr int CMAX_HARD = 128;   // upper bound of the per-cell neighbour list (the launch picks cmax <= this)
 constexpr int NB_OVERFLOW = 255; // nb_cnt: more neighbours within 2r than the list holds
@@ -187,7 +190,15 @@ __global__ void __launch_bounds__(128) k_nbrs(GeomArgs a, const int cmax) {
 __device__ __forceinline__ double2 bisector_junction(double ax, double ay, double bx, double by) {
     // explicit roundings: the compiler must not contract the two inlined copies of this expression differently
     const double ca = __dmul_rn(0.5, __fma_rn(ax, ax, __dmul_rn(ay, ay))), cb = __dmul_rn(0.5, __fma_rn(bx, bx, __dmul_rn(by, by)));
+#ifdef AFV_FAST_RCP
+    const double det = __fma_rn(ax, by, -__dmul_rn(ay, bx));
+    double idet;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(idet) : "d"(det));          // ~20 good bits, then two Newton steps
+    idet = __fma_rn(idet, __fma_rn(-det, idet, 1.0), idet);
+    idet = __fma_rn(idet, __fma_rn(-det, idet, 1.0), idet);
+#else
     const double idet = __drcp_rn(__fma_rn(ax, by, -__dmul_rn(ay, bx)));
+#endif
     return make_double2(__dmul_rn(__fma_rn(ca, by, -__dmul_rn(cb, ay)), idet), __dmul_rn(__fma_rn(ax, cb, -__dmul_rn(bx, ca)), idet));
 }
 

@@ -1,12 +1,17 @@
 #!/bin/bash
-# Final evidence run on the GPU box: tests, bench, ncu launch list of the bench command, ncu --set full of the three hot kernels.
-TAG=${1:-final}
+# usage: scripts/gpu_final.sh TAG   (one GPU, through gpurun): the evidence of a round -- GPU tests, both bench arms, the ncu
+# launch list of the bench command and one --set full capture per hot kernel (each after its own plain run exited 0)
+TAG=$1
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log; tail -3 gpurun_out/${TAG}_pytest.log
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err; echo "ref rc=$?"
-timeout 300 python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_bench_short.json 2> gpurun_out/${TAG}_bench_short.err &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_ncu_launch.log 2>&1
-python scripts/prof_step.py 1000000 4 > gpurun_out/${TAG}_plain.log 2>&1 && for k in k_hull k_ring k_force; do
-  ncu --set full --clock-control none --import-source on -k regex:^$k\$ -s 2 -c 1 -o gpurun_out/${TAG}_$k python scripts/prof_step.py 1000000 4 > gpurun_out/${TAG}_ncu_$k.log 2>&1; tail -1 gpurun_out/${TAG}_ncu_$k.log; done
-for args in "1000000 0.1" "1000000 0.3183" "1000000 1.0 30 jammed" "4000000 1.0 10" "16000000 1.0 5"; do python scripts/ab_stage.py $args; done > gpurun_out/${TAG}_regimes.txt 2>&1; cat gpurun_out/${TAG}_regimes.txt
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log; tail -2 gpurun_out/${TAG}_pytest.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+python scripts/bench_summary.py gpurun_out/${TAG}_bench.json
+timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err; echo "reference rc=$?"; cat gpurun_out/${TAG}_bench_reference.json | cut -c1-400
+timeout 600 python bench.py --steps 2 --warmup 3 --skip-config4 --skip-regimes > gpurun_out/${TAG}_bench_short.json 2> gpurun_out/${TAG}_bench_short.err \
+  && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --skip-config4 --skip-regimes > gpurun_out/${TAG}_ncu_launch.log 2>&1
+tail -1 gpurun_out/${TAG}_ncu_launch.log | cut -c1-200
+python scripts/prof_step.py 1000000 4 > gpurun_out/${TAG}_plain.log 2>&1 || { cat gpurun_out/${TAG}_plain.log; exit 1; }
+for K in k_clip k_force k_nbrs; do
+  ncu --set full --clock-control none --import-source on -k regex:$K -s 2 -c 1 -o gpurun_out/${TAG}_$K python scripts/prof_step.py 1000000 4 > gpurun_out/${TAG}_ncu_$K.log 2>&1
+  tail -1 gpurun_out/${TAG}_ncu_$K.log
+done
