@@ -234,8 +234,9 @@ def run_ours(args) -> dict:
     verify = verify_sharded(torch, dist, afv, SlabShardedSimulator, phys, rank, world, local, stream) if world > 1 else None
 
     # ---- the headline workload: `cells` per GPU ----
-    # the late-cell overlap pays while the exchange is a visible share of the step
-    overlap = world > 1 and (not args.no_overlap) and (args.overlap or cells <= 4_000_000)
+    # exchange-then-step by default: with this round's kernels the late-cell overlap (face pass, late sort, event waits) costs
+    # more than the ~0.1 ms of exchange it hides (measured on 2 GPUs: 0.947 against 0.993 ms/step)
+    overlap = world > 1 and args.overlap and not args.no_overlap
     sim, step_k, L = make_sim(cells, overlap)
     h = sim._h
     sampler = ClockSampler(local)
@@ -567,9 +568,9 @@ def main():
     ap.add_argument("--reference-cells", type=int, default=0, help="reference arm: cells (default: the full N = 10^6 workload)")
     ap.add_argument("--skip-config4", action="store_true", help="do not time the N = 10^8 block")
     ap.add_argument("--skip-regimes", action="store_true", help="N = 1: do not time the jammed / rho l^2 = 0.1 regimes")
-    ap.add_argument("--no-overlap", action="store_true", help="N > 1: exchange, then step (default up to 4x10^6 cells/GPU: the exchange of "
-                    "a step travels while the step sorts its cells and builds its interior geometry -- late cells, DESIGN.md section 5)")
-    ap.add_argument("--overlap", action="store_true", help="N > 1: the late-cell overlap at any size")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: exchange, then step (the default)")
+    ap.add_argument("--overlap", action="store_true", help="N > 1: the exchange of a step travels while the step sorts its cells and builds "
+                    "its interior geometry (late cells, DESIGN.md section 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
