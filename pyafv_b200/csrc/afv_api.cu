@@ -1,6 +1,7 @@
 // C-ABI implementation (include/afv_b200.h): context, memory, stage scheduling on one CUDA stream.
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges cost nothing unless a profiler is attached
 
 #include <algorithm>
 #include <cmath>
@@ -248,11 +249,15 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     return AFV_OK;
 }
 
+// One stage of a build / step: an NVTX range around its launches (tracing) and, when profiling is
+// switched on, a pair of CUDA events on the launching stream.
+static const char *const STAGE_NAMES[AFV_N_STAGES] = {"afv:cell_list", "afv:k_nbrs", "afv:k_clip", "afv:k_force", "afv:export", "afv:k_geometry_slow"};
 struct StageTimer {
     AfvHandle h;
     int idx = -1;
     cudaStream_t st;
     StageTimer(AfvHandle h_, int stage, cudaStream_t stream = nullptr) : h(h_), st(stream ? stream : h_->stream) {
+        nvtxRangePushA(STAGE_NAMES[stage]);
         if (!h->profiling) return;
         AfvContext::Span sp;
         sp.stage = stage;
@@ -269,6 +274,7 @@ struct StageTimer {
     }
     ~StageTimer() {
         if (idx >= 0) cudaEventRecord(h->spans[idx].b, st);
+        nvtxRangePop();
     }
 };
 
