@@ -176,7 +176,9 @@ int afv_pack_pair(AfvHandle h, double lo0, double hi0, double shift0, double lo1
                   double *msg0_dev, double *msg1_dev, int64_t cap_rows);
 int afv_finish_pair(AfvHandle h, const double *in0_dev, const double *in1_dev, int64_t cap_rows, int is_halo, int remove_packed);
 /* One exchange per step: ownership transfers and halo cells in the same message.  Message = (cap_rows+1, 5): header
- * [n_transfer, n_halo, 0, 0, 0], then the transfer rows, then the halo rows.  afv_pack_exchange selects, for the slab
+ * [n_transfer, n_halo, n_deep, 0, 0]; the transfer rows fill rows 1 .. n_transfer, the halo rows fill the buffer from
+ * the back (halo row i at row cap_rows - i); the order inside either group is arbitrary (one launch packs both messages
+ * with atomics).  afv_pack_exchange selects, for the slab
  * [lo, hi) and with d = the offset of x to lo (on a slab handle: the minimum image about the slab centre): left
  * message = owned cells with d < 0 (transfers) and 0 <= d < halo (halo), x + shift_left; right message = d >= hi-lo
  * (transfers) and hi-lo-halo <= d < hi-lo (halo), x + shift_right (both shifts are 0 for slab handles).  The same pass retires the halo

@@ -100,6 +100,7 @@ struct AfvContext {
     bool defer_checks = false;  // afv_step returns without synchronising; the flags are read at the next exchange / synchronize
     // pair exchange state (afv_pack_pair -> afv_finish_pair)
     int *pair_cnt = nullptr;       // device: list lengths of the last pack (2 for the pair form, 4 for the exchange)
+    int *xch_work = nullptr;       // device int[8]: working counters of k_exchange_pack (zero between launches)
     double *pair_host = nullptr;   // pinned [20]: counts sent / received, the deferred flags, the displacement slots
     double *pair_dev = nullptr;    // device [20]
     double pair_rng[4] = {0, 0, 0, 0};
@@ -554,7 +555,8 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
         cudaMalloc((void **)&h->ovf_arc_pts, (size_t)OVF_MAX * ARC_SLOW * sizeof(double4)) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; afv_destroy(h); return AFV_ERR_CUDA;
     }
-    if (cudaMalloc((void **)&h->pair_cnt, 4 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 20 * sizeof(double)) != cudaSuccess ||
+    if (cudaMalloc((void **)&h->xch_work, 8 * sizeof(int)) != cudaSuccess || cudaMemset(h->xch_work, 0, 8 * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&h->pair_cnt, 4 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 20 * sizeof(double)) != cudaSuccess ||
         cudaHostAlloc((void **)&h->pair_host, 20 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; afv_destroy(h); return AFV_ERR_CUDA;
     }
@@ -572,7 +574,7 @@ void afv_destroy(AfvHandle h) {
     cudaFree(h->d_grid); cudaFree(h->flags); cudaFree(h->bbox_part);
     cudaFree(h->ovf_cells); cudaFree(h->ovf_len); cudaFree(h->ovf_hull); cudaFree(h->ovf_m); cudaFree(h->ovf_ring_h); cudaFree(h->ovf_ring_nbr);
     cudaFree(h->ovf_arc_key); cudaFree(h->ovf_arc_pts);
-    cudaFree(h->pair_cnt); cudaFree(h->pair_dev); cudaFreeHost(h->pair_host);
+    cudaFree(h->pair_cnt); cudaFree(h->xch_work); cudaFree(h->pair_dev); cudaFreeHost(h->pair_host);
     for (cudaEvent_t e : {h->ev_sorted, h->ev_late, h->ev_force, h->ev_pack, h->ev_interior}) if (e) cudaEventDestroy(e);
     for (DevBuf *b : {&h->late_keys, &h->late_keys_sorted, &h->late_perm, &h->late_tmp}) cudaFree(b->p);
     for (DevBuf *b : {&h->scratch_a, &h->scratch_b, &h->noise_buf, &h->conn_buf, &h->ring_types, &h->ring_xy, &h->ring_off,

@@ -568,127 +568,84 @@ __global__ void k_pack_message(const int *__restrict__ idx, const int *__restric
     double *q = msg + 5 * (size_t)(i + 1);
     q[0] = xy[s].x + x_shift; q[1] = xy[s].y; q[2] = th[s]; q[3] = a0[s]; q[4] = (double)gid[s];
 }
-// ---- the per-step exchange, three launches, no atomics (message order = slot order, reproducible) ----------------
-// exchange message = (cap+1, 5) rows: header [n_transfer, n_halo, 0, 0, 0], then the transfer rows (cells that change
-// owner) followed by the halo rows.
-// Owned cells fall into up to four lists (xch_lists above): q = 0 transfers to the left rank (x < lo), 1 halo rows for
-// the left rank (lo <= x < lo + halo), 2 transfers to the right rank (x >= hi), 3 halo rows for the right rank
-// (hi - halo <= x < hi).
+// ---- the per-step exchange: ONE launch packs both messages ------------------------------------------------------
+// exchange message = (cap+1, 5) rows: header [n_transfer, n_halo, n_deep, 0, 0]; the transfer rows (cells that change
+// owner) fill rows 1 .. n_transfer, the halo rows fill the buffer from the BACK (halo row i at row cap - i), so that both
+// kinds can be appended concurrently without knowing each other's count.  Rows are claimed with warp-aggregated atomics:
+// their order is arbitrary, and nothing downstream depends on it.
+// Owned cells fall into up to four lists (xch_lists above): q = 0 transfers to the left rank, 1 halo rows for the left
+// rank, 2 transfers to the right rank, 3 halo rows for the right rank.
 constexpr int XCH_TPB = 256;
-// pass 1: members of every list per block
-__global__ void __launch_bounds__(XCH_TPB) k_exchange_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n,
-                                                            double lo, double hi, double halo, double L, int *__restrict__ blk_cnt) {
-    const int i = blockIdx.x * XCH_TPB + threadIdx.x;
-    const unsigned m = (i < n) ? xch_lists(slab_offset(xy[i].x, lo, hi - lo, L), owned[i], hi - lo, halo) : 0u;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int c = __syncthreads_count((m >> q) & 1u);
-        if (threadIdx.x == 0) blk_cnt[4 * blockIdx.x + q] = c;
-    }
+// row k of the cells a message carries (k < n_own: transfers, then the halo rows)
+__device__ __forceinline__ const double *msg_row(const double *__restrict__ msg, int k, int n_own, int cap) {
+    return msg + 5 * (size_t)(k < n_own ? k + 1 : cap - (k - n_own));
 }
-// pass 2 (one block): exclusive scan of the block counts of every list, list totals, message headers
-__global__ void __launch_bounds__(1024) k_exchange_scan(const int *__restrict__ blk_cnt, int nblocks, int *__restrict__ blk_off,
-                                                        int *__restrict__ totals, double *__restrict__ msg_left, double *__restrict__ msg_right) {
-    __shared__ int warp_sum[32][4];
-    __shared__ int carry[4];
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (t < 4) carry[t] = 0;
-    __syncthreads();
-    for (int base = 0; base < nblocks; base += 1024) {
-        const int b = base + t;
-        int v[4], inc[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            v[q] = (b < nblocks) ? blk_cnt[4 * b + q] : 0;
-            int x = v[q];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL_MASK, x, d); if (lane >= d) x += y; }
-            inc[q] = x;
-            if (lane == 31) warp_sum[w][q] = x;
-        }
-        __syncthreads();
-        if (w == 0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                int x = warp_sum[lane][q];
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL_MASK, x, d); if (lane >= d) x += y; }
-                warp_sum[lane][q] = x;       // inclusive over warps
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int before = carry[q] + (w ? warp_sum[w - 1][q] : 0) + inc[q] - v[q];
-            if (b < nblocks) blk_off[4 * b + q] = before;
-        }
-        __syncthreads();
-        if (t < 4) carry[t] += warp_sum[31][t];
-        __syncthreads();
-    }
-    if (t < 4) totals[t] = carry[t];
-    if (t == 0) {
-        msg_left[0] = (double)carry[0]; msg_left[1] = (double)carry[1]; msg_left[2] = msg_left[3] = msg_left[4] = 0.0;
-        msg_right[0] = (double)carry[2]; msg_right[1] = (double)carry[3]; msg_right[2] = msg_right[3] = msg_right[4] = 0.0;
-    }
-}
-// pass 3: write the rows ([header][transfers][halo rows]; rows beyond `cap` are dropped, the header keeps the true
-// counts so that both ends see the overflow) and update the ownership marks: halo copies of the previous step
-// become CELL_DEAD (the next sort drops them), cells that left the slab stay as halo copies of their new owner's cell.
+// work: int[8], zero on entry and zero again on exit: [0..3] rows claimed per list, [4] / [5] deep transfers left / right,
+// [6] blocks done.  The last block writes the headers and the totals (pair_cnt, read back with the counts of the received
+// messages).  Also updates the ownership marks: halo copies of the previous step become CELL_DEAD (the next cell-list pass
+// drops them), cells that left the slab stay as halo copies of their new owner's cell.
 __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__restrict__ xy, const double *__restrict__ th,
                                                            const double *__restrict__ a0, const int64_t *__restrict__ gid,
                                                            unsigned char *__restrict__ owned, int n,
                                                            double lo, double hi, double halo, double L, double shift_left, double shift_right,
-                                                           double deep_lo, double deep_hi, const int *__restrict__ blk_off,
-                                                           const int *__restrict__ totals, int cap, double *__restrict__ msg_left,
-                                                           double *__restrict__ msg_right) {
-    __shared__ int warp_cnt[XCH_TPB / 32][4];
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+                                                           double deep_lo, double deep_hi, int *__restrict__ work, int *__restrict__ totals,
+                                                           int cap, double *__restrict__ msg_left, double *__restrict__ msg_right) {
+    const int t = threadIdx.x, lane = t & 31;
     const int i = blockIdx.x * XCH_TPB + t;
     double2 p = make_double2(0.0, 0.0);
     unsigned char own = CELL_DEAD;
     unsigned m = 0u;
     double xr = 0.0;
     if (i < n) { p = xy[i]; own = owned[i]; xr = slab_offset(p.x, lo, hi - lo, L); m = xch_lists(xr, own, hi - lo, halo); }
-    int rank_in_warp[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const unsigned bal = __ballot_sync(FULL_MASK, (m >> q) & 1u);
-        rank_in_warp[q] = __popc(bal & ((1u << lane) - 1u));
-        if (lane == 0) warp_cnt[w][q] = __popc(bal);
-    }
-    __syncthreads();
     if (i < n) {
         if (own == CELL_HALO) owned[i] = CELL_DEAD;
         else if (m & 5u) owned[i] = CELL_HALO;
     }
-    if (!m) return;
     // transfers that land beyond the receiver's face columns (header slot 2): its face pass then covers every cell
-    if ((m & 1u) && xr < deep_lo - lo) atomicAdd(&msg_left[2], 1.0);
-    if ((m & 4u) && xr >= deep_hi - lo) atomicAdd(&msg_right[2], 1.0);
-    const double tv = th[i], av = a0[i], gv = (double)gid[i];
+    const unsigned deepl = __ballot_sync(FULL_MASK, (m & 1u) && xr < deep_lo - lo), deepr = __ballot_sync(FULL_MASK, (m & 4u) && xr >= deep_hi - lo);
+    if (lane == 0) { if (deepl) atomicAdd(&work[4], __popc(deepl)); if (deepr) atomicAdd(&work[5], __popc(deepr)); }
+    double tv = 0.0, av = 0.0, gv = 0.0;
+    if (m) { tv = th[i]; av = a0[i]; gv = (double)gid[i]; }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
+        const unsigned bal = __ballot_sync(FULL_MASK, (m >> q) & 1u);
+        if (!bal) continue;
+        int base = 0;
+        if (lane == __ffs(bal) - 1) base = atomicAdd(&work[q], __popc(bal));
+        base = __shfl_sync(FULL_MASK, base, __ffs(bal) - 1);
         if (!((m >> q) & 1u)) continue;
-        int r = blk_off[4 * blockIdx.x + q] + rank_in_warp[q];
-        for (int k = 0; k < w; ++k) r += warp_cnt[k][q];
-        if (q & 1) r += totals[q - 1];                       // halo rows follow the transfers
-        if (r >= cap) continue;
-        double *row = ((q < 2) ? msg_left : msg_right) + 5 * (size_t)(r + 1);
+        const int r = base + __popc(bal & ((1u << lane) - 1u));
+        if (r >= cap) continue;                                  // dropped; the header keeps the true count, both ends see the overflow
+        double *row = ((q < 2) ? msg_left : msg_right) + 5 * (size_t)((q & 1) ? cap - r : r + 1);
         row[0] = p.x + ((q < 2) ? shift_left : shift_right); row[1] = p.y; row[2] = tv; row[3] = av; row[4] = gv;
+    }
+    // the last block to finish publishes the counts
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (t == 0) s_last = (atomicAdd(&work[6], 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (s_last && t == 0) {
+        __threadfence();
+        volatile int *w = work;
+        const int c0 = w[0], c1 = w[1], c2 = w[2], c3 = w[3], dl = w[4], dr = w[5];
+        totals[0] = c0; totals[1] = c1; totals[2] = c2; totals[3] = c3;
+        msg_left[0] = (double)c0; msg_left[1] = (double)c1; msg_left[2] = (double)dl; msg_left[3] = msg_left[4] = 0.0;
+        msg_right[0] = (double)c2; msg_right[1] = (double)c3; msg_right[2] = (double)dr; msg_right[3] = msg_right[4] = 0.0;
+        for (int k = 0; k < 7; ++k) work[k] = 0;
     }
 }
 // received messages -> cells appended behind slot `base`: [left transfers][left halo][right transfers][right halo];
 // with `perm` (late cells, sorted by bin among themselves) row perm[i] of that sequence goes to slot base + i
 __global__ void k_exchange_append(const double *__restrict__ in_left, const double *__restrict__ in_right, int nl_own, int nl, int nr_own,
-                                  int nr, int base, const int *__restrict__ perm, double2 *__restrict__ xy, double *__restrict__ th,
+                                  int nr, int base, int cap, const int *__restrict__ perm, double2 *__restrict__ xy, double *__restrict__ th,
                                   double *__restrict__ a0, int64_t *__restrict__ gid, unsigned char *__restrict__ owned) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nl + nr) return;
     const int src = perm ? perm[i] : i;
     const bool left = src < nl;
     const int k = left ? src : src - nl;
-    const double *q = (left ? in_left : in_right) + 5 * (size_t)(k + 1);
+    const double *q = msg_row(left ? in_left : in_right, k, left ? nl_own : nr_own, cap);
     const int d = base + i;
     xy[d] = make_double2(q[0], q[1]); th[d] = q[2]; a0[d] = q[3]; gid[d] = (int64_t)q[4];
     owned[d] = (k < (left ? nl_own : nr_own)) ? CELL_OWNED : CELL_HALO;
@@ -706,11 +663,11 @@ __global__ void k_bin_start_search(const unsigned *__restrict__ keys_sorted, int
     bin_start[b] = lo;
 }
 // bin keys of the received rows, in the order of k_exchange_append's unpermuted sequence
-__global__ void k_late_keys(const double *__restrict__ in_left, const double *__restrict__ in_right, int nl, int nr,
-                            const GridDesc *__restrict__ gp, unsigned *__restrict__ keys) {
+__global__ void k_late_keys(const double *__restrict__ in_left, const double *__restrict__ in_right, int nl_own, int nl, int nr_own, int nr,
+                            int cap, const GridDesc *__restrict__ gp, unsigned *__restrict__ keys) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nl + nr) return;
-    const double *q = (i < nl ? in_left + 5 * (size_t)(i + 1) : in_right + 5 * (size_t)(i - nl + 1));
+    const double *q = (i < nl) ? msg_row(in_left, i, nl_own, cap) : msg_row(in_right, i - nl, nr_own, cap);
     const GridDesc g = *gp;
     const int bx = bin_col(g, q[0]);
     int by = (int)floor((q[1] - g.y0) * g.inv_by);

@@ -231,6 +231,7 @@ class SlabShardedSimulator:
         self.overlapped_steps = 0         # steps taken in the overlapped form so far
         self._xs = None
         self._inbox = None
+        self._sent = None                 # plain form: messages for the current positions, packed and on their way already
         self.set_cells(pts, theta, A0, gids)
         if self.overlap:
             # high priority: its blocks (pack, append, the face pass) are dispatched ahead of the pending blocks of the interior pass
@@ -253,9 +254,12 @@ class SlabShardedSimulator:
         self._cap = None
         self._halo_fresh = False          # the halo copies on the device belong to the current positions
         self._inbox = None                # overlapped form: messages packed for the current positions, on their way, not yet appended
+        self._sent = None
 
     @property
     def n_owned(self) -> int:
+        if self._sent is not None:        # transfers of an exchange in flight are booked when it is finished
+            self._refresh_halo()
         return self.store.n_owned
 
     def close(self) -> None:
@@ -297,6 +301,9 @@ class SlabShardedSimulator:
         if self._inbox is not None:       # left over from the overlapped form: already packed and on its way
             self.store.stream_wait(self._xs.cuda_stream)
             inbox, self._inbox = self._inbox, None
+            self.exchange_in(*inbox)
+        elif self._sent is not None:      # issued right behind the last update (see step())
+            inbox, self._sent = self._sent, None
             self.exchange_in(*inbox)
         else:
             self.exchange_in(*self.comm.exchange_fixed(*self.exchange_out()))
@@ -343,6 +350,12 @@ class SlabShardedSimulator:
             if not self.overlap:
                 self._refresh_halo()
                 self.compute_step(dt, mu, v0, Dr, seed)
+                # The next exchange is packed and handed to NCCL right away, behind the update on the same stream: the host
+                # side of that (torch's P2P batch: >= 0.1 ms) runs while the GPU is still busy with this step, instead of
+                # leaving it idle at the start of the next one.  The counts are read (one synchronisation) when the next
+                # step, or a build, begins.
+                if self.world > 1 and self.comm:
+                    self._sent = self.comm.exchange_fixed(*self.exchange_out())
                 continue
             if self._inbox is None:       # first step of a run: pack and transport on the handle's stream
                 self._halo_fresh = False
@@ -431,6 +444,14 @@ class LoopbackShardedSimulator:
             self.ranks.append(SlabShardedSimulator(p, th, phys, L, rank=rk, world=world, device=dv, gids=g, A0=a0, halo_width=halo_width,
                                                    comm=False, stream=stream, overlap=self.overlap, exchange_stream=xs))
         self.N = pts.shape[0]
+        self._same_capacity()
+
+    def _same_capacity(self) -> None:
+        """Every rank must use the same message size (the halo rows are addressed from the back of the buffer): the
+        largest of the per-rank estimates, as the all-reduce of the one-process-per-GPU form gives."""
+        cap = max(halo_capacity(s.store.n_owned, s.geo) for s in self.ranks)
+        for s in self.ranks:
+            s._cap = (cap,)
 
     def _deal(self, pts, theta, A0):
         """(pts, theta, A0, gids) of every slab: ownership by x (right-sided, the last slab takes the upper face)."""
@@ -449,6 +470,7 @@ class LoopbackShardedSimulator:
             sim.set_cells(p, th, a0, g)
         self.N = pts.shape[0]
         self._inbox = None
+        self._same_capacity()
 
     def _move(self, t: torch.Tensor, sim) -> torch.Tensor:
         return t if t.device == sim.device else t.to(sim.device, non_blocking=True)

@@ -40,7 +40,8 @@ class NumpyCellStore:
     def drop_halo(self):
         self.rows, self.owned = self.rows[self.owned], self.owned[self.owned]
 
-    # the message format of afv_pack_exchange / afv_finish_exchange: (cap+1, ROW), header [n_transfer, n_halo, 0, 0, 0]
+    # the message format of afv_pack_exchange / afv_finish_exchange: (cap+1, ROW), header [n_transfer, n_halo, 0, 0, 0],
+    # transfers in rows 1 .. n_transfer, halo rows from the back (halo row i at row cap - i)
     def pack_exchange(self, geo, cap):
         self.drop_halo()                              # copies of the previous exchange are retired by the pack pass
         x = geo.offset(self.rows[:, 0])               # minimum-image offset to the lower face (k_exchange_count / _pack)
@@ -52,9 +53,9 @@ class NumpyCellStore:
             assert len(a) + len(b) <= cap
             msg = np.zeros((cap + 1, ROW))
             msg[0, 0], msg[0, 1] = len(a), len(b)
-            msg[1:1 + len(a)] = a
-            msg[1 + len(a):1 + len(a) + len(b)] = b
-            msg[1:1 + len(a) + len(b), 0] += shift
+            msg[1:1 + len(a)] = a                       # transfers from the front ...
+            msg[cap - np.arange(len(b))] = b            # ... halo rows from the back (k_exchange_pack)
+            msg[1:, 0] += shift
             out.append(torch.from_numpy(msg))
         return out
 
@@ -64,7 +65,7 @@ class NumpyCellStore:
         for m in (from_left, from_right):
             na, nb = int(m[0, 0]), int(m[0, 1])
             self.append(m[1:1 + na].clone(), False)
-            self.append(m[1 + na:1 + na + nb].clone(), True)
+            self.append(m[cap - torch.arange(nb)].clone(), True)
 
 
 def _worker(rank, world, port, L, N, halo, q):
