@@ -385,7 +385,7 @@ def run_ours(args) -> dict:
 
 def verify_sharded(torch, dist, afv, SlabShardedSimulator, phys, rank, world, local, stream, n_total=200_000, steps=30) -> dict:
     """The real multi-rank path against one handle: n_total cells stepped `steps` times (a) sharded over the ranks of this
-    run, exchanging over NCCL, with the late-cell overlap, and (b) as a single periodic handle on rank 0.  Positions must
+    run, exchanging over NCCL (both step forms), and (b) as a single periodic handle on rank 0.  Positions must
     agree bit for bit (results do not depend on the number of GPUs); also checked: no cell lost or duplicated, no ring
     look-up miss, zero net force."""
     L = float(np.sqrt(n_total / DENSITY))
@@ -396,9 +396,14 @@ def verify_sharded(torch, dist, afv, SlabShardedSimulator, phys, rank, world, lo
     owner = np.minimum((pts[:, 0] // W).astype(int), world - 1)
     mine = owner == rank
     gids = np.flatnonzero(mine)
+    # half of the steps exchange-then-step (the form the bench times), half with the late-cell overlap
     sim = SlabShardedSimulator(pts[mine], theta[mine], phys, L, rank=rank, world=world, device=local, stream=stream.cuda_stream,
-                               gids=gids, overlap=True)
-    sim.step(STEP["dt"], STEP["mu"], STEP["v0"], STEP["Dr"], seed=11, n_steps=steps)
+                               gids=gids, overlap=False)
+    sim.step(STEP["dt"], STEP["mu"], STEP["v0"], STEP["Dr"], seed=11, n_steps=steps // 2)
+    sim._refresh_halo()
+    sim.overlap = True
+    sim._xs = torch.cuda.Stream(sim.device, priority=-1)
+    sim.step(STEP["dt"], STEP["mu"], STEP["v0"], STEP["Dr"], seed=11, n_steps=steps - steps // 2)
     res = sim.build()
     diag = np.zeros(4, dtype=np.int64)
     sim._h.call("afv_get_diagnostics", diag.ctypes.data)
@@ -435,7 +440,7 @@ def verify_sharded(torch, dist, afv, SlabShardedSimulator, phys, rank, world, lo
         else:
             max_dx = max_df = net = float("nan")
         fscale = float(np.abs(rf).max())
-        out = {"cells": n_total, "steps": steps, "ranks": world, "transport": "NCCL, late-cell overlap", "cells_conserved": bool(conserved),
+        out = {"cells": n_total, "steps": steps, "ranks": world, "transport": "NCCL; half of the steps exchange-then-step, half with the late-cell overlap", "cells_conserved": bool(conserved),
                "max_dx": max_dx, "max_dF": max_df, "bit_identical": bool(conserved and max_dx == 0.0 and max_df == 0.0),
                "lookup_misses": int(misses.item()), "net_force_over_max_force": net / fscale if fscale else None,
                "ok": bool(conserved and max_dx <= 1e-9 and int(misses.item()) == 0 and net <= 1e-9 * max(1.0, fscale) * np.sqrt(n_total))}

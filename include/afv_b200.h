@@ -188,6 +188,11 @@ int afv_finish_pair(AfvHandle h, const double *in0_dev, const double *in1_dev, i
 int afv_pack_exchange(AfvHandle h, double lo, double hi, double halo, double shift_left, double shift_right,
                       double *msg_left_dev, double *msg_right_dev, int64_t cap_rows);
 int afv_finish_exchange(AfvHandle h, const double *in_left_dev, const double *in_right_dev, int64_t cap_rows);
+/* afv_finish_exchange followed by one step (afv_step with n_steps = 1 and the built-in generator), ordered so that the
+ * GPU never waits for the host: the received rows are appended and the cell list of the step is built with the counts
+ * still on the device, and the host's one synchronisation of the step (to read them) overlaps those launches. */
+int afv_finish_exchange_step(AfvHandle h, const double *in_left_dev, const double *in_right_dev, int64_t cap_rows, double dt, double mu,
+                             double v0, double Dr, uint64_t seed, int64_t step);
 /* Exchange overlapped with the geometry of the interior cells, exact for any displacement ("late cells").  Per step:
  *   afv_late_step_begin   handle's stream: sort of the cells on the device, geometry of the interior cells;
  *   afv_late_finish       exchange stream: one synchronisation (of that stream only) for the counts of the messages

@@ -21,7 +21,7 @@ SYMBOLS = [
     "afv_get_coord_nums", "afv_get_num_connections", "afv_get_connections", "afv_get_num_ring_entries", "afv_get_rings",
     "afv_get_diagnostics", "afv_set_profiling", "afv_get_stage_times", "afv_launch_count", "afv_host_alloc",
     "afv_host_free", "afv_measure_fp64_peak", "afv_device_ptr", "afv_stream", "afv_synchronize", "afv_set_deferred_checks",
-    "afv_set_slab", "afv_set_cells_device", "afv_extract_slab", "afv_drop_halo", "afv_append_cells", "afv_num_owned", "afv_pack_owned", "afv_pack_pair", "afv_finish_pair", "afv_pack_exchange", "afv_finish_exchange", "afv_late_step_begin", "afv_late_finish", "afv_late_step_end", "afv_stream_wait", "afv_get_exchange_stats",
+    "afv_set_slab", "afv_set_cells_device", "afv_extract_slab", "afv_drop_halo", "afv_append_cells", "afv_num_owned", "afv_pack_owned", "afv_pack_pair", "afv_finish_pair", "afv_pack_exchange", "afv_finish_exchange", "afv_finish_exchange_step", "afv_late_step_begin", "afv_late_finish", "afv_late_step_end", "afv_stream_wait", "afv_get_exchange_stats",
     "afv_cluster_analysis", "afv_get_cluster_labels", "afv_get_cluster_sizes", "afv_components_of_edges",
     "afv_get_energy", "afv_get_cell_energies", "afv_relax",
 ]
@@ -96,6 +96,7 @@ def load() -> C.CDLL:
         "afv_finish_pair": (C.c_int, [H, P, P, I64, C.c_int, C.c_int]),
         "afv_pack_exchange": (C.c_int, [H, D, D, D, D, D, P, P, I64]),
         "afv_finish_exchange": (C.c_int, [H, P, P, I64]),
+        "afv_finish_exchange_step": (C.c_int, [H, P, P, I64, D, D, D, D, C.c_uint64, I64]),
         "afv_late_step_begin": (C.c_int, [H, I64]),
         "afv_late_finish": (C.c_int, [H, P, P, I64, P]),
         "afv_late_step_end": (C.c_int, [H, D, D, D, D, C.c_uint64, I64, D, D, D, D, D, P, P, I64, P]),

@@ -101,6 +101,8 @@ struct AfvContext {
     // pair exchange state (afv_pack_pair -> afv_finish_pair)
     int *pair_cnt = nullptr;       // device: list lengths of the last pack (2 for the pair form, 4 for the exchange)
     int *xch_work = nullptr;       // device int[8]: working counters of k_exchange_pack (zero between launches)
+    int *n_all_dev = nullptr;      // device: cell count after an append whose counts the host has not read yet
+    cudaEvent_t ev_counts = nullptr;
     double *pair_host = nullptr;   // pinned [20]: counts sent / received, the deferred flags, the displacement slots
     double *pair_dev = nullptr;    // device [20]
     double pair_rng[4] = {0, 0, 0, 0};
@@ -328,10 +330,15 @@ int upload_grid_periodic(AfvHandle h) {
 
 // The cell list: counting sort by bin (k_bin_count, exclusive scan, k_bin_scatter).  Cells marked dead by the exchange land
 // behind the live ones and are dropped here.
-int stage_sort(AfvHandle h) {
+// n_dev != nullptr: the number of cells (h->n is then only what the host knows so far) is read on the device, the launches
+// cover n_upper cells; the caller finishes the bookkeeping with sort_booked() once it has the count.
+void sort_booked(AfvHandle h, int64_t n_all) {
+    h->n = n_all - h->n_dead; h->n_dead = 0;
+    h->n_main = h->n; h->n_late = 0; h->late_deep = false;
+}
+int stage_sort(AfvHandle h, const int *n_dev = nullptr, int64_t n_upper = 0) {
     StageTimer t(h, 0);
-    const int n_all = (int)h->n;
-    const int n = (int)(h->n - h->n_dead);
+    const int n_all = (int)(n_dev ? n_upper : h->n);
     const int c = h->cur, o = 1 - c;
     if (h->L > 0.0) {
         int rc = upload_grid_periodic(h);
@@ -348,15 +355,14 @@ int stage_sort(AfvHandle h) {
     if (h->L > 0.0) nbins = h->grid_host.nbx * h->grid_host.nby;
     const unsigned dead_key = (unsigned)nbins;
     CK(cudaMemsetAsync(h->bin_cnt, 0, (size_t)(nbins + 2) * sizeof(int), h->stream));
-    k_bin_count<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->xy[c], h->owned[c], n_all, h->d_grid, dead_key, h->keys, h->bin_cnt);
+    k_bin_count<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->xy[c], h->owned[c], n_all, n_dev, h->d_grid, dead_key, h->keys, h->bin_cnt);
     size_t tmp = h->cub_tmp_bytes;
     CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp, tmp, h->bin_cnt, h->bin_start, nbins + 2, h->stream));
-    k_bin_scatter<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->keys, n_all, dead_key, h->bin_start, h->bin_cnt, h->xy[c], h->th[c], h->a0[c],
+    k_bin_scatter<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->keys, n_all, n_dev, dead_key, h->bin_start, h->bin_cnt, h->xy[c], h->th[c], h->a0[c],
                                                             h->gid[c], h->owned[c], h->xy[o], h->th[o], h->a0[o], h->gid[o], h->owned[o],
                                                             h->keys_sorted, h->gid_is_perm ? h->slot_of_gid : nullptr);
     h->cur = o;
-    h->n = n; h->n_dead = 0;
-    h->n_main = n; h->n_late = 0; h->late_deep = false;
+    if (!n_dev) sort_booked(h, h->n);
     if (h->L > 0.0) h->h_flags[3] = nbins;
     h->launches += 3;  // count, scan, scatter
     CK(cudaGetLastError());
@@ -555,7 +561,7 @@ int afv_create(int device, const AfvParams *params, double box_L, void *stream, 
         cudaMalloc((void **)&h->ovf_arc_pts, (size_t)OVF_MAX * ARC_SLOW * sizeof(double4)) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; afv_destroy(h); return AFV_ERR_CUDA;
     }
-    if (cudaMalloc((void **)&h->xch_work, 8 * sizeof(int)) != cudaSuccess || cudaMemset(h->xch_work, 0, 8 * sizeof(int)) != cudaSuccess ||
+    if (cudaMalloc((void **)&h->n_all_dev, sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->xch_work, 8 * sizeof(int)) != cudaSuccess || cudaMemset(h->xch_work, 0, 8 * sizeof(int)) != cudaSuccess ||
         cudaMalloc((void **)&h->pair_cnt, 4 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&h->pair_dev, 20 * sizeof(double)) != cudaSuccess ||
         cudaHostAlloc((void **)&h->pair_host, 20 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
         g_create_error = "cudaMalloc failed"; afv_destroy(h); return AFV_ERR_CUDA;
@@ -574,8 +580,8 @@ void afv_destroy(AfvHandle h) {
     cudaFree(h->d_grid); cudaFree(h->flags); cudaFree(h->bbox_part);
     cudaFree(h->ovf_cells); cudaFree(h->ovf_len); cudaFree(h->ovf_hull); cudaFree(h->ovf_m); cudaFree(h->ovf_ring_h); cudaFree(h->ovf_ring_nbr);
     cudaFree(h->ovf_arc_key); cudaFree(h->ovf_arc_pts);
-    cudaFree(h->pair_cnt); cudaFree(h->xch_work); cudaFree(h->pair_dev); cudaFreeHost(h->pair_host);
-    for (cudaEvent_t e : {h->ev_sorted, h->ev_late, h->ev_force, h->ev_pack, h->ev_interior}) if (e) cudaEventDestroy(e);
+    cudaFree(h->pair_cnt); cudaFree(h->xch_work); cudaFree(h->n_all_dev); cudaFree(h->pair_dev); cudaFreeHost(h->pair_host);
+    for (cudaEvent_t e : {h->ev_sorted, h->ev_late, h->ev_force, h->ev_pack, h->ev_interior, h->ev_counts}) if (e) cudaEventDestroy(e);
     for (DevBuf *b : {&h->late_keys, &h->late_keys_sorted, &h->late_perm, &h->late_tmp}) cudaFree(b->p);
     for (DevBuf *b : {&h->scratch_a, &h->scratch_b, &h->noise_buf, &h->conn_buf, &h->ring_types, &h->ring_xy, &h->ring_off,
                       &h->cc_parent, &h->cc_flag, &h->cc_rank, &h->cc_labels, &h->cc_sizes, &h->cc_tmp, &h->cc_edges,

@@ -78,9 +78,11 @@ __global__ void k_bbox_final(const double *__restrict__ part, int nblocks, doubl
 // Cells marked CELL_DEAD (stale halo copies, see k_exchange_pack) get `dead_key`, the bin behind every real one: they
 // land behind the live cells, where the scatter drops them.
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_bin_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, const GridDesc *__restrict__ gp,
-                            unsigned dead_key, unsigned *__restrict__ keys, int *__restrict__ bin_cnt) {
+// n_dev (may be null): the cell count lives on the device (the host launched for an upper bound and has not read it yet)
+__global__ void k_bin_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, const int *__restrict__ n_dev,
+                            const GridDesc *__restrict__ gp, unsigned dead_key, unsigned *__restrict__ keys, int *__restrict__ bin_cnt) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n = *n_dev;
     if (i >= n) return;
     unsigned key = dead_key;
     if (owned[i] != CELL_DEAD) {
@@ -97,12 +99,14 @@ __global__ void k_bin_count(const double2 *__restrict__ xy, const unsigned char 
 
 // (c): cell i takes the slot bin_start[key] + (count left in its bin) - 1; the counts are back at zero afterwards.  Dead
 // cells are dropped.  slot_of_gid (may be null): where the caller's cell gid went (fixed-order reductions).
-__global__ void k_bin_scatter(const unsigned *__restrict__ keys, int n, unsigned dead_key, const int *__restrict__ bin_start, int *__restrict__ bin_cnt,
+__global__ void k_bin_scatter(const unsigned *__restrict__ keys, int n, const int *__restrict__ n_dev, unsigned dead_key,
+                              const int *__restrict__ bin_start, int *__restrict__ bin_cnt,
                               const double2 *__restrict__ xy0, const double *__restrict__ t0, const double *__restrict__ a0,
                               const int64_t *__restrict__ g0, const unsigned char *__restrict__ o0, double2 *__restrict__ xy1,
                               double *__restrict__ t1, double *__restrict__ a1, int64_t *__restrict__ g1, unsigned char *__restrict__ o1,
                               unsigned *__restrict__ keys_sorted, int *__restrict__ slot_of_gid) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n = *n_dev;
     if (i >= n) return;
     const unsigned key = keys[i];
     const int left = atomicSub(&bin_cnt[key], 1);
@@ -637,10 +641,17 @@ __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__rest
 }
 // received messages -> cells appended behind slot `base`: [left transfers][left halo][right transfers][right halo];
 // with `perm` (late cells, sorted by bin among themselves) row perm[i] of that sequence goes to slot base + i
+// nl < 0: the four counts are read from the message headers on the device (clamped to the capacity; the host has not seen
+// them yet) and the new cell count base + nl + nr goes to n_all_dev
 __global__ void k_exchange_append(const double *__restrict__ in_left, const double *__restrict__ in_right, int nl_own, int nl, int nr_own,
                                   int nr, int base, int cap, const int *__restrict__ perm, double2 *__restrict__ xy, double *__restrict__ th,
-                                  double *__restrict__ a0, int64_t *__restrict__ gid, unsigned char *__restrict__ owned) {
+                                  double *__restrict__ a0, int64_t *__restrict__ gid, unsigned char *__restrict__ owned, int *__restrict__ n_all_dev) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nl < 0) {
+        nl_own = min((int)in_left[0], cap); nl = nl_own + min((int)in_left[1], cap - nl_own);
+        nr_own = min((int)in_right[0], cap); nr = nr_own + min((int)in_right[1], cap - nr_own);
+        if (i == 0) *n_all_dev = base + nl + nr;
+    }
     if (i >= nl + nr) return;
     const int src = perm ? perm[i] : i;
     const bool left = src < nl;

@@ -85,6 +85,11 @@ class GpuCellStore:
     def finish_exchange(self, from_left: torch.Tensor, from_right: torch.Tensor, cap: int) -> None:
         self.h.call("afv_finish_exchange", from_left.data_ptr(), from_right.data_ptr(), int(cap))
 
+    def finish_exchange_step(self, from_left: torch.Tensor, from_right: torch.Tensor, cap: int, dt, mu, v0, Dr, seed, step_index) -> None:
+        """finish_exchange + one step; the host's synchronisation for the counts overlaps the cell-list launches."""
+        self.h.call("afv_finish_exchange_step", from_left.data_ptr(), from_right.data_ptr(), int(cap), float(dt), float(mu), float(v0),
+                    float(Dr), C.c_uint64(int(seed)), C.c_int64(int(step_index)))
+
     # -- exchange overlapped with the interior geometry: the received rows become "late" cells (afv_late_*) --
     def late_begin(self, cap: int) -> None:
         self.h.call("afv_late_step_begin", int(cap))
@@ -348,8 +353,14 @@ class SlabShardedSimulator:
         travels while the step sorts its cells and builds its interior geometry."""
         for _ in range(n_steps):
             if not self.overlap:
-                self._refresh_halo()
-                self.compute_step(dt, mu, v0, Dr, seed)
+                if self._sent is not None and self._inbox is None and not self._halo_fresh:
+                    # the usual case inside a loop: finish the exchange issued behind the last update and step, in one call
+                    inbox, self._sent = self._sent, None
+                    self.store.finish_exchange_step(inbox[0], inbox[1], self._caps()[0], dt, mu, v0, Dr, seed, self._step_index)
+                    self._step_index += 1
+                else:
+                    self._refresh_halo()
+                    self.compute_step(dt, mu, v0, Dr, seed)
                 # The next exchange is packed and handed to NCCL right away, behind the update on the same stream: the host
                 # side of that (torch's P2P batch: >= 0.1 ms) runs while the GPU is still busy with this step, instead of
                 # leaving it idle at the start of the next one.  The counts are read (one synchronisation) when the next
@@ -481,6 +492,10 @@ class LoopbackShardedSimulator:
         if all(s._inbox is not None for s in self.ranks):      # left over from the overlapped form
             for sim in self.ranks:
                 sim._refresh_halo()
+        elif all(s._sent is not None for s in self.ranks):     # issued behind the last update
+            for sim in self.ranks:
+                inbox, sim._sent = sim._sent, None
+                sim.exchange_in(self._move(inbox[0], sim), self._move(inbox[1], sim))
         else:
             for sim, inbox in zip(self.ranks, loopback_exchange([s.exchange_out() for s in self.ranks])):
                 sim.exchange_in(self._move(inbox[0], sim), self._move(inbox[1], sim))
@@ -488,9 +503,19 @@ class LoopbackShardedSimulator:
     def step(self, dt, mu=1.0, v0=0.0, Dr=0.0, *, seed=0, n_steps=1) -> None:
         for _ in range(n_steps):
             if not self.overlap:
-                self._refresh_halo()
-                for sim in self.ranks:
-                    sim.compute_step(dt, mu, v0, Dr, seed)
+                if self.world > 1 and all(s._sent is not None and not s._halo_fresh for s in self.ranks):
+                    for sim in self.ranks:     # the exchange issued behind the last update: finish it and step, in one call
+                        inbox, sim._sent = sim._sent, None
+                        sim.store.finish_exchange_step(self._move(inbox[0], sim), self._move(inbox[1], sim), sim._caps()[0], dt, mu, v0, Dr, seed,
+                                                       sim._step_index)
+                        sim._step_index += 1
+                else:
+                    self._refresh_halo()
+                    for sim in self.ranks:
+                        sim.compute_step(dt, mu, v0, Dr, seed)
+                if self.world > 1:             # as SlabShardedSimulator.step: the next exchange right behind the update
+                    for sim, inbox in zip(self.ranks, loopback_exchange([s.exchange_out() for s in self.ranks])):
+                        sim._sent = inbox
                 continue
             if any(s._inbox is None for s in self.ranks):
                 for sim in self.ranks:
