@@ -144,3 +144,27 @@ def test_decompose_points_one_domain_allows_zero_span_axes():
         (d,) = afv.decompose_points(pts, grid_shape=(1, 1), halo_width=0.5)
         assert np.array_equal(d.local_global_ids, np.arange(len(pts))) and np.array_equal(d.owned_local_ids, np.arange(len(pts)))
         assert np.array_equal(d.local_pts, pts) and d.halo_x_range == (pts[:, 0].min() - 0.5, pts[:, 0].max() + 0.5)
+
+
+def test_decompose_points_equals_the_live_reference_if_available():
+    """When oracle/_ref (the compiled, unmodified reference) is present: every field of every domain is identical to the
+    reference's decompose_points (pyafv/parallel_voronoi.py:125-338), for all three of its methods."""
+    import build_ref
+    if not build_ref.ref_available():
+        pytest.skip("oracle/_ref not built on this machine")
+    ref = build_ref.import_reference()
+    rng = np.random.default_rng(12)
+    for shape, halo, N in (((4, 3), 0.4, 100), ((2, 2), 0.1, 6), ((1, 1), 0.5, 3), ((5, 1), 1.3, 500), ((3, 4), 0.0, 200)):
+        pts = rng.random((N, 2)) * np.array([8.0, 5.0])
+        k = min(6, N)
+        pts[:k] = np.array([[0, 0], [4, 0], [8, 0], [0, 5], [4, 5], [8, 5]], dtype=float)[:k]     # points on the domain boundaries
+        for bounds in (None, ((0.0, 8.0), (0.0, 5.0))):
+            for m in ("dense", "binned", "sorted_x"):
+                a = afv.decompose_points(pts, shape, halo, domain_bounds=bounds, method=m)
+                b = ref.decompose_points(pts, shape, halo, domain_bounds=bounds, method=m)
+                assert len(a) == len(b)
+                for da, db in zip(a, b):
+                    for f in ("domain_id", "grid_ix", "grid_iy", "x_range", "y_range", "halo_x_range", "halo_y_range"):
+                        assert getattr(da, f) == getattr(db, f), f
+                    assert np.array_equal(da.local_global_ids, db.local_global_ids)
+                    assert np.array_equal(da.owned_local_ids, db.owned_local_ids) and np.array_equal(da.local_pts, db.local_pts)
