@@ -63,6 +63,7 @@ struct AfvContext {
     // cell list
     unsigned *keys = nullptr, *keys_sorted = nullptr;
     int *iota = nullptr, *perm = nullptr, *bin_start = nullptr, *bin_cnt = nullptr;
+    bool bin_cnt_zero = false;     // every counter is zero (k_bin_scatter counts them back down)
     int *slot_of_gid = nullptr;     // where the caller's cell gid sits in the sorted order (handles filled by afv_set_positions)
     int nbins_cap = 0, key_bits = 0;
     GridDesc *d_grid = nullptr;
@@ -218,6 +219,7 @@ int reserve(AfvHandle h, int64_t want, int64_t keep) {
     if ((rc = dev_alloc(h, &h->perm, cap))) return rc;
     if ((rc = dev_alloc(h, &h->bin_start, (size_t)h->nbins_cap + 2))) return rc;
     if ((rc = dev_alloc(h, &h->bin_cnt, (size_t)h->nbins_cap + 2))) return rc;
+    h->bin_cnt_zero = false;
     if ((rc = dev_alloc(h, &h->slot_of_gid, cap))) return rc;
     if ((rc = dev_alloc(h, &h->bin_start_late, (size_t)h->nbins_cap + 2))) return rc;
     if ((rc = dev_alloc(h, &h->fx, cap))) return rc;
@@ -354,8 +356,12 @@ int stage_sort(AfvHandle h, const int *n_dev = nullptr, int64_t n_upper = 0) {
     int nbins = h->nbins_cap;
     if (h->L > 0.0) nbins = h->grid_host.nbx * h->grid_host.nby;
     const unsigned dead_key = (unsigned)nbins;
-    CK(cudaMemsetAsync(h->bin_cnt, 0, (size_t)(nbins + 2) * sizeof(int), h->stream));
-    k_bin_count<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->xy[c], h->owned[c], n_all, n_dev, h->d_grid, dead_key, h->keys, h->bin_cnt);
+    if (!h->bin_cnt_zero) {   // fresh allocation; afterwards k_bin_scatter leaves every counter at zero
+        CK(cudaMemsetAsync(h->bin_cnt, 0, ((size_t)h->nbins_cap + 2) * sizeof(int), h->stream));
+        h->bin_cnt_zero = true;
+    }
+    // (thread 0 also restarts the queue of the slow path: flags[0])
+    k_bin_count<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->xy[c], h->owned[c], n_all, n_dev, h->d_grid, dead_key, h->keys, h->bin_cnt, h->flags);
     size_t tmp = h->cub_tmp_bytes;
     CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp, tmp, h->bin_cnt, h->bin_start, nbins + 2, h->stream));
     k_bin_scatter<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->keys, n_all, n_dev, dead_key, h->bin_start, h->bin_cnt, h->xy[c], h->th[c], h->a0[c],
@@ -428,7 +434,7 @@ int stage_geometry(AfvHandle h, GeomPass gp = GeomPass()) {
         StageTimer t(h, 5, st);
         // cells queued by the fast kernels (usually none): large-capacity path, reads the queue length on the device
         a.filter = 0;
-        k_geometry_slow<<<16, 64, 0, st>>>(a);
+        k_geometry_slow<<<148, 64, 0, st>>>(a);
         h->launches += 1;
     }
     CK(cudaGetLastError());
@@ -736,7 +742,7 @@ int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t s
     const bool deferred = h->defer_checks && !noise_host;
     if (!deferred) CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
     for (int s = 0; s < n_steps; ++s) {
-        CK(cudaMemsetAsync(h->flags, 0, sizeof(int), h->stream));   // the slow-path queue restarts every step (the error counters run on)
+        // (the slow-path queue, flags[0], restarts with every cell list: k_bin_count; the error counters run on)
         if ((rc = stage_sort(h))) return rc;
         // open boundaries: the local density is unknown, so the capacity is checked (and grown) before the positions move
         if ((rc = (h->L > 0.0 ? stage_geometry(h) : geometry_checked(h)))) return rc;

@@ -119,10 +119,40 @@ __device__ __forceinline__ int cell_rows(const int nline, const bool per, int li
 #define GEOM_TPB_ 128
 #endif
 constexpr int GEOM_TPB = GEOM_TPB_;
+#ifndef NBRS_MIN_BLOCKS
+#define NBRS_MIN_BLOCKS 8
+#endif
 constexpr int KP = 14;           // polygon edges on the fast path (<= 16: the order of the slots is a sequence of 4-bit ids)
 constexpr int CMAX_HARD = 128;   // upper bound of the per-cell neighbour list (the launch picks cmax <= this)
 constexpr int NB_OVERFLOW = 255; // nb_cnt: more neighbours within 2r than the list holds
 constexpr int LAB_SIDE = -2;     // polygon-edge labels LAB_SIDE - q: side q of the bounding square (labels >= 0: sorted slots)
+
+// One contiguous run of sorted slots [c_begin, c_end) against cell s at (xi, yi): the slots within 2r are appended at wp
+// (stride apart, up to wend), the nearest is tracked.  The body is short and branch-free on purpose: two of three
+// candidates fail the distance test, and a divergent accept branch would run for nearly every candidate with a third of
+// the lanes.  WRAP: minimum image (cells in the outermost bins of a periodic direction; every cell of a slab grid).
+template <bool WRAP>
+__device__ __forceinline__ void scan_run(const double2 *__restrict__ xy, const int c_begin, const int c_end, const int s, const double xi,
+                                         const double yi, const double cut2, const bool wrapx, const bool wrapy, const GridDesc &g,
+                                         const size_t stride, int *const wend, int *&wp, double &dmin, int &smin, bool &tie, bool &ok) {
+    const double Lx = wrapx ? g.Lx : 0.0, hx = wrapx ? g.halfLx : 1e300, Ly = wrapy ? g.Ly : 0.0, hy = wrapy ? g.halfLy : 1e300;
+#pragma unroll 4
+    for (int c = c_begin; c < c_end; ++c) {
+        const double2 pc = __ldg(xy + c);
+        double dx = pc.x - xi, dy = pc.y - yi;
+        if (WRAP) { dx = min_image(dx, Lx, hx); dy = min_image(dy, Ly, hy); }   // (a direction that does not wrap: h = 1e300)
+        const double d2 = dx * dx + dy * dy;
+        const bool acc = d2 < cut2 && d2 > 0.0;               // (the cell itself: d2 == 0)
+        const bool lt = acc && d2 < dmin, eq = acc && d2 == dmin;
+        tie = eq || (tie && !lt);             // several cells at exactly the smallest distance so far
+        dmin = lt ? d2 : dmin;
+        smin = lt ? c : smin;
+        const bool put = acc && wp != wend;
+        if (put) *wp = c;
+        wp += put ? stride : 0;
+        ok = ok && (put || !acc);
+    }
+}
 
 // ------------------------------------------------------------------------------------------------------
 // K2a: neighbour lists.  One thread per cell: the sorted slots of all cells within 2r, from the 3 bin rows (<= 2
@@ -132,7 +162,7 @@ constexpr int LAB_SIDE = -2;     // polygon-edge labels LAB_SIDE - q: side q of 
 // compiled in).  SLAB = true: an x-slab -- columns contiguous, pass filters, the late cells' bin table.
 // ------------------------------------------------------------------------------------------------------
 template <bool SLAB>
-__global__ void __launch_bounds__(128) k_nbrs(GeomArgs a, const int cmax) {
+__global__ void __launch_bounds__(128, NBRS_MIN_BLOCKS) k_nbrs(GeomArgs a, const int cmax) {
     const int t_ = blockIdx.x * blockDim.x + threadIdx.x;
     if (t_ >= a.n) return;
     const int s = SLAB ? slot_of_thread(a, t_) : t_;
@@ -152,9 +182,11 @@ __global__ void __launch_bounds__(128) k_nbrs(GeomArgs a, const int cmax) {
     int rows[3];
     const int nrow = cell_rows(nline, per_line, g.swap ? bx : by, rows);
     int *const list = a.nb_list + s;
-    int n = 0, smin = -1;
-    bool ok = true;
-    double dmin = 1e300, mdx = 0.0, mdy = 0.0;
+    int *wp = list;                                       // next free entry of the list
+    int *const wend = list + (size_t)cmax * a.stride;
+    int smin = -1;
+    bool ok = true, tie = false;
+    double dmin = 1e300;
     for (int tab = 0; tab < (SLAB ? 2 : 1); ++tab) {     // the sorted cells, then (face pass of a slab) the late cells
         const int *const bin_start = tab ? a.bin_start_late : a.bin_start;
         if (!bin_start) break;
@@ -163,21 +195,32 @@ __global__ void __launch_bounds__(128) k_nbrs(GeomArgs a, const int cmax) {
             int c0[2], c1[2];
             const int nrun = row_runs(npos, per_pos, bin_start, rows[ir], pos, c0, c1);
             for (int q = 0; q < nrun; ++q) {
-#pragma unroll 4
-                for (int c = first + c0[q]; c < first + c1[q]; ++c) {
-                    const double2 pc = a.xy[c];
-                    double dx = pc.x - xi, dy = pc.y - yi;
-                    if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
-                    if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
-                    const double d2 = dx * dx + dy * dy;
-                    if (d2 < cut2 && c != s && d2 > 0.0) {
-                        // nearest neighbour; among equals (lattices) the smallest displacement: the ring start must not
-                        // depend on the order the candidates are met in
-                        if (d2 < dmin || (d2 == dmin && (dx < mdx || (dx == mdx && dy < mdy)))) { dmin = d2; smin = c; mdx = dx; mdy = dy; }
-                        if (n < cmax) { list[(size_t)n * a.stride] = c; ++n; }
-                        else ok = false;
+                if (wrapx || wrapy) scan_run<true>(a.xy, first + c0[q], first + c1[q], s, xi, yi, cut2, wrapx, wrapy, g, a.stride, wend, wp, dmin, smin, tie, ok);
+                else scan_run<false>(a.xy, first + c0[q], first + c1[q], s, xi, yi, cut2, false, false, g, a.stride, wend, wp, dmin, smin, tie, ok);
+            }
+        }
+    }
+    const int n = (int)((size_t)(wp - list) / a.stride);
+    if (tie) {
+        // nearest neighbour among equals (lattices): the smallest displacement -- the ring start must not depend on the
+        // order the candidates are met in.  Rare: scan the runs once more.
+        double mdx = 0.0, mdy = 0.0;
+        bool have = false;
+        for (int tab = 0; tab < (SLAB ? 2 : 1); ++tab) {
+            const int *const bin_start = tab ? a.bin_start_late : a.bin_start;
+            if (!bin_start) break;
+            const int first = tab ? a.n_main : 0;
+            for (int ir = 0; ir < nrow; ++ir) {
+                int c0[2], c1[2];
+                const int nrun = row_runs(npos, per_pos, bin_start, rows[ir], pos, c0, c1);
+                for (int q = 0; q < nrun; ++q)
+                    for (int c = first + c0[q]; c < first + c1[q]; ++c) {
+                        const double2 pc = a.xy[c];
+                        double dx = pc.x - xi, dy = pc.y - yi;
+                        if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
+                        if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
+                        if (c != s && dx * dx + dy * dy == dmin && (!have || dx < mdx || (dx == mdx && dy < mdy))) { have = true; smin = c; mdx = dx; mdy = dy; }
                     }
-                }
             }
         }
     }
@@ -781,9 +824,17 @@ __device__ __noinline__ int clip_cell_slow(const GeomArgs &a, const int s, const
     return m;
 }
 
+// The queue is usually a handful of cells and each is a long serial job: they are spread over the launch, one cell per
+// warp (and one warp per block first) as long as there are warps to spare, so that the kernel lasts as long as its
+// longest cell and not as long as a warp's worth of divergent ones.
 __global__ void __launch_bounds__(64) k_geometry_slow(GeomArgs a) {
     const int cnt = min(a.flags[0], OVF_MAX);
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x) {
+    const int T = gridDim.x * blockDim.x;
+    const bool sparse = cnt * 32 <= T;                     // a warp for every queued cell: its lane 0 works
+    if (sparse && (threadIdx.x & 31) != 0) return;
+    const int job0 = sparse ? (threadIdx.x >> 5) * gridDim.x + blockIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
+    const int njob = sparse ? T / 32 : T;
+    for (int idx = job0; idx < cnt; idx += njob) {
         const int s = a.ovf_cells[idx];
         const int m0 = a.ovf_m[idx];
         const int m = m0 > 0 ? m0 : clip_cell_slow(a, s, idx);

@@ -80,8 +80,10 @@ __global__ void k_bbox_final(const double *__restrict__ part, int nblocks, doubl
 // ------------------------------------------------------------------------------------------------------
 // n_dev (may be null): the cell count lives on the device (the host launched for an upper bound and has not read it yet)
 __global__ void k_bin_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, const int *__restrict__ n_dev,
-                            const GridDesc *__restrict__ gp, unsigned dead_key, unsigned *__restrict__ keys, int *__restrict__ bin_cnt) {
+                            const GridDesc *__restrict__ gp, unsigned dead_key, unsigned *__restrict__ keys, int *__restrict__ bin_cnt,
+                            int *__restrict__ queue_count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *queue_count = 0;            // the queue of the slow path restarts with every cell list
     if (n_dev) n = *n_dev;
     if (i >= n) return;
     unsigned key = dead_key;
@@ -623,9 +625,9 @@ __global__ void __launch_bounds__(XCH_TPB) k_exchange_pack(const double2 *__rest
         double *row = ((q < 2) ? msg_left : msg_right) + 5 * (size_t)((q & 1) ? cap - r : r + 1);
         row[0] = p.x + ((q < 2) ? shift_left : shift_right); row[1] = p.y; row[2] = tv; row[3] = av; row[4] = gv;
     }
-    // the last block to finish publishes the counts
+    // the last block to finish publishes the counts (only warps that claimed rows have anything to order before the block count)
     __shared__ int s_last;
-    __threadfence();
+    if (__any_sync(FULL_MASK, m != 0u)) __threadfence();
     __syncthreads();
     if (t == 0) s_last = (atomicAdd(&work[6], 1) == (int)gridDim.x - 1);
     __syncthreads();

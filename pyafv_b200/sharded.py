@@ -384,39 +384,58 @@ class SlabShardedSimulator:
         return results_dict(self.compute_build())
 
     def e2e_measure(self, k: int, step: dict) -> dict:
-        """End-to-end leg of bench.py for N > 1: every step uploads this rank's cells from pinned host memory,
-        exchanges halos, advances one step, and reads the updated cells (and forces) back."""
+        """End-to-end leg of bench.py for N > 1, the same traffic per cell as the single-GPU leg: every step uploads the
+        positions of this rank's cells from pinned host memory (16 B / cell; angle, A0 and id stay resident), exchanges
+        transfers and halos, advances one step, and reads back position and id of the cells the rank owns afterwards
+        (24 B / cell)."""
         import time
         import torch.distributed as dist
         res = self.build()
         order = np.argsort(res["gids"])
         n = len(order)
-        host = torch.empty((n, ROW), dtype=torch.float64).pin_memory()
-        host[:, 0:2] = torch.from_numpy(res["pts"][order])
-        host[:, 2] = 0.0
-        host[:, 3] = self.phys.A0
-        host[:, 4] = torch.from_numpy(res["gids"][order])
-        dev = torch.empty((n, ROW), dtype=torch.float64, device=self.device)
-        out = torch.empty((n, RES_ROW), dtype=torch.float64).pin_memory()
-        dist.barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(k):
-            dev.copy_(host, non_blocking=True)
-            self.store.set_cells(dev, n)
+        host = torch.from_numpy(res["pts"][order]).contiguous().pin_memory()
+        rows = torch.empty((n, ROW), dtype=torch.float64, device=self.device)
+        rows[:, 2] = 0.0
+        rows[:, 3] = self.phys.A0
+        rows[:, 4] = torch.from_numpy(res["gids"][order].astype(np.float64)).to(self.device)
+        dev_pos = torch.empty((n, 2), dtype=torch.float64, device=self.device)
+        cols = torch.tensor([0, 1, 4], device=self.device)
+        cap_out = int(n * 1.25) + 64
+        dev_out = torch.empty((cap_out, 3), dtype=torch.float64, device=self.device)
+        out = torch.empty((cap_out, 3), dtype=torch.float64).pin_memory()
+        h2d = d2h = 0
+
+        def one_step():
+            nonlocal h2d, d2h
+            dev_pos.copy_(host, non_blocking=True)
+            rows[:, 0:2] = dev_pos
+            self.store.set_cells(rows, n)
             self._halo_fresh = False
+            self._sent = None
             self._refresh_halo()
             r = self.compute_step(step["dt"], step["mu"], step["v0"], step["Dr"], 7, want_results=True)
-            out[: r.shape[0]].copy_(r, non_blocking=True)
+            m = r.shape[0]
+            torch.index_select(r, 1, cols, out=dev_out[:m])
+            out[:m].copy_(dev_out[:m], non_blocking=True)
             torch.cuda.synchronize()
+            h2d += host.numel() * 8
+            d2h += m * 24
+
+        one_step()
+        dist.barrier(); torch.cuda.synchronize()
+        h2d = d2h = 0
+        t0 = time.perf_counter()
+        for _ in range(k):
+            one_step()
         dist.barrier()
         dt = time.perf_counter() - t0
-        tot = torch.tensor([float(n)], device=self.device, dtype=torch.float64)
+        tot = torch.tensor([float(n), float(h2d) / k, float(d2h) / k], device=self.device, dtype=torch.float64)
         dist.all_reduce(tot)
         tmax = torch.tensor([dt], device=self.device, dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        return {"value": float(tot.item()) * k / float(tmax.item()), "unit": "cell-steps/s", "h2d_bytes_per_step": 8 * ROW * n,
-                "d2h_bytes_per_step": 8 * RES_ROW * n, "steps": k,
-                "api": "SlabShardedSimulator: H2D cells (pinned) + halo exchange + step + D2H updated cells and forces, per rank"}
+        return {"value": float(tot[0].item()) * k / float(tmax.item()), "unit": "cell-steps/s", "h2d_bytes_per_step": int(tot[1].item()),
+                "d2h_bytes_per_step": int(tot[2].item()), "steps": k,
+                "api": "SlabShardedSimulator, per rank: H2D positions (pinned) + set_cells + exchange + step + D2H position and id of the owned cells"}
 
 
 def results_dict(res: torch.Tensor) -> dict[str, np.ndarray]:
