@@ -268,6 +268,16 @@ def run_ours(args) -> dict:
             tr = json.loads(traffic_file.read_text())
             if tr.get("cells") == n_local and tr.get("kernel") == roofline["kernel"]:
                 roofline["traffic"] = tr.get("dram_bytes_per_launch")
+                # what actually binds the kernel: warp instructions issued (counted by ncu for this launch shape) per second
+                # of the live launch time, against 4 schedulers x 1 instruction per clock per SM
+                wi = (tr.get("warp_instructions_per_launch") or {}).get(roofline["kernel"])
+                if wi:
+                    props = torch.cuda.get_device_properties(local)
+                    peak = 4.0 * props.multi_processor_count * props.clock_rate * 1e3 / 1e9     # Gwarp-inst/s at the boost clock
+                    ach = wi / (roofline["kernel_ms"] * 1e-3) / 1e9
+                    roofline["issue_slots"] = {"achieved": ach, "peak": peak, "unit": "Gwarp-inst/s", "frac": ach / peak,
+                                               "warp_instructions_per_launch": wi,
+                                               "under_ncu_pct_of_peak": (tr.get("under_ncu_pct_of_peak") or {}).get(roofline["kernel"])}
         except Exception:
             pass
 

@@ -103,7 +103,7 @@ struct AfvContext {
     int *pair_cnt = nullptr;       // device: list lengths of the last pack (2 for the pair form, 4 for the exchange)
     int *xch_work = nullptr;       // device int[8]: working counters of k_exchange_pack (zero between launches)
     int *n_all_dev = nullptr;      // device: cell count after an append whose counts the host has not read yet
-    cudaEvent_t ev_counts = nullptr;
+    cudaEvent_t ev_counts = nullptr, ev_copy = nullptr;
     double *pair_host = nullptr;   // pinned [20]: counts sent / received, the deferred flags, the displacement slots
     double *pair_dev = nullptr;    // device [20]
     double pair_rng[4] = {0, 0, 0, 0};
@@ -587,7 +587,7 @@ void afv_destroy(AfvHandle h) {
     cudaFree(h->ovf_cells); cudaFree(h->ovf_len); cudaFree(h->ovf_hull); cudaFree(h->ovf_m); cudaFree(h->ovf_ring_h); cudaFree(h->ovf_ring_nbr);
     cudaFree(h->ovf_arc_key); cudaFree(h->ovf_arc_pts);
     cudaFree(h->pair_cnt); cudaFree(h->xch_work); cudaFree(h->n_all_dev); cudaFree(h->pair_dev); cudaFreeHost(h->pair_host);
-    for (cudaEvent_t e : {h->ev_sorted, h->ev_late, h->ev_force, h->ev_pack, h->ev_interior, h->ev_counts}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->ev_sorted, h->ev_late, h->ev_force, h->ev_pack, h->ev_interior, h->ev_counts, h->ev_copy}) if (e) cudaEventDestroy(e);
     for (DevBuf *b : {&h->late_keys, &h->late_keys_sorted, &h->late_perm, &h->late_tmp}) cudaFree(b->p);
     for (DevBuf *b : {&h->scratch_a, &h->scratch_b, &h->noise_buf, &h->conn_buf, &h->ring_types, &h->ring_xy, &h->ring_off,
                       &h->cc_parent, &h->cc_flag, &h->cc_rank, &h->cc_labels, &h->cc_sizes, &h->cc_tmp, &h->cc_edges,
@@ -620,30 +620,33 @@ int afv_set_positions(AfvHandle h, const double *xy_host, int64_t N) {
     }
     const int n = (int)N;
     const int c = h->cur, o = 1 - c;
-    if (same && N > 0) {
-        // bring theta and A0 back to the caller's order, then reset the order
-        k_unsort_f64<<<nblk(n, 256), 256, 0, h->stream>>>(h->th[c], h->gid[c], n, h->th[o], 1, 0);
-        k_unsort_f64<<<nblk(n, 256), 256, 0, h->stream>>>(h->a0[c], h->gid[c], n, h->a0[o], 1, 0);
-        h->cur = o;
-        h->launches += 2;
-    } else if (N > 0) {
-        k_fill<<<nblk(n, 256), 256, 0, h->stream>>>(h->th[h->cur], n, 0.0);
-        k_fill<<<nblk(n, 256), 256, 0, h->stream>>>(h->a0[h->cur], n, h->prm.A0);
-        h->launches += 2;
-    }
+    const double wrapL = (h->L > 0.0 && !h->slab) ? h->L : 0.0;   // cells outside the box would miss their neighbours across the other face
     if (N > 0) {
-        // the caller's (N,2) row-major array is exactly the device layout
-        CK(cudaMemcpyAsync(h->xy[h->cur], xy_host, (size_t)N * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-        k_init_cells<<<nblk(n, 256), 256, 0, h->stream>>>(n, h->gid[h->cur], h->owned[h->cur]);
-        h->launches += 1;
-        if (h->L > 0.0 && !h->slab) {   // cells outside the box would miss their neighbours across the other face
-            k_wrap_box<<<nblk(n, 256), 256, 0, h->stream>>>(h->xy[h->cur], n, h->L);
+        // The caller's (N,2) row-major array is exactly the device layout.  The copy goes first and the host waits for it alone
+        // (xy_host is borrowed for the call only); the kernels behind it run while the caller is already issuing the next call.
+        double2 *const dst = same ? h->xy[o] : h->xy[c];
+        CK(cudaMemcpyAsync(dst, xy_host, (size_t)N * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+        if (!h->ev_copy) CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+        CK(cudaEventRecord(h->ev_copy, h->stream));
+        if (same) {
+            // theta and A0 back to the caller's order, ids and marks reset, positions wrapped: one pass
+            k_reset_order<<<nblk(n, 256), 256, 0, h->stream>>>(n, h->th[c], h->a0[c], h->gid[c], h->th[o], h->a0[o], h->gid[o], h->owned[o], h->xy[o], wrapL);
+            h->cur = o;
             h->launches += 1;
+        } else {
+            k_fill<<<nblk(n, 256), 256, 0, h->stream>>>(h->th[c], n, 0.0);
+            k_fill<<<nblk(n, 256), 256, 0, h->stream>>>(h->a0[c], n, h->prm.A0);
+            k_init_cells<<<nblk(n, 256), 256, 0, h->stream>>>(n, h->gid[c], h->owned[c]);
+            h->launches += 3;
+            if (wrapL > 0.0) {
+                k_wrap_box<<<nblk(n, 256), 256, 0, h->stream>>>(h->xy[c], n, wrapL);
+                h->launches += 1;
+            }
         }
     }
     h->n = N; h->n_owned = N; h->n_dead = 0; h->gid_is_perm = true; h->built = false;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));  // xy_host is borrowed for the call only
+    if (N > 0) CK(cudaEventSynchronize(h->ev_copy));
     return AFV_OK;
 }
 

@@ -429,6 +429,23 @@ __global__ void k_init_cells(int n, int64_t *__restrict__ gid, unsigned char *__
     if (i >= n) return;
     gid[i] = i; owned[i] = 1;
 }
+// afv_set_positions on a handle that keeps its cells: one pass brings theta and A0 back to the caller's order (scatter by id
+// into the other buffers), resets ids and ownership marks, and wraps the uploaded positions into the box (L > 0)
+__global__ void k_reset_order(int n, const double *__restrict__ th0, const double *__restrict__ a00, const int64_t *__restrict__ gid0,
+                              double *__restrict__ th1, double *__restrict__ a01, int64_t *__restrict__ gid1, unsigned char *__restrict__ owned1,
+                              double2 *__restrict__ xy1, double L) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t g = gid0[i];
+    th1[g] = th0[i]; a01[g] = a00[i];
+    gid1[i] = i; owned1[i] = 1;
+    if (L > 0.0) {
+        double2 q = xy1[i];
+        q.x -= L * floor(q.x / L); if (q.x >= L) q.x = 0.0;
+        q.y -= L * floor(q.y / L); if (q.y >= L) q.y = 0.0;
+        xy1[i] = q;
+    }
+}
 __global__ void k_unsort_xy(const double2 *__restrict__ src, const int64_t *__restrict__ gid, int n, double2 *__restrict__ out) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < n) out[gid[s]] = src[s];

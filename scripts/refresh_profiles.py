@@ -20,14 +20,22 @@ with open(f"{P}r2_bench_launch_shares.txt", "w") as f:
             "# (cold-cache, serialised: compare SHARES with roofline.stage_ms_per_step of the bench line, not absolute times)\n")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k:62s} launches {n:4d}  total {t/1e3:10.1f} us  share {100*t/tot:5.1f}%\n")
-def traffic(rep):
+def raw_metrics(rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw))); h, u, v = rows[0], rows[1], rows[2]
-    val = lambda name: float(v[h.index(name)]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u[h.index(name)]]
-    return val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
-t = {k: traffic(f"{G}{tag}_{k}.ncu-rep") for k in KERNELS}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    val = lambda name: float(v[h.index(name)]) * scale.get(u[h.index(name)], 1)
+    return {"dram": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"), "warp_inst": val("smsp__inst_executed.sum"),
+            "issue_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "l1_wavefront_pct": val("l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"),
+            "fp64_pipe_pct": val("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+            "lanes_per_inst": val("smsp__thread_inst_executed_per_inst_executed.ratio")}
+m = {k: raw_metrics(f"{G}{tag}_{k}.ncu-rep") for k in KERNELS}
+t = {k: m[k]["dram"] for k in KERNELS}
 json.dump({"cells": 1000000, "source": "ncu --set full --clock-control none, scripts/prof_step.py 1000000 4 (same workload as bench.py at 1 GPU)",
-           "dram_bytes_per_launch": t["k_clip"], "kernel": "k_clip", "all_kernels": t, "step_total_of_these": sum(t.values())},
+           "dram_bytes_per_launch": t["k_clip"], "kernel": "k_clip", "all_kernels": t, "step_total_of_these": sum(t.values()),
+           "warp_instructions_per_launch": {k: m[k]["warp_inst"] for k in KERNELS},
+           "under_ncu_pct_of_peak": {k: {q: m[k][q] for q in ("issue_pct", "l1_wavefront_pct", "fp64_pipe_pct", "lanes_per_inst")} for k in KERNELS}},
           open(f"{P}dominant_kernel_traffic.json", "w"), indent=1)
 d = json.loads(open(f"{P}r2_bench_1gpu.json").read().strip().splitlines()[-1])
 print("value %.4g ms/step %.4f e2e %.4g" % (d["value"], d["ms_per_step"], d["e2e"]["value"]), {k: round(v, 3) for k, v in d["roofline"]["stage_ms_per_step"].items()})
