@@ -455,7 +455,9 @@ int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, doub
     a.do_step = do_step ? 1 : 0; a.xy = h->xy[c]; a.theta = h->th[c];
     a.dt = dt; a.mu = mu; a.v0 = v0; a.noise_amp = std::sqrt(2.0 * Dr * dt); a.seed = seed; a.step = step;
     a.noise = noise_row; a.Lx = h->L; a.Ly = h->L;   // a slab keeps the box's own coordinates, wrapped like the single-GPU run
-    k_force<<<nblk(n), TPB, 0, h->stream>>>(a);
+    // (a periodic box -- whole or an x-slab of it -- takes the minimum image in both directions; an open system in none)
+    a.mi_Lx = a.mi_Ly = h->L > 0.0 ? h->L : 0.0; a.mi_hx = a.mi_hy = 0.5 * a.mi_Lx;
+    k_force<<<nblk(n, FB_CELLS), FB_THREADS, 0, h->stream>>>(a);
     h->launches += 1;
     CK(cudaGetLastError());
     return AFV_OK;

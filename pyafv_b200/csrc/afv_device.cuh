@@ -56,9 +56,9 @@ struct __align__(16) CellRec {
 // warp -- consecutive cells working on the same entry -- touch consecutive words:
 //   ring_h[e]   vertex position relative to the cell centre (double2)
 //   ring_nbr[e] sorted slot of the neighbour across the edge LEAVING this vertex (clockwise), ARC for an arc
-// Arcs, slot-major as well (arc q of cell s): arc_key = (slot of the neighbour whose contact edge ENDS where the arc
-// starts, slot of the neighbour whose contact edge STARTS where the arc ends), arc_pts = (start x, y, end x, y)
-// relative to the cell centre.  A ring of E entries has at most E/2 arcs; the fast path stores 4 (a cell with more free
+// Arcs, CELL-major (arc q of cell s at [s * ARC_MAX + q]: the four keys of a cell are one 32-byte sector, which is what a
+// neighbour gathers): arc_key = (slot of the neighbour whose contact edge ENDS where the arc starts, slot of the
+// neighbour whose contact edge STARTS where the arc ends), arc_pts = (start x, y, end x, y) relative to the cell centre.  A ring of E entries has at most E/2 arcs; the fast path stores 4 (a cell with more free
 // boundary pieces than that goes to the pool like a cell with a long ring).
 constexpr int ARC_MAX = 4;
 constexpr int ARC_SLOW = RS_SLOW / 2;

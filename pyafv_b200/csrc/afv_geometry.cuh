@@ -23,8 +23,8 @@ struct GeomArgs {
     double2 *ring_h;           // [RS * stride] slot-major ring vertices (relative to the cell centre)
     int *ring_nbr;             // [RS * stride] slot-major: neighbour slot across the edge leaving the vertex, ARC for an arc
     unsigned char *ring_len;   // [n] ring entries; RING_IN_POOL when the ring lives in the overflow pool
-    int2 *arc_key;             // [ARC_MAX * stride] slot-major, see afv_device.cuh
-    double4 *arc_pts;          // [ARC_MAX * stride]
+    int2 *arc_key;             // [stride * ARC_MAX] cell-major, see afv_device.cuh
+    double4 *arc_pts;          // [stride * ARC_MAX]
     unsigned char *n_arc;      // [n]
     CellRec *rec;              // [n] what the neighbours gather in k_force
     int *nb_list;              // [cmax * stride] slot-major neighbour lists (k_nbrs -> k_clip)
@@ -431,8 +431,8 @@ __global__ void __launch_bounds__(GEOM_TPB, CLIP_MIN_BLOCKS) k_clip(GeomArgs a) 
     const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
     double2 *const rh = a.ring_h + (live ? s : 0);
     int *const rn = a.ring_nbr + (live ? s : 0);
-    int2 *const ak = a.arc_key + (live ? s : 0);
-    double4 *const ap = a.arc_pts + (live ? s : 0);
+    int2 *const ak = a.arc_key + (size_t)(live ? s : 0) * ARC_MAX;       // cell-major: what a neighbour looks up is one sector
+    double4 *const ap = a.arc_pts + (size_t)(live ? s : 0) * ARC_MAX;
     const size_t ros = a.stride;
     int E = 0, z = 0, na = 0;
     double A = 0.0, P = 0.0;
@@ -449,8 +449,8 @@ __global__ void __launch_bounds__(GEOM_TPB, CLIP_MIN_BLOCKS) k_clip(GeomArgs a) 
             A += -0.5 * (xp * y - yp * x);
             ++z;
         } else if (na < ARC_MAX) {               // the arc that started at (xp, yp) ends here
-            ak[na * ros] = make_int2(arc_from, nb);
-            ap[na * ros] = make_double4(xp, yp, x, y);
+            ak[na] = make_int2(arc_from, nb);
+            ap[na] = make_double4(xp, yp, x, y);
             ++na;
         } else ok = false;                       // more arcs than the fast path stores
     };
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(GEOM_TPB, CLIP_MIN_BLOCKS) k_clip(GeomArgs a) 
         const int aloop = __reduce_max_sync(FULL_MASK, nq);
         for (int q = 0; q < aloop; ++q) {
             if (q < nq) {
-                const double4 c = ap[q * ros];            // (v1, v2) = (start, end)
+                const double4 c = ap[q];                  // (v1, v2) = (start, end)
                 double ang = atan2(c.z * c.y - c.w * c.x, c.x * c.z + c.y * c.w);   // angle(v1) - angle(v2)
                 if (ang < 0.0) ang += TWO_PI;
                 Larc += r * ang;
@@ -622,8 +622,8 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
     const double PI = 3.14159265358979323846, TWO_PI = 6.2831853071795864769;
     double2 *const rh = POOL ? a.ovf_ring_h + (size_t)pool_idx * RS_SLOW : a.ring_h + s;
     int *const rn = POOL ? a.ovf_ring_nbr + (size_t)pool_idx * RS_SLOW : a.ring_nbr + s;
-    int2 *const ak = POOL ? a.ovf_arc_key + (size_t)pool_idx * ARC_SLOW : a.arc_key + s;
-    double4 *const ap = POOL ? a.ovf_arc_pts + (size_t)pool_idx * ARC_SLOW : a.arc_pts + s;
+    int2 *const ak = POOL ? a.ovf_arc_key + (size_t)pool_idx * ARC_SLOW : a.arc_key + (size_t)s * ARC_MAX;
+    double4 *const ap = POOL ? a.ovf_arc_pts + (size_t)pool_idx * ARC_SLOW : a.arc_pts + (size_t)s * ARC_MAX;
     const size_t ros = POOL ? 1 : a.stride;
     constexpr int ECAP = POOL ? RS_SLOW : RS, ACAP = POOL ? ARC_SLOW : ARC_MAX;
     const int mm = m;
@@ -658,8 +658,8 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
             A += -0.5 * (xp * y - yp * x);
             ++z;
         } else if (na < ACAP) {                  // the arc that started at (xp, yp) ends here
-            ak[na * ros] = make_int2(arc_from, nb);
-            ap[na * ros] = make_double4(xp, yp, x, y);
+            ak[na] = make_int2(arc_from, nb);
+            ap[na] = make_double4(xp, yp, x, y);
             ++na;
         } else ok = false;                       // more arcs than the fast path stores: the cell goes to the pool
     };
@@ -751,7 +751,7 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
         const int aloop = POOL ? nq : __reduce_max_sync(FULL_MASK, nq);
         for (int q = 0; q < aloop; ++q) {
             if (q < nq) {
-                const double4 c = ap[q * ros];            // (v1, v2) = (start, end)
+                const double4 c = ap[q];                  // (v1, v2) = (start, end)
                 double ang = atan2(c.z * c.y - c.w * c.x, c.x * c.z + c.y * c.w);   // angle(v1) - angle(v2)
                 if (ang < 0.0) ang += TWO_PI;
                 Larc += r * ang;

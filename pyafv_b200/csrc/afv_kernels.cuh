@@ -136,8 +136,8 @@ __global__ void k_reorder(const int *__restrict__ perm, int n, const double2 *__
 #include "afv_geometry.cuh"
 
 // ------------------------------------------------------------------------------------------------------
-// K3: force gather (+ fused active-Langevin update).  One thread per owned cell walks its own ring (slot-major,
-// coalesced) and gathers ONE 32-byte record (position, cA = 2KA(A-A0), cP = 2KP(P-P0)) per contact neighbour.
+// K3: force gather (+ fused active-Langevin update).  The ring of every owned cell (slot-major, coalesced) is walked
+// and ONE 32-byte record (position, cA = 2KA(A-A0), cP = 2KP(P-P0)) is gathered per contact neighbour.
 //
 // The reference assembles F_i = -sum_h (dE/dh)(dh/dr_i) with dE/dh = sum over the (<= 3) cells c around vertex h of
 // cA_c dA_c/dh + cP_c dP_c/dh (cell_geom.pyx:478-518, finite_voronoi.py:537-634).  dA_c/dh, dP_c/dh involve c's two
@@ -181,6 +181,9 @@ struct ForceArgs {
     int64_t step;
     const double *noise;           // nullptr -> Philox; else row of this step, indexed by gid
     double Lx, Ly;                 // periodic wrap of the updated positions per direction (0 = none)
+    // minimum image of the displacements per direction (period, half period; 0 = none).  By value: the kernel reads them
+    // from the constant bank instead of keeping a copy of the grid description in registers
+    double mi_Lx, mi_hx, mi_Ly, mi_hy;
 };
 
 // offset of x to the lower face `lo` of a slab of width W; with a box period L > 0 the positions are the box's own
@@ -201,220 +204,231 @@ __device__ __forceinline__ unsigned xch_lists(double xr, unsigned char own, doub
 // far end (relative to cell j) of j's arc that STARTS where j's contact edge with `self` ends (starts_there) or that
 // ENDS where j's contact edge with `self` starts (!starts_there)
 __device__ __forceinline__ bool arc_far_end(const ForceArgs &a, int j, int self, bool starts_there, double &qx, double &qy) {
-    int na = a.n_arc[j];
-    const int2 *ak = a.arc_key + j;
-    const double4 *ap = a.arc_pts + j;
-    size_t st = a.stride;
-    if (a.ring_len[j] == RING_IN_POOL) {
-        const int pi = a.ovf_index[j];
-        ak = a.ovf_arc_key + (size_t)pi * ARC_SLOW; ap = a.ovf_arc_pts + (size_t)pi * ARC_SLOW; st = 1;
+    // everything that depends on j alone is requested at once: one round trip, then the matching arc's end points
+    const int na = a.n_arc[j];
+    const int rl = a.ring_len[j];
+    const int4 *const kp = reinterpret_cast<const int4 *>(a.arc_key + (size_t)j * ARC_MAX);
+    const int4 k01 = kp[0], k23 = kp[1];
+    qx = qy = 0.0;
+    if (rl != RING_IN_POOL) {
+        const int m0 = starts_there ? k01.x : k01.y, m1 = starts_there ? k01.z : k01.w, m2 = starts_there ? k23.x : k23.y, m3 = starts_there ? k23.z : k23.w;
+        int q = -1;
+        if (na > 3 && m3 == self) q = 3;
+        if (na > 2 && m2 == self) q = 2;
+        if (na > 1 && m1 == self) q = 1;
+        if (na > 0 && m0 == self) q = 0;
+        if (q < 0) return false;
+        const double4 c = a.arc_pts[(size_t)j * ARC_MAX + q];
+        qx = starts_there ? c.z : c.x; qy = starts_there ? c.w : c.y;
+        return true;
     }
+    const int pi = a.ovf_index[j];
+    const int2 *const ak = a.ovf_arc_key + (size_t)pi * ARC_SLOW;
+    const double4 *const ap = a.ovf_arc_pts + (size_t)pi * ARC_SLOW;
     for (int q = 0; q < na; ++q) {
-        const int2 k = ak[q * st];
+        const int2 k = ak[q];
         if ((starts_there ? k.x : k.y) == self) {
-            const double4 c = ap[q * st];
+            const double4 c = ap[q];
             qx = starts_there ? c.z : c.x; qy = starts_there ? c.w : c.y;
             return true;
         }
     }
-    qx = qy = 0.0;
     return false;
 }
 
-#ifndef FORCE_MIN_BLOCKS
-#define FORCE_MIN_BLOCKS 6
+// ------------------------------------------------------------------------------------------------------
+// K3, entry-parallel.  The terms of dE/dr_i are independent per ring vertex, so a cell's ring is split over FB_ROWS
+// threads: a block takes FB_CELLS consecutive cells, thread (cell c, row w) does the entries w, w + FB_ROWS, ... of
+// cell c (entry e of 32 consecutive cells is one coalesced load per operand in the slot-major ring).  Every entry is
+// loaded from scratch -- no rolling window over the ring -- so the kernel needs 64 registers instead of 80 + spills
+// and a thread keeps all the gathers of an entry in flight at once; the serial ring walk it replaces was bound by its
+// chain of dependent loads (52 % long-scoreboard stalls at 30 % issue utilisation).  Measured at N = 1e6 (ms):
+// rows x cells x blocks/SM  1x128x6 0.246, 2x64x8 0.238, 2x32x16 0.237, 4x64x4 0.329, 8x32x4 0.491; serial walk 0.272.
+// Inner vertices (circumcentres) are finished on the spot; outer vertices (circle-circle intersections: a long code
+// path that one entry in six takes) are queued in shared memory and then done by the whole block with all lanes
+// busy.  The terms meet in a shared-memory table [entry][cell]; one thread per cell adds them up IN RING ORDER -- the
+// sum does not depend on who computed what -- and does the Langevin update.  No atomics on the result.
+// ------------------------------------------------------------------------------------------------------
+#ifndef FB_CELLS_
+#define FB_CELLS_ 64
 #endif
-__global__ void __launch_bounds__(128, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
-    // the cells of the block are dealt to its threads by ring length (as in k_clip), so that the lanes of a warp walk rings
-    // of (nearly) the same length (-14 % in the fragmenting regime, where ring lengths range from 0 to 9)
-    __shared__ int s_hist[RS + 3], s_deal[128];
-    int s;
-    {
-        const int t0 = blockIdx.x * 128 + threadIdx.x;
-        int key = RS + 2;                                                  // threads without an owned cell rank last
-        if (t0 < a.n && a.owned[t0] == CELL_OWNED) { const int E0 = a.ring_len[t0]; key = (E0 == RING_IN_POOL) ? 0 : RS + 1 - min(E0, RS); }
-        if (threadIdx.x < RS + 3) s_hist[threadIdx.x] = 0;
-        __syncthreads();
-        atomicAdd(&s_hist[key], 1);
-        __syncthreads();
-        if (threadIdx.x == 0) { int run = 0; for (int k = 0; k < RS + 3; ++k) { const int c = s_hist[k]; s_hist[k] = run; run += c; } }
-        __syncthreads();
-        s_deal[atomicAdd(&s_hist[key], 1)] = threadIdx.x;
-        __syncthreads();
-        s = blockIdx.x * 128 + s_deal[threadIdx.x];
-    }
-    const bool live = s < a.n && a.owned[s] == CELL_OWNED;
-    if (s < a.n && !live) { a.fx[s] = 0.0; a.fy[s] = 0.0; }
-    int E = live ? a.ring_len[s] : 0;
+#ifndef FB_ROWS_
+#define FB_ROWS_ 2
+#endif
+#ifndef FORCE_MIN_BLOCKS
+#define FORCE_MIN_BLOCKS 8
+#endif
+constexpr int FB_CELLS = FB_CELLS_, FB_ROWS = FB_ROWS_, FB_THREADS = FB_CELLS * FB_ROWS;
+
+struct RingRef { const double2 *h; const int *nb; size_t st; int E; };
+
+__device__ __forceinline__ double force_inv_len(double ax, double ay, double bx, double by) {
+    const double sx = ax - bx, sy = ay - by, l2 = sx * sx + sy * sy;
+    return l2 > 0.0 ? rsqrt(l2) : 0.0;
+}
+// neighbour j seen from the cell with record mec: minimum-image displacement and prefactors
+__device__ __forceinline__ double4 force_fetch(const ForceArgs &a, const double4 mec, int j) {
+    double4 v = *reinterpret_cast<const double4 *>(a.rec + j);
+    v.x -= mec.x; v.y -= mec.y;
+    if (a.mi_Lx > 0.0) v.x = min_image(v.x, a.mi_Lx, a.mi_hx);
+    if (a.mi_Ly > 0.0) v.y = min_image(v.y, a.mi_Ly, a.mi_hy);
+    return v;
+}
+// inner vertex h = hc = circumcentre(0, pa, pb) between the contact edges with bp (arriving) and bc (leaving):
+// dh = eps (h . dr_i) / (pa . eps), eps = perp(pb - pa)   (see the derivation at the top of K3)
+__device__ __forceinline__ double2 force_inner_term(const double4 mec, const double4 bp, const double4 bc, const double2 hp, const double2 hc,
+                                                    const double2 hn) {
+    const double cAi = mec.z, cPi = mec.w;
+    const double hx = hc.x, hy = hc.y;
+    const double ilp = force_inv_len(hp.x, hp.y, hx, hy), ilc = force_inv_len(hx, hy, hn.x, hn.y);
+    const double epx = -(bc.y - bp.y), epy = bc.x - bp.x;
+    const double den = bp.x * epx + bp.y * epy;
+    // sum_c cA_c dA_c/dh . eps  with the unseen far end replaced by h
+    const double Sx = cAi * (hp.x - hn.x) + bp.z * (hx - hp.x) + bc.z * (hn.x - hx);
+    const double Sy = cAi * (hp.y - hn.y) + bp.z * (hy - hp.y) + bc.z * (hn.y - hy);
+    // unit vectors from the far ends of i's two edges towards h
+    const double eax = (hx - hp.x) * ilp, eay = (hy - hp.y) * ilp;
+    const double ebx = (hx - hn.x) * ilc, eby = (hy - hn.y) * ilc;
+    const double e2n = epx * epx + epy * epy;
+    const double elen = e2n * rsqrt(e2n);
+    const double Ge = -0.5 * (Sx * epy - Sy * epx) + (cPi + bp.w) * (eax * epx + eay * epy) + (cPi + bc.w) * (ebx * epx + eby * epy);
+    // edge (a, b) leaves h away from cell i: its unit vector is sign(den) eps / |eps|
+    const double coef = (Ge - (bp.w + bc.w) * (den > 0.0 ? elen : -elen)) / den;
+    return make_double2(coef * hx, coef * hy);
+}
+// Outer vertex at hc of the cell in slot cs (record mec), between the entries hp and hn: the contact edge with j (bj: its
+// displacement and prefactors) starts (entry) or ends (!entry) here  (finite_voronoi.py:653-746)
+__device__ __forceinline__ double2 force_outer_term(const ForceArgs &a, const int cs, const double4 mec, const bool entry, const int j, const double4 bj,
+                                                    const double2 hp, const double2 hc, const double2 hn, int &misses) {
     const double r = a.ph.r, r2 = r * r;
-    double dEx = 0.0, dEy = 0.0;
-    const double2 *rh = a.ring_h + (live ? s : 0);
-    const int *rn = a.ring_nbr + (live ? s : 0);
-    size_t ros = a.stride;
-    bool pooled = false;
-    if (E == RING_IN_POOL) {
-        const int pi = a.ovf_index[s];
-        E = a.ovf_len[pi]; rh = a.ovf_ring_h + (size_t)pi * RS_SLOW; rn = a.ovf_ring_nbr + (size_t)pi * RS_SLOW; ros = 1; pooled = true;
+    const double cAc = mec.z, cPc = mec.w, cLc = mec.w + a.ph.Lambda;
+    const double hx = hc.x, hy = hc.y;
+    const double fxe = entry ? hn.x : hp.x, fye = entry ? hn.y : hp.y;     // far end of the contact edge
+    const double oxe = entry ? hp.x : hn.x, oye = entry ? hp.y : hn.y;     // other end of i's arc
+    const double pjx = bj.x, pjy = bj.y, cAj = bj.z, cPj = bj.w;
+    const double il = force_inv_len(hx, hy, fxe, fye);
+    double qx, qy;                            // other end of j's arc at h, relative to j
+    misses += !arc_far_end(a, j, cs, entry, qx, qy);
+    const double ujx = hx - pjx, ujy = hy - pjy;                           // h relative to j
+    const double Qx = qx + pjx, Qy = qy + pjy;                             // ... relative to i
+    // unit vector from the far end of the contact edge towards h: dP/dh of both cells along the edge
+    const double tx = (hx - fxe) * il, ty = (hy - fye) * il;
+    // polygon parts (cell_geom.pyx:478-518): dA/dv1 = 0.5 (y0 - y2, x2 - x0) with (v0, v2) the ring neighbours of
+    // h -- for i: (hp, hn); for j: (far end, Q) when the edge arrives at h in j's ring (entry), (Q, far end) else
+    const double sgn = entry ? 1.0 : -1.0;
+    const double Gx = cAc * 0.5 * (hp.y - hn.y) + cAj * 0.5 * sgn * (fye - Qy) + (cPc + cPj) * tx;
+    const double Gy = cAc * 0.5 * (hn.x - hp.x) + cAj * 0.5 * sgn * (Qx - fxe) + (cPc + cPj) * ty;
+    // arc-end weights (cell_geom.pyx:521-539): +-(cA/2 (r^2 - v1 . v2) + (cP + Lambda) r), + where the arc starts
+    const double wi = cAc * 0.5 * (r2 - (hx * oxe + hy * oye)) + cLc * r;
+    const double wj = cAj * 0.5 * (r2 - (ujx * qx + ujy * qy)) + (cPj + a.ph.Lambda) * r;
+    const double Wi = entry ? -wi : wi, Wj = entry ? wj : -wj;
+    const double rho2 = pjx * pjx + pjy * pjy, irho = rsqrt(rho2);
+    const double root = sqrt(fmax(4.0 * r2 - rho2, 0.0));
+    const double cr = pjx * hy - pjy * hx;
+    const double sg = (cr > 0.0) ? 1.0 : ((cr < 0.0) ? -1.0 : 0.0);
+    const double k1 = 2.0 * r2 * irho * irho * irho / fmax(root, a.ph.delta);
+    const double k2 = 0.5 * root * irho;
+    // T_x = dx_terms, T_y = dy_terms of the reference with r_IJ = -p_j
+    const double Txx = -k1 * pjx * pjy,       Txy = k1 * pjx * pjx - k2;
+    const double Tyx = -k1 * pjy * pjy + k2,  Tyy = k1 * pjx * pjy;
+    // dh/dx_i = (1/2 + s Txx, s Txy), dh/dy_i = (s Tyx, 1/2 + s Tyy); dh/dr_j = e - dh/dr_i
+    const double hxi_x = 0.5 + sg * Txx, hxi_y = sg * Txy, hyi_x = sg * Tyx, hyi_y = 0.5 + sg * Tyy;
+    const double hxj_x = 0.5 - sg * Txx, hxj_y = -sg * Txy, hyj_x = -sg * Tyx, hyj_y = 0.5 - sg * Tyy;
+    // arc angles: theta_i of h about i, theta_j of h about j
+    const double iui = 1.0 / (hx * hx + hy * hy), iuj = 1.0 / (ujx * ujx + ujy * ujy);
+    const double upix = -hy * iui, upiy = hx * iui, upjx = -ujy * iuj, upjy = ujx * iuj;
+    const double dti_x = -(hxj_x * upix + hxj_y * upiy), dti_y = -(hyj_x * upix + hyj_y * upiy);
+    const double dtj_x = hxi_x * upjx + hxi_y * upjy, dtj_y = hyi_x * upjx + hyi_y * upjy;
+    return make_double2((Gx * hxi_x + Gy * hxi_y) + (Wi * dti_x + Wj * dtj_x), (Gx * hyi_x + Gy * hyi_y) + (Wi * dti_y + Wj * dtj_y));
+}
+// the term of ring entry e of the cell in slot cs, whatever its kind (pooled rings, and the outer vertices of the queue)
+__device__ __forceinline__ double2 force_entry_term(const ForceArgs &a, const int cs, const double4 mec, const RingRef R, const int e, int &misses) {
+    const int e0 = (e == 0) ? R.E - 1 : e - 1, e1 = (e + 1 == R.E) ? 0 : e + 1;
+    const double2 hp = R.h[(size_t)e0 * R.st], hc = R.h[(size_t)e * R.st], hn = R.h[(size_t)e1 * R.st];
+    const int np_ = R.nb[(size_t)e0 * R.st], nc = R.nb[(size_t)e * R.st];
+    if (np_ != ARC && nc != ARC) return force_inner_term(mec, force_fetch(a, mec, np_), force_fetch(a, mec, nc), hp, hc, hn);
+    if ((np_ != ARC) != (nc != ARC)) {
+        const bool entry = (nc != ARC);
+        const int j = entry ? nc : np_;
+        return force_outer_term(a, cs, mec, entry, j, force_fetch(a, mec, j), hp, hc, hn, misses);
     }
-    if (E < 2) E = 0;
-    // the whole ring is requested up front: the walk below then finds it in L1 instead of paying one DRAM round trip per entry
-    for (int e = 0; e < E; ++e) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(rh + (size_t)e * ros));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(rn + (size_t)e * ros));
-    }
-    const GridDesc g = *a.grid;
-    CellRec me = {0.0, 0.0, 0.0, 0.0};
-    if (live) me = a.rec[s];
-    const double cAi = me.cA, cPi = me.cP, cLi = me.cP + a.ph.Lambda;
-    // contact neighbour across an edge: displacement (minimum image; a no-op for |d| <= L/2, so the bits are those
-    // k_hull / k_measure worked with) and energy prefactors
-    struct Nb { double px, py, cA, cP; };
-    auto fetch = [&](int j) {
-        const double4 v = *reinterpret_cast<const double4 *>(a.rec + j);
-        Nb o;
-        o.px = v.x - me.x; o.py = v.y - me.y;
-        if (g.perx || g.mix) o.px = min_image(o.px, g.Lx, g.halfLx);
-        if (g.pery) o.py = min_image(o.py, g.Ly, g.halfLy);
-        o.cA = v.z; o.cP = v.w;
-        return o;
-    };
-    auto inv_len = [](double ax, double ay, double bx, double by) {
-        const double sx = ax - bx, sy = ay - by, l2 = sx * sx + sy * sy;
-        return l2 > 0.0 ? rsqrt(l2) : 0.0;
-    };
-    int misses = 0;
-    // outer vertex at ring entry e, between entries (hp, np_) and (hn, .): the contact edge with j = bj starts (entry) or
-    // ends (!entry) here; il = 1 / its length  (finite_voronoi.py:653-746)
-    auto outer_vertex = [&](bool entry, int j, const Nb &bj, double il, double2 hp, double2 hc, double2 hn) {
-        const double hx = hc.x, hy = hc.y;
-        const double fxe = entry ? hn.x : hp.x, fye = entry ? hn.y : hp.y;     // far end of the contact edge
-        const double oxe = entry ? hp.x : hn.x, oye = entry ? hp.y : hn.y;     // other end of i's arc
-        const double pjx = bj.px, pjy = bj.py;
-        double qx, qy;                            // other end of j's arc at h, relative to j
-        misses += !arc_far_end(a, j, s, entry, qx, qy);
-        const double ujx = hx - pjx, ujy = hy - pjy;                           // h relative to j
-        const double Qx = qx + pjx, Qy = qy + pjy;                             // ... relative to i
-        // unit vector from the far end of the contact edge towards h: dP/dh of both cells along the edge
-        const double tx = (hx - fxe) * il, ty = (hy - fye) * il;
-        // polygon parts (cell_geom.pyx:478-518): dA/dv1 = 0.5 (y0 - y2, x2 - x0) with (v0, v2) the ring neighbours of
-        // h -- for i: (hp, hn); for j: (far end, Q) when the edge arrives at h in j's ring (entry), (Q, far end) else
-        const double sgn = entry ? 1.0 : -1.0;
-        const double Gx = cAi * 0.5 * (hp.y - hn.y) + bj.cA * 0.5 * sgn * (fye - Qy) + (cPi + bj.cP) * tx;
-        const double Gy = cAi * 0.5 * (hn.x - hp.x) + bj.cA * 0.5 * sgn * (Qx - fxe) + (cPi + bj.cP) * ty;
-        // arc-end weights (cell_geom.pyx:521-539): +-(cA/2 (r^2 - v1 . v2) + (cP + Lambda) r), + where the arc starts
-        const double wi = cAi * 0.5 * (r2 - (hx * oxe + hy * oye)) + cLi * r;
-        const double wj = bj.cA * 0.5 * (r2 - (ujx * qx + ujy * qy)) + (bj.cP + a.ph.Lambda) * r;
-        const double Wi = entry ? -wi : wi, Wj = entry ? wj : -wj;
-        const double rho2 = pjx * pjx + pjy * pjy, irho = rsqrt(rho2);
-        const double root = sqrt(fmax(4.0 * r2 - rho2, 0.0));
-        const double cr = pjx * hy - pjy * hx;
-        const double sg = (cr > 0.0) ? 1.0 : ((cr < 0.0) ? -1.0 : 0.0);
-        const double k1 = 2.0 * r2 * irho * irho * irho / fmax(root, a.ph.delta);
-        const double k2 = 0.5 * root * irho;
-        // T_x = dx_terms, T_y = dy_terms of the reference with r_IJ = -p_j
-        const double Txx = -k1 * pjx * pjy,       Txy = k1 * pjx * pjx - k2;
-        const double Tyx = -k1 * pjy * pjy + k2,  Tyy = k1 * pjx * pjy;
-        // dh/dx_i = (1/2 + s Txx, s Txy), dh/dy_i = (s Tyx, 1/2 + s Tyy); dh/dr_j = e - dh/dr_i
-        const double hxi_x = 0.5 + sg * Txx, hxi_y = sg * Txy, hyi_x = sg * Tyx, hyi_y = 0.5 + sg * Tyy;
-        const double hxj_x = 0.5 - sg * Txx, hxj_y = -sg * Txy, hyj_x = -sg * Tyx, hyj_y = 0.5 - sg * Tyy;
-        dEx += Gx * hxi_x + Gy * hxi_y;
-        dEy += Gx * hyi_x + Gy * hyi_y;
-        // arc angles: theta_i of h about i, theta_j of h about j
-        const double iui = 1.0 / (hx * hx + hy * hy), iuj = 1.0 / (ujx * ujx + ujy * ujy);
-        const double upix = -hy * iui, upiy = hx * iui, upjx = -ujy * iuj, upjy = ujx * iuj;
-        const double dti_x = -(hxj_x * upix + hxj_y * upiy), dti_y = -(hyj_x * upix + hyj_y * upiy);
-        const double dtj_x = hxi_x * upjx + hxi_y * upjy, dtj_y = hyi_x * upjx + hyi_y * upjy;
-        dEx += Wi * dti_x + Wj * dtj_x;
-        dEy += Wi * dti_y + Wj * dtj_y;
-    };
-    // ---- pass 1, all lanes of the warp in step over their rings: inner vertices; outer vertices (rarer, and a long
-    //      code path) are only noted down -- 4 bits each -- and done together afterwards ----
-    unsigned long long outer = 0ull;
-    int n_outer = 0;
-    {
-        // rolling window over entries e-1, e, e+1 (vertex, neighbour across the leaving edge and its record); what
-        // entry e+2 needs is requested one iteration ahead, so no load sits on the critical path of the loop
-        double2 hp = make_double2(0.0, 0.0), hc = hp, hn = hp;
-        int np_ = ARC, nc = ARC, nn = ARC;
-        Nb bp = {0.0, 0.0, 0.0, 0.0}, bc = bp;
-        double ilp = 0.0;
-        if (E) {
-            const int e1 = (1 == E) ? 0 : 1;
-            hp = rh[(size_t)(E - 1) * ros]; hc = rh[0]; hn = rh[(size_t)e1 * ros];
-            np_ = rn[(size_t)(E - 1) * ros]; nc = rn[0]; nn = rn[(size_t)e1 * ros];
-            if (np_ != ARC) { bp = fetch(np_); ilp = inv_len(hp.x, hp.y, hc.x, hc.y); }
-            if (nc != ARC) bc = fetch(nc);
-        }
-        const int Eloop = __reduce_max_sync(FULL_MASK, E);
-        for (int e = 0; e < Eloop; ++e) {
-            if (e < E) {
-                int e2 = e + 2; if (e2 >= E) e2 -= E;
-                const double2 h2 = rh[(size_t)e2 * ros];
-                const int n2 = rn[(size_t)e2 * ros];
-                Nb bn = {0.0, 0.0, 0.0, 0.0};
-                if (nn != ARC) bn = fetch(nn);
-                const double ilc = (nc != ARC) ? inv_len(hc.x, hc.y, hn.x, hn.y) : 0.0;
-                const double hx = hc.x, hy = hc.y;
-                if (np_ != ARC && nc != ARC) {
-                    // inner vertex h = circumcentre(0, pa, pb): dh = eps (h . dr_i) / (pa . eps), eps = perp(pb - pa)
-                    const double epx = -(bc.py - bp.py), epy = bc.px - bp.px;
-                    const double den = bp.px * epx + bp.py * epy;
-                    // sum_c cA_c dA_c/dh . eps  with the unseen far end replaced by h (see above)
-                    const double Sx = cAi * (hp.x - hn.x) + bp.cA * (hx - hp.x) + bc.cA * (hn.x - hx);
-                    const double Sy = cAi * (hp.y - hn.y) + bp.cA * (hy - hp.y) + bc.cA * (hn.y - hy);
-                    // unit vectors from the far ends of i's two edges towards h
-                    const double eax = (hx - hp.x) * ilp, eay = (hy - hp.y) * ilp;
-                    const double ebx = (hx - hn.x) * ilc, eby = (hy - hn.y) * ilc;
-                    const double e2n = epx * epx + epy * epy;
-                    const double elen = e2n * rsqrt(e2n);
-                    const double Ge = -0.5 * (Sx * epy - Sy * epx) + (cPi + bp.cP) * (eax * epx + eay * epy) + (cPi + bc.cP) * (ebx * epx + eby * epy);
-                    // edge (a, b) leaves h away from cell i: its unit vector is sign(den) eps / |eps|
-                    const double coef = (Ge - (bp.cP + bc.cP) * (den > 0.0 ? elen : -elen)) / den;
-                    dEx += coef * hx; dEy += coef * hy;
-                } else if ((np_ != ARC) != (nc != ARC)) {
-                    if (!pooled) { outer |= (unsigned long long)e << (4 * n_outer); ++n_outer; }
-                    else { const bool entry = (nc != ARC); outer_vertex(entry, entry ? nc : np_, entry ? bc : bp, entry ? ilc : ilp, hp, hc, hn); }
-                }
-                hp = hc; hc = hn; hn = h2; np_ = nc; nc = nn; nn = n2; bp = bc; bc = bn; ilp = ilc;
-            }
-        }
-    }
-    // ---- pass 2: the q-th outer vertex of every lane ----
-    {
-        const int qloop = __reduce_max_sync(FULL_MASK, n_outer);
-        for (int q = 0; q < qloop; ++q) {
-            if (q < n_outer) {
-                const int e = (int)((outer >> (4 * q)) & 15ull);
-                const int e0 = (e == 0) ? E - 1 : e - 1, e1 = (e + 1 == E) ? 0 : e + 1;
-                const double2 hp = rh[(size_t)e0 * ros], hc = rh[(size_t)e * ros], hn = rh[(size_t)e1 * ros];
-                const int nc = rn[(size_t)e * ros];
-                const bool entry = (nc != ARC);
-                const int j = entry ? nc : rn[(size_t)e0 * ros];
-                const Nb bj = fetch(j);
-                const double il = entry ? inv_len(hc.x, hc.y, hn.x, hn.y) : inv_len(hp.x, hp.y, hc.x, hc.y);
-                outer_vertex(entry, j, bj, il, hp, hc, hn);
-            }
-        }
-    }
-    if (misses) atomicAdd(&a.flags[1], misses);
-    if (!live) return;
-    const double Fx = -dEx, Fy = -dEy;
-    a.fx[s] = Fx; a.fy[s] = Fy;
-    // a step whose geometry exceeded every capacity does not move the cells: the state stays the one the error is about
-    if (a.do_step && a.flags[3] == 0) {
-        const double th = a.theta[s];
-        double sn, cs_;
-        sincos(th, &sn, &cs_);
-        const double2 pos = a.xy[s];
-        double xn = pos.x + (a.mu * Fx + a.v0 * cs_) * a.dt;
-        double yn = pos.y + (a.mu * Fy + a.v0 * sn) * a.dt;
-        if (a.Lx > 0.0) { xn -= a.Lx * floor(xn / a.Lx); if (xn >= a.Lx) xn = 0.0; }
-        if (a.Ly > 0.0) { yn -= a.Ly * floor(yn / a.Ly); if (yn >= a.Ly) yn = 0.0; }
-        double xi_ = 0.0;
+    return make_double2(0.0, 0.0);
+}
+
+__global__ void __launch_bounds__(FB_THREADS, FORCE_MIN_BLOCKS) k_force(ForceArgs a) {
+    __shared__ double2 s_term[RS][FB_CELLS];          // [entry][cell of the block]
+    __shared__ unsigned short s_queue[FB_CELLS * RS]; // outer vertices: cell << 4 | entry
+    __shared__ unsigned char s_len[FB_CELLS];
+    __shared__ int s_nq;
+    const int c = threadIdx.x & (FB_CELLS - 1), row0 = threadIdx.x / FB_CELLS;
+    const int s = blockIdx.x * FB_CELLS + c;
+    const bool live = s < a.n && a.owned[s] == CELL_OWNED;
+    int Eraw = live ? a.ring_len[s] : 0;
+    const bool pooled = Eraw == RING_IN_POOL;
+    const int E = (pooled || Eraw < 2) ? 0 : Eraw;    // entries of the fast-path ring done in parallel (a pooled ring: by its cell, below)
+    if (threadIdx.x == 0) s_nq = 0;
+    if (row0 == 0) s_len[c] = (unsigned char)E;
+    double4 mec = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (live) mec = *reinterpret_cast<const double4 *>(a.rec + s);
+    // what the update at the end needs is requested now: its round trip overlaps everything in between
+    double th = 0.0, xi_ = 0.0;
+    double2 pos = make_double2(0.0, 0.0);
+    if (row0 == 0 && live && a.do_step) {
+        th = a.theta[s]; pos = a.xy[s];
         if (a.noise_amp != 0.0) {
             const int64_t id = a.gid[s];
             xi_ = a.noise ? a.noise[id] : philox_normal(a.seed, id, a.step);
         }
+    }
+    __syncthreads();
+    int misses = 0;
+    {
+        const double2 *const rh = a.ring_h + (live ? s : 0);
+        const int *const rn = a.ring_nbr + (live ? s : 0);
+        const size_t st = a.stride;
+        for (int e = row0; e < E; e += FB_ROWS) {
+            const int e0 = (e == 0) ? E - 1 : e - 1, e1 = (e + 1 == E) ? 0 : e + 1;
+            const int np_ = rn[(size_t)e0 * st], nc = rn[(size_t)e * st];
+            const double2 hp = rh[(size_t)e0 * st], hc = rh[(size_t)e * st], hn = rh[(size_t)e1 * st];
+            double2 t = make_double2(0.0, 0.0);
+            if (np_ != ARC && nc != ARC) t = force_inner_term(mec, force_fetch(a, mec, np_), force_fetch(a, mec, nc), hp, hc, hn);
+            else if ((np_ != ARC) != (nc != ARC)) s_queue[atomicAdd(&s_nq, 1)] = (unsigned short)(c << 4 | e);
+            s_term[e][c] = t;
+        }
+    }
+    __syncthreads();
+    {
+        // the queue, one outer vertex per thread (their order in the queue is arbitrary: each result has its own place)
+        const int nq = s_nq;
+        for (int i = threadIdx.x; i < nq; i += FB_THREADS) {
+            const int qc = s_queue[i] >> 4, qe = s_queue[i] & 15, qs = blockIdx.x * FB_CELLS + qc;
+            const RingRef R = {a.ring_h + qs, a.ring_nbr + qs, a.stride, (int)s_len[qc]};
+            s_term[qe][qc] = force_entry_term(a, qs, *reinterpret_cast<const double4 *>(a.rec + qs), R, qe, misses);
+        }
+    }
+    __syncthreads();
+    if (misses) atomicAdd(&a.flags[1], misses);
+    if (row0 != 0 || s >= a.n) return;
+    if (!live) { a.fx[s] = 0.0; a.fy[s] = 0.0; return; }
+    double dEx = 0.0, dEy = 0.0;
+    for (int e = 0; e < E; ++e) { const double2 t = s_term[e][c]; dEx += t.x; dEy += t.y; }
+    if (pooled) {   // a ring in the overflow pool (a handful of cells per step): walked by its own thread
+        const int pi = a.ovf_index[s];
+        const RingRef R = {a.ovf_ring_h + (size_t)pi * RS_SLOW, a.ovf_ring_nbr + (size_t)pi * RS_SLOW, 1, a.ovf_len[pi]};
+        int m2 = 0;
+        if (R.E >= 2) for (int e = 0; e < R.E; ++e) { const double2 t = force_entry_term(a, s, mec, R, e, m2); dEx += t.x; dEy += t.y; }
+        if (m2) atomicAdd(&a.flags[1], m2);
+    }
+    const double Fx = -dEx, Fy = -dEy;
+    a.fx[s] = Fx; a.fy[s] = Fy;
+    // a step whose geometry exceeded every capacity does not move the cells: the state stays the one the error is about
+    if (a.do_step && a.flags[3] == 0) {
+        double sn, cs_;
+        sincos(th, &sn, &cs_);
+        double xn = pos.x + (a.mu * Fx + a.v0 * cs_) * a.dt;
+        double yn = pos.y + (a.mu * Fy + a.v0 * sn) * a.dt;
+        if (a.Lx > 0.0) { xn -= a.Lx * floor(xn / a.Lx); if (xn >= a.Lx) xn = 0.0; }
+        if (a.Ly > 0.0) { yn -= a.Ly * floor(yn / a.Ly); if (yn >= a.Ly) yn = 0.0; }
         a.xy[s] = make_double2(xn, yn); a.theta[s] = th + a.noise_amp * xi_;
     }
 }
