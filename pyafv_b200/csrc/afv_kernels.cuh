@@ -362,8 +362,10 @@ __global__ void __launch_bounds__(FB_THREADS, FORCE_MIN_BLOCKS) k_force(ForceArg
     __shared__ int s_nq;
     const int c = threadIdx.x & (FB_CELLS - 1), row0 = threadIdx.x / FB_CELLS;
     const int s = blockIdx.x * FB_CELLS + c;
-    const bool live = s < a.n && a.owned[s] == CELL_OWNED;
-    int Eraw = live ? a.ring_len[s] : 0;
+    // (both loads at once: the ring length is not held back until the ownership mark has arrived)
+    const int own_ = s < a.n ? a.owned[s] : CELL_HALO, len_ = s < a.n ? a.ring_len[s] : 0;
+    const bool live = own_ == CELL_OWNED;
+    const int Eraw = live ? len_ : 0;
     const bool pooled = Eraw == RING_IN_POOL;
     const int E = (pooled || Eraw < 2) ? 0 : Eraw;    // entries of the fast-path ring done in parallel (a pooled ring: by its cell, below)
     if (threadIdx.x == 0) s_nq = 0;
@@ -386,6 +388,12 @@ __global__ void __launch_bounds__(FB_THREADS, FORCE_MIN_BLOCKS) k_force(ForceArg
         const double2 *const rh = a.ring_h + (live ? s : 0);
         const int *const rn = a.ring_nbr + (live ? s : 0);
         const size_t st = a.stride;
+        // the thread's rows of the ring are requested up front: the loop below then finds them in L1 instead of paying one DRAM
+        // round trip per entry (0.239 -> 0.229 ms; requesting the neighbours' records as well: 0.244)
+        for (int e = row0; e < E; e += FB_ROWS) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rh + (size_t)e * st));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rn + (size_t)e * st));
+        }
         for (int e = row0; e < E; e += FB_ROWS) {
             const int e0 = (e == 0) ? E - 1 : e - 1, e1 = (e + 1 == E) ? 0 : e + 1;
             const int np_ = rn[(size_t)e0 * st], nc = rn[(size_t)e * st];
