@@ -400,6 +400,7 @@ int stage_geometry(AfvHandle h, GeomPass gp = GeomPass()) {
     a.ovf_ring_h = h->ovf_ring_h; a.ovf_ring_nbr = h->ovf_ring_nbr; a.ovf_arc_key = h->ovf_arc_key; a.ovf_arc_pts = h->ovf_arc_pts;
     a.n_main = (int)h->n_main; a.bin_start_late = (gp.late && h->n_late > 0) ? h->bin_start_late : nullptr;
     a.filter = gp.filter; a.face_cols = h->face_cols;
+    a.mi_Lx = a.mi_Ly = h->L > 0.0 ? h->L : 0.0; a.mi_hx = a.mi_hy = 0.5 * a.mi_Lx;
     // candidate-list capacity per cell (shared memory scales with it): for a periodic box the mean number of cells
     // within 2r is known, 4 pi r^2 N / L^2; otherwise start at 32 and grow when the slow path gets busy
     if (h->L > 0.0) {

@@ -52,6 +52,9 @@ struct GeomArgs {
     // filter == 2: the launch is dense over the face cells -- thread t handles slot t (t < face_len0: the first face_cols
     // columns), face_s1 + (t - face_len0) (the last face_cols columns, face_len1 cells), or a late cell
     int face_len0, face_len1, face_s1;
+    // minimum image per direction (period, half period; 0 in an open system).  By value: the hot loops read them from the
+    // constant bank instead of holding the grid description's copies in registers
+    double mi_Lx, mi_hx, mi_Ly, mi_hy;
 };
 
 // sorted slot handled by thread t of a geometry launch (n = number of threads with work)
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(GEOM_TPB, CLIP_MIN_BLOCKS) k_clip(GeomArgs a) 
     if (!SLAB) g.swap = 0;
     int n = 0, smin = -1;
     bool ok = true;
-    double xi = 0.0, yi = 0.0;
+    double xi = 0.0, yi = 0.0, a0s = 0.0;
     bool wrapx = false, wrapy = false;
     if (live) {
         int bx, by;
@@ -327,6 +330,7 @@ __global__ void __launch_bounds__(GEOM_TPB, CLIP_MIN_BLOCKS) k_clip(GeomArgs a) 
             wrapx = g.mix || (g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3));
             wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
             n = a.nb_cnt[s]; smin = a.nb_min[s];
+            a0s = a.a0[s];                         // (needed at the very end; requested here, its round trip is free)
             if (n == NB_OVERFLOW) { ok = false; n = 0; }
         }
     }
@@ -334,8 +338,8 @@ __global__ void __launch_bounds__(GEOM_TPB, CLIP_MIN_BLOCKS) k_clip(GeomArgs a) 
     auto disp_of = [&](int slot, double &dx, double &dy) {
         const double2 pc = a.xy[slot];
         dx = pc.x - xi; dy = pc.y - yi;
-        if (wrapx) dx = min_image(dx, g.Lx, g.halfLx);
-        if (wrapy) dy = min_image(dy, g.Ly, g.halfLy);
+        if (wrapx) dx = min_image(dx, a.mi_Lx, a.mi_hx);
+        if (wrapy) dy = min_image(dy, a.mi_Ly, a.mi_hy);
     };
     const double B = 2.0 * r;                     // half side of the bounding square: its sides are bisectors of virtual neighbours at 4r
     // (no branch: a side label reads the cell's own position -- a zero displacement -- and the normal of the side is
@@ -376,8 +380,8 @@ __global__ void __launch_bounds__(GEOM_TPB, CLIP_MIN_BLOCKS) k_clip(GeomArgs a) 
             if (work && ci + 1 < n) p1 = a.xy[c1];
             if (work && ci + 2 < n) c2 = list[(size_t)(ci + 2) * a.stride];
             double nx = pc.x - xi, ny = pc.y - yi;
-            if (wrapx) nx = min_image(nx, g.Lx, g.halfLx);
-            if (wrapy) ny = min_image(ny, g.Ly, g.halfLy);
+            if (wrapx) nx = min_image(nx, a.mi_Lx, a.mi_hx);
+            if (wrapy) ny = min_image(ny, a.mi_Ly, a.mi_hy);
             const double cc = 0.5 * (nx * nx + ny * ny);
             // which vertices lie inside the new half-plane?  (bit p; the loop bound is the warp's largest polygon)
             unsigned in = 0u;
@@ -493,8 +497,8 @@ __global__ void __launch_bounds__(GEOM_TPB, CLIP_MIN_BLOCKS) k_clip(GeomArgs a) 
                 if (st + 1 < mw) { jn = sl[NIB(ord, p) * T]; if (jn >= 0) pn = a.xy[jn]; }
                 if (j >= 0 && ok) {                        // a real neighbour (the sides of the square emit nothing)
                     double pcx = pj.x - xi, pcy = pj.y - yi;
-                    if (wrapx) pcx = min_image(pcx, g.Lx, g.halfLx);
-                    if (wrapy) pcy = min_image(pcy, g.Ly, g.halfLy);
+                    if (wrapx) pcx = min_image(pcx, a.mi_Lx, a.mi_hx);
+                    if (wrapy) pcy = min_image(pcy, a.mi_Ly, a.mi_hy);
                     const bool in1 = V1.x * V1.x + V1.y * V1.y <= r2;
                     // first entry of the edge: its inner start vertex (d1 <= r) or the point where it enters the disk (never
                     // both); second: the point where it leaves the disk.  An edge between two inner vertices has neither.
@@ -560,7 +564,7 @@ __global__ void __launch_bounds__(GEOM_TPB, CLIP_MIN_BLOCKS) k_clip(GeomArgs a) 
         a.area[s] = A; a.perim[s] = P; a.arcl[s] = Larc; a.coord[s] = zz;
         CellRec q;
         q.x = xi; q.y = yi;
-        q.cA = 2.0 * a.ph.KA * (A - a.a0[s]);
+        q.cA = 2.0 * a.ph.KA * (A - a0s);
         q.cP = 2.0 * a.ph.KP * (P - a.ph.P0);
         a.rec[s] = q;
     }
