@@ -318,6 +318,15 @@ void periodic_grid(AfvHandle h, GridDesc &g) {
     // late-cell stepping of an x-slab: columns contiguous, so that the face columns are the two ends of the sorted order
     g.swap = (h->slab && h->late_mode) ? 1 : 0;
     g.mix = h->slab ? 1 : 0;
+    g.seam_lo = 0; g.seam_hi = -1;
+    if (h->slab) {   // where the box seam x = 0 = L lies in this grid: wrapped offset of x = 0 to the grid origin
+        double so = std::fmod(-g.x0, h->L);
+        if (so < 0.0) so += h->L;
+        if (so < wx + 1.0 / g.inv_bx) {
+            const int sc = (int)std::floor(so * g.inv_bx);
+            g.seam_lo = std::max(sc - 1, 0); g.seam_hi = std::min(sc + 1, nbx - 1);
+        }
+    }
 }
 
 int upload_grid_periodic(AfvHandle h) {

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128, NBRS_MIN_BLOCKS) k_nbrs(GeomArgs a, const
     const double r = a.ph.r, cut2 = 4.0 * r * r;
     const double2 pi_ = a.xy[s];
     const double xi = pi_.x, yi = pi_.y;
-    const bool wrapx = g.mix || (g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3));   // only cells in the outermost bins can see a periodic image
+    const bool wrapx = (g.mix && bx >= g.seam_lo && bx <= g.seam_hi) || (g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3));   // only cells in the outermost bins can see a periodic image
     const bool wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
     // lines of bins: rows, or columns in a swapped (slab) grid
     const int npos = g.swap ? g.nby : g.nbx, nline = g.swap ? g.nbx : g.nby, pos = g.swap ? by : bx;
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(GEOM_TPB, CLIP_MIN_BLOCKS) k_clip(GeomArgs a) 
         if (live) {
             const double2 pi_ = a.xy[s];
             xi = pi_.x; yi = pi_.y;
-            wrapx = g.mix || (g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3));
+            wrapx = (g.mix && bx >= g.seam_lo && bx <= g.seam_hi) || (g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3));
             wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
             n = a.nb_cnt[s]; smin = a.nb_min[s];
             a0s = a.a0[s];                         // (needed at the very end; requested here, its round trip is free)
@@ -595,7 +595,7 @@ __device__ __forceinline__ bool ring_cell(const GeomArgs &a, const int s, const 
         if (live) {
             const double2 pi_ = a.xy[s];
             xi = pi_.x; yi = pi_.y;
-            wrapx = g.mix || (g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3));
+            wrapx = (g.mix && bx >= g.seam_lo && bx <= g.seam_hi) || (g.perx && (bx == 0 || bx == g.nbx - 1 || g.nbx < 3));
             wrapy = g.pery && (by == 0 || by == g.nby - 1 || g.nby < 3);
             m = m_pool;
         }

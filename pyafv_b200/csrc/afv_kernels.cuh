@@ -65,7 +65,7 @@ __global__ void k_bbox_final(const double *__restrict__ part, int nblocks, doubl
         int nbx = (int)fx, nby = (int)fy;
         double bsx = fmax(cut, sx / (double)nbx), bsy = fmax(cut, sy / (double)nby);
         g->x0 = xmin; g->y0 = ymin; g->inv_bx = 1.0 / bsx; g->inv_by = 1.0 / bsy;
-        g->Lx = g->Ly = 0.0; g->halfLx = g->halfLy = 0.0; g->nbx = nbx; g->nby = nby; g->perx = 0; g->pery = 0; g->swap = 0; g->mix = 0;
+        g->Lx = g->Ly = 0.0; g->halfLx = g->halfLy = 0.0; g->nbx = nbx; g->nby = nby; g->perx = 0; g->pery = 0; g->swap = 0; g->mix = 0; g->seam_lo = 0; g->seam_hi = -1;
     }
 }
 
