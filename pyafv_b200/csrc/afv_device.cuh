@@ -59,11 +59,13 @@ struct __align__(16) CellRec {
 // warp -- consecutive cells working on the same entry -- touch consecutive words:
 //   ring_h[e]   vertex position relative to the cell centre (double2)
 //   ring_nbr[e] sorted slot of the neighbour across the edge LEAVING this vertex (clockwise), ARC for an arc
-// Arcs, CELL-major (arc q of cell s at [s * ARC_MAX + q]: the four keys of a cell are one 32-byte sector, which is what a
-// neighbour gathers): arc_key = (slot of the neighbour whose contact edge ENDS where the arc starts, slot of the
-// neighbour whose contact edge STARTS where the arc ends), arc_pts = (start x, y, end x, y) relative to the cell centre.  A ring of E entries has at most E/2 arcs; the fast path stores 4 (a cell with more free
-// boundary pieces than that goes to the pool like a cell with a long ring).
-constexpr int ARC_MAX = 4;
+// Arcs, CELL-major (arc q of cell s at [s * ARC_MAX + q]: the first four keys of a cell are one 32-byte sector, which is
+// what a neighbour gathers): arc_key = (slot of the neighbour whose contact edge ENDS where the arc starts, slot of the
+// neighbour whose contact edge STARTS where the arc ends), arc_pts = (start x, y, end x, y) relative to the cell centre.
+// A ring of E entries has at most E/2 arcs, and the fast path stores that many: at rho l^2 = 1 ten cells in a million
+// have five or more, and with room for four they were the whole population of the slow path (0.019 ms per step for a
+// dozen cells).
+constexpr int ARC_MAX = RS / 2;
 constexpr int ARC_SLOW = RS_SLOW / 2;
 
 // bin column of x (clamped)

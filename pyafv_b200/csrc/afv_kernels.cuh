@@ -213,6 +213,14 @@ __device__ __forceinline__ bool arc_far_end(const ForceArgs &a, int j, int self,
     if (rl != RING_IN_POOL) {
         const int m0 = starts_there ? k01.x : k01.y, m1 = starts_there ? k01.z : k01.w, m2 = starts_there ? k23.x : k23.y, m3 = starts_there ? k23.z : k23.w;
         int q = -1;
+        if (na > 4) {   // (rare: the second half of the table)
+            const int4 k45 = kp[2], k67 = kp[3];
+            const int m4 = starts_there ? k45.x : k45.y, m5 = starts_there ? k45.z : k45.w, m6 = starts_there ? k67.x : k67.y, m7 = starts_there ? k67.z : k67.w;
+            if (na > 7 && m7 == self) q = 7;
+            if (na > 6 && m6 == self) q = 6;
+            if (na > 5 && m5 == self) q = 5;
+            if (m4 == self) q = 4;
+        }
         if (na > 3 && m3 == self) q = 3;
         if (na > 2 && m2 == self) q = 2;
         if (na > 1 && m1 == self) q = 1;
