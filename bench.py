@@ -238,6 +238,7 @@ def run_ours(args) -> dict:
     # more than the ~0.1 ms of exchange it hides (measured on 2 GPUs: 0.947 against 0.993 ms/step)
     overlap = world > 1 and args.overlap and not args.no_overlap
     sim, step_k, L = make_sim(cells, overlap)
+    transport = transport_name(sim)
     h = sim._h
     sampler = ClockSampler(local)
     if rank == 0:
@@ -363,7 +364,7 @@ def run_ours(args) -> dict:
                 assert tot4 == world * c4, f"cells lost or duplicated by the exchange: {tot4} != {world * c4}"
             rl4, rl4_64 = rooflines(s6, k4, int(s4._h.n), tot4 / world, m4 / k4, float(fp64.value))
             config4 = {"value": tot4 * k4 / (m4 * 1e-3), "unit": "cell-steps/s", "ms_per_step": m4 / k4, "steps": k4, "warmup": 3,
-                       "cells_total": tot4, "cells_per_gpu": c4, "box_L": L4, "exchange": "none (1 GPU)" if world == 1 else "exchange, then step",
+                       "cells_total": tot4, "cells_per_gpu": c4, "box_L": L4, "exchange": "none (1 GPU)" if world == 1 else f"exchange over {transport_name(s4)}, then step",
                        "roofline": rl4, "roofline_fp64": rl4_64}
             s4.close()
         except Exception as e:   # e.g. not enough memory on a smaller device: say so instead of dying
@@ -378,7 +379,7 @@ def run_ours(args) -> dict:
                "config": {"workload": f"N={total_cells} periodic active AFV, uniform random rho*l^2=1 "
                                       f"(BASELINE config[{3 if world == 1 else 4}] shape), {cells} cells/GPU" + (", x-slabs" if world > 1 else ""),
                           "cells_per_gpu": cells, "box_L": L, **STEP,
-                          "exchange": ("none (1 GPU)" if world == 1 else "per step, NCCL point-to-point with both ring neighbours, " +
+                          "exchange": ("none (1 GPU)" if world == 1 else f"per step, {transport} with both ring neighbours, " +
                                        ("overlapped with the sort and the interior geometry of the step (late cells)" if overlap_used else "then step")),
                           "exchange_overlapped_steps": ov_steps,
                           "l2_policy": f"per-step working set (~{n_local * 0.45 / 1e3:.0f} MB of rings, neighbour lists and state) exceeds the 126 MB L2; "
@@ -391,6 +392,13 @@ def run_ours(args) -> dict:
         dist.barrier()
         dist.destroy_process_group()
     return out
+
+
+def transport_name(sim) -> str:
+    """How the ranks exchange their messages (pyafv_b200/sharded.py: NvlinkPeerComm or TorchDistComm)."""
+    name = type(getattr(sim, "comm", None)).__name__
+    return {"NvlinkPeerComm": "peer memory over NVLink (the pack kernel writes into the neighbours' inboxes, flag words for the hand-over)",
+            "TorchDistComm": "NCCL point-to-point"}.get(name, name)
 
 
 def verify_sharded(torch, dist, afv, SlabShardedSimulator, phys, rank, world, local, stream, n_total=200_000, steps=30) -> dict:
@@ -429,6 +437,7 @@ def verify_sharded(torch, dist, afv, SlabShardedSimulator, phys, rank, world, lo
     dist.all_gather(bufs, pad)
     misses = torch.tensor([float(diag[1])], device="cuda", dtype=torch.float64)
     dist.all_reduce(misses)
+    transport = transport_name(sim)
     sim.close()
     out = None
     if rank == 0:
@@ -450,7 +459,7 @@ def verify_sharded(torch, dist, afv, SlabShardedSimulator, phys, rank, world, lo
         else:
             max_dx = max_df = net = float("nan")
         fscale = float(np.abs(rf).max())
-        out = {"cells": n_total, "steps": steps, "ranks": world, "transport": "NCCL; half of the steps exchange-then-step, half with the late-cell overlap", "cells_conserved": bool(conserved),
+        out = {"cells": n_total, "steps": steps, "ranks": world, "transport": transport + "; half of the steps exchange-then-step, half with the late-cell overlap", "cells_conserved": bool(conserved),
                "max_dx": max_dx, "max_dF": max_df, "bit_identical": bool(conserved and max_dx == 0.0 and max_df == 0.0),
                "lookup_misses": int(misses.item()), "net_force_over_max_force": net / fscale if fscale else None,
                "ok": bool(conserved and max_dx <= 1e-9 and int(misses.item()) == 0 and net <= 1e-9 * max(1.0, fscale) * np.sqrt(n_total))}

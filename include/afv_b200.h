@@ -216,6 +216,25 @@ int afv_late_step_end(AfvHandle h, double dt, double mu, double v0, double Dr, u
 int afv_get_exchange_stats(AfvHandle h, int64_t out[4]);
 /* make the handle's stream wait for everything issued so far on other_stream */
 int afv_stream_wait(AfvHandle h, void *other_stream);
+
+/* ---- the exchange over peer memory (NVLink) instead of a send / receive pair ---------------------------------
+ * Replaces the transport of pyafv/parallel_voronoi.py:536-633 (there: pickled sub-arrays through a process pool) between
+ * the GPUs of one node.  The caller maps the inboxes of the two ring neighbours into its address space (CUDA IPC) and
+ * passes them to afv_pack_exchange / afv_late_step_end as msg_left_dev / msg_right_dev: the pack kernel then writes
+ * its messages straight into the neighbours' memory.  afv_flag_signal, issued behind the pack on the same stream,
+ * publishes a sequence number in the neighbour's memory once those writes are complete; afv_flag_wait holds a stream
+ * until the number in this rank's own flag word has reached `value` (sequence numbers compare wrap-safe).  Two
+ * inboxes per side, used alternately, are enough: a rank cannot be more than one exchange ahead of a neighbour it also
+ * receives from.  A wait that lasts longer than 20 s gives up: the next status read reports AFV_ERR_CAPACITY with
+ * "... did not arrive", and the cells are not moved.
+ * afv_peer_buffer_create: zero-filled device memory owned by the handle (released by afv_destroy) and its CUDA IPC
+ * handle (64 bytes, to be passed to the neighbours by any means); afv_peer_buffer_open: map a neighbour's buffer into
+ * this process for this handle's device (unmapped by afv_destroy; not for a buffer of the same process).
+ * stream: NULL = the handle's stream. */
+int afv_peer_buffer_create(AfvHandle h, int64_t bytes, void **dev_out, unsigned char ipc_handle_out[64]);
+int afv_peer_buffer_open(AfvHandle h, const unsigned char ipc_handle[64], void **dev_out);
+int afv_flag_signal(AfvHandle h, void *stream, unsigned *flag_dev, unsigned value);
+int afv_flag_wait(AfvHandle h, void *stream, const unsigned *flag_dev, unsigned value);
 /* after afv_build: rows (count,11) of the OWNED cells in device memory:
  * x, y, theta, A0, gid, fx, fy, area, perimeter, arclen, coord_num */
 int afv_pack_owned(AfvHandle h, double *rows_dev_out, int64_t capacity, int64_t *count);

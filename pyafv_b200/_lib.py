@@ -22,6 +22,7 @@ SYMBOLS = [
     "afv_get_diagnostics", "afv_set_profiling", "afv_get_stage_times", "afv_launch_count", "afv_host_alloc",
     "afv_host_free", "afv_measure_fp64_peak", "afv_device_ptr", "afv_stream", "afv_synchronize", "afv_set_deferred_checks",
     "afv_set_slab", "afv_set_cells_device", "afv_extract_slab", "afv_drop_halo", "afv_append_cells", "afv_num_owned", "afv_pack_owned", "afv_pack_pair", "afv_finish_pair", "afv_pack_exchange", "afv_finish_exchange", "afv_finish_exchange_step", "afv_late_step_begin", "afv_late_finish", "afv_late_step_end", "afv_stream_wait", "afv_get_exchange_stats",
+    "afv_peer_buffer_create", "afv_peer_buffer_open", "afv_flag_signal", "afv_flag_wait",
     "afv_cluster_analysis", "afv_get_cluster_labels", "afv_get_cluster_sizes", "afv_components_of_edges",
     "afv_get_energy", "afv_get_cell_energies", "afv_relax",
 ]
@@ -101,6 +102,10 @@ def load() -> C.CDLL:
         "afv_late_finish": (C.c_int, [H, P, P, I64, P]),
         "afv_late_step_end": (C.c_int, [H, D, D, D, D, C.c_uint64, I64, D, D, D, D, D, P, P, I64, P]),
         "afv_stream_wait": (C.c_int, [H, P]),
+        "afv_peer_buffer_create": (C.c_int, [H, I64, C.POINTER(P), P]),
+        "afv_peer_buffer_open": (C.c_int, [H, P, C.POINTER(P)]),
+        "afv_flag_signal": (C.c_int, [H, P, P, C.c_uint]),
+        "afv_flag_wait": (C.c_int, [H, P, P, C.c_uint]),
         "afv_get_exchange_stats": (C.c_int, [H, P]),
         "afv_pack_owned": (C.c_int, [H, P, I64, C.POINTER(I64)]),
         "afv_cluster_analysis": (C.c_int, [H, C.POINTER(I64)]),

@@ -110,6 +110,7 @@ struct AfvContext {
     // profiling
     bool profiling = false;
     struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<void *> peer_own, peer_open;   // exchange over peer memory: this rank's inboxes; the neighbours' (CUDA IPC mappings)
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
     double stage_ms[AFV_N_STAGES] = {0, 0, 0, 0, 0, 0};
@@ -481,7 +482,8 @@ int check_flags(AfvHandle h) {
     if ((int64_t)f[0] * 100 > h->n + 400) h->cmax_hint = std::min(CMAX_HARD, h->cmax_hint + 12);  // busy slow path: longer lists next time
     if (f[3] > 0) {
         char buf[200];
-        snprintf(buf, sizeof buf, "%d cell(s) exceeded every capacity (slow path: ring %d, polygon %d, at most %d cells per build)",
+        if (f[3] >= FLAG_TIMEOUT_MARK) snprintf(buf, sizeof buf, "the exchange message of a ring neighbour did not arrive (peer-memory flag wait timed out)");
+        else snprintf(buf, sizeof buf, "%d cell(s) exceeded every capacity (slow path: ring %d, polygon %d, at most %d cells per build)",
                  f[3], RS_SLOW, KPOLY_SLOW, OVF_MAX);
         h->err = buf;
         return AFV_ERR_CAPACITY;
@@ -606,6 +608,8 @@ void afv_destroy(AfvHandle h) {
                       &h->sums_partial, &h->fire_state, &h->fire_vel}) cudaFree(b->p);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
+    for (void *q : h->peer_open) cudaIpcCloseMemHandle(q);
+    for (void *q : h->peer_own) cudaFree(q);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

@@ -586,6 +586,35 @@ __global__ void k_ring_emit(RingView rv, const int64_t *__restrict__ gid, const 
 #include "afv_relax.cuh"
 
 // ------------------------------------------------------------------------------------------------------
+// Exchange over peer memory (NVLink): the pack kernel of a rank writes its two messages straight into the inboxes of
+// its ring neighbours (device memory of the other GPU, mapped through CUDA IPC), and the two ends synchronise with a
+// sequence number per inbox instead of a send / receive pair: k_flag_signal, launched behind the pack, publishes the
+// number (the writes of the kernels before it on the stream are complete; the fences order the flag behind them at
+// system scope), k_flag_wait holds the receiving stream until the number has arrived.  No library call, no staging copy,
+// no host in between.  A wait that outlives FLAG_WAIT_NS gives up and raises the error flag instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------------------
+constexpr int FLAG_TIMEOUT_MARK = 1 << 20;                  // added to flags[3]: told apart from capacity overflows
+constexpr unsigned long long FLAG_WAIT_NS = 20000000000ull; // 20 s
+__global__ void k_flag_signal(unsigned *flag, unsigned value) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned *>(flag) = value;
+    __threadfence_system();
+}
+__global__ void k_flag_wait(const unsigned *flag, unsigned value, int *flags) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned cur;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(flag) : "memory");
+        if ((int)(cur - value) >= 0) break;                 // (sequence numbers: wrap-safe)
+        __nanosleep(100);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > FLAG_WAIT_NS) { atomicAdd(&flags[3], FLAG_TIMEOUT_MARK); break; }
+    }
+    __threadfence_system();
+}
+
+// ------------------------------------------------------------------------------------------------------
 // slab sharding helpers.  Rows are (n,5) float64: x, y, theta, A0, gid
 // ------------------------------------------------------------------------------------------------------
 __global__ void k_unpack_rows(const double *__restrict__ rows, int n, int offset, int n_owned_in_rows, double2 *__restrict__ xy,

@@ -74,10 +74,11 @@ class GpuCellStore:
     def drop_halo(self) -> None:
         self.h.call("afv_drop_halo")
 
-    def pack_exchange(self, geo, cap: int):
+    def pack_exchange(self, geo, cap: int, outbox=None):
         """(to_left, to_right) messages carrying ownership transfers + halo rows; no host synchronisation.  Halo copies
-        left from the previous exchange are retired by the same pass."""
-        ml, mr = self._msg("xl", cap), self._msg("xr", cap)
+        left from the previous exchange are retired by the same pass.  ``outbox``: where to write them (the neighbours'
+        inboxes when the exchange runs over peer memory) instead of this rank's own message buffers."""
+        ml, mr = outbox if outbox is not None else (self._msg("xl", cap), self._msg("xr", cap))
         self.h.call("afv_pack_exchange", float(geo.lo), float(geo.hi), float(geo.halo), float(geo.shift_to_left),
                     float(geo.shift_to_right), ml.data_ptr(), mr.data_ptr(), int(cap))
         return ml, mr
@@ -97,8 +98,8 @@ class GpuCellStore:
     def late_finish(self, from_left: torch.Tensor, from_right: torch.Tensor, cap: int, exchange_stream: int) -> None:
         self.h.call("afv_late_finish", from_left.data_ptr(), from_right.data_ptr(), int(cap), C.c_void_p(int(exchange_stream)))
 
-    def late_end(self, geo, cap: int, exchange_stream: int, dt, mu, v0, Dr, seed, step_index):
-        ml, mr = self._msg("xl", cap), self._msg("xr", cap)
+    def late_end(self, geo, cap: int, exchange_stream: int, dt, mu, v0, Dr, seed, step_index, outbox=None):
+        ml, mr = outbox if outbox is not None else (self._msg("xl", cap), self._msg("xr", cap))
         self.h.call("afv_late_step_end", float(dt), float(mu), float(v0), float(Dr), C.c_uint64(int(seed)), C.c_int64(int(step_index)),
                     float(geo.lo), float(geo.hi), float(geo.halo), float(geo.shift_to_left), float(geo.shift_to_right),
                     ml.data_ptr(), mr.data_ptr(), int(cap), C.c_void_p(int(exchange_stream)))
@@ -145,6 +146,107 @@ class TorchDistComm:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
         return from_left, from_right
+
+
+class NvlinkPeerComm:
+    """Ring neighbours over peer memory (NVLink / NVSwitch), one process per GPU on one node.
+
+    Every rank owns two inboxes per side (used alternately) and one flag word per side, and maps those of its two
+    neighbours into its address space through CUDA IPC.  ``outbox()`` hands the pack kernel the neighbours' inboxes, so
+    the messages are written straight into the other GPU's memory; ``exchange_fixed`` then only publishes the sequence
+    number of the exchange in the neighbours' flag words (``afv_flag_signal``, behind the pack on the same stream) and
+    makes the stream wait for the neighbours' numbers in its own (``afv_flag_wait``).  No NCCL call, no staging copy and
+    no host work beyond four tiny launches per exchange.  ``torch.distributed`` is used once, to pass the IPC handles
+    around."""
+
+    def __init__(self, rank: int, world: int, device: torch.device, handle):
+        self.rank, self.world = rank, world
+        self.left, self.right = (rank - 1) % world, (rank + 1) % world
+        self.device, self.h = device, handle
+        self._seq = 0
+        self._cap = None
+
+    def _setup(self, cap: int) -> None:
+        import torch.distributed as dist
+        self._msg_bytes = (cap + 1) * ROW * 8
+        nbytes = 4 * self._msg_bytes + 256               # [parity][0: from left, 1: from right] messages, then one flag word per side
+        mine, ipc = C.c_void_p(), (C.c_ubyte * 64)()
+        self.h.call("afv_peer_buffer_create", nbytes, C.byref(mine), ipc)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, bytes(ipc))
+        self._base = {self.rank: mine.value}
+        for r in {self.left, self.right} - {self.rank}:
+            q = C.c_void_p()
+            self.h.call("afv_peer_buffer_open", (C.c_ubyte * 64).from_buffer_copy(everyone[r]), C.byref(q))
+            self._base[r] = q.value
+        self._cap = cap
+        dist.barrier()
+
+    def _msg(self, r: int, parity: int, side: int) -> "DevicePointer":
+        return DevicePointer(self._base[r] + (2 * parity + side) * self._msg_bytes)
+
+    def _flag(self, r: int, side: int) -> int:
+        return self._base[r] + 4 * self._msg_bytes + 4 * side
+
+    def outbox(self, cap: int):
+        """(to_left, to_right): the inboxes of the two neighbours that the NEXT exchange fills."""
+        if self._cap != cap:
+            if self._cap is not None:
+                raise RuntimeError("the message capacity of a peer-memory exchange is fixed at first use")
+            self._setup(cap)
+        par = (self._seq + 1) & 1
+        return self._msg(self.left, par, 1), self._msg(self.right, par, 0)    # I am my left neighbour's right neighbour
+
+    def exchange_fixed(self, to_left, to_right):
+        """The messages are in place already (``outbox``): publish, then wait for the neighbours' -- all on the current stream."""
+        self._seq += 1
+        seq, par = self._seq & 0x7FFFFFFF, self._seq & 1
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self.h.call("afv_flag_signal", st, self._flag(self.left, 1), seq)
+        self.h.call("afv_flag_signal", st, self._flag(self.right, 0), seq)
+        self.h.call("afv_flag_wait", st, self._flag(self.rank, 0), seq)
+        self.h.call("afv_flag_wait", st, self._flag(self.rank, 1), seq)
+        return self._msg(self.rank, par, 0), self._msg(self.rank, par, 1)
+
+
+class DevicePointer:
+    """A raw device address where the exchange code expects a message tensor (it only ever asks for ``data_ptr()``)."""
+
+    def __init__(self, ptr: int):
+        self._ptr = int(ptr)
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+
+def default_comm(rank: int, world: int, device: torch.device, handle):
+    """The transport of a one-process-per-GPU run: peer memory when every rank can set it up (``AFV_EXCHANGE=nccl`` forces
+    the send / receive pairs of ``TorchDistComm``).  The choice is collective -- one rank without peer access and every
+    rank uses NCCL -- and visible as ``type(sim.comm).__name__`` (bench.py reports it)."""
+    import os
+    import torch.distributed as dist
+    want = os.environ.get("AFV_EXCHANGE", "auto").lower()
+    if want == "nccl" or not (dist.is_available() and dist.is_initialized()) or dist.get_backend() != "nccl":
+        return TorchDistComm(rank, world)
+    ok = 1
+    try:
+        n_dev = torch.cuda.device_count()
+        if world > n_dev:
+            ok = 0
+        else:
+            me = device.index
+            for r in {(rank - 1) % world, (rank + 1) % world}:
+                if r != rank and not torch.cuda.can_device_access_peer(me, r % n_dev):
+                    ok = 0
+    except Exception:
+        ok = 0
+    t = torch.tensor([ok], device=device, dtype=torch.int32)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if int(t.item()) == 0:
+        if want == "peer":
+            raise RuntimeError("AFV_EXCHANGE=peer, but not every rank has peer access to its ring neighbours")
+        return TorchDistComm(rank, world)
+    return NvlinkPeerComm(rank, world, device, handle)
 
 
 def loopback_exchange(outboxes: list[tuple[torch.Tensor, torch.Tensor]]) -> list[tuple[torch.Tensor, torch.Tensor]]:
@@ -230,7 +332,7 @@ class SlabShardedSimulator:
             self._h.call("afv_set_slab", self.geo.grid_x0, self.geo.grid_x1)
             self._h.call("afv_set_deferred_checks", 1)    # one host synchronisation per step (at the exchange), not two
         self.store = GpuCellStore(self._h, self.device)
-        self.comm = comm if comm is not None else (TorchDistComm(rank, world) if world > 1 else None)
+        self.comm = comm if comm is not None else (default_comm(rank, world, self.device, self._h) if world > 1 else None)
         self._step_index = 0
         self.overlap = bool(overlap) and world > 1
         self.overlapped_steps = 0         # steps taken in the overlapped form so far
@@ -268,6 +370,13 @@ class SlabShardedSimulator:
         return self.store.n_owned
 
     def close(self) -> None:
+        if isinstance(self.comm, NvlinkPeerComm) and self.comm._cap is not None:
+            # the neighbours write into this rank's inboxes and this rank into theirs: nothing may be released before every
+            # rank has seen its last message arrive (collective, like the exchange itself)
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized():
+                dist.barrier()
         self._h.close()
 
     def connections(self) -> np.ndarray:
@@ -293,7 +402,8 @@ class SlabShardedSimulator:
 
     def exchange_out(self):
         """Messages for the (left, right) neighbour: cells that left the slab (ownership transfer) + halo cells."""
-        return self.store.pack_exchange(self.geo, self._caps()[0])
+        cap = self._caps()[0]
+        return self.store.pack_exchange(self.geo, cap, self.comm.outbox(cap) if hasattr(self.comm, "outbox") else None)
 
     def exchange_in(self, from_left, from_right) -> None:
         self.store.finish_exchange(from_left, from_right, self._caps()[0])
@@ -327,7 +437,9 @@ class SlabShardedSimulator:
         self.store.late_finish(inbox[0], inbox[1], self._caps()[0], self._xs.cuda_stream)
 
     def late_end(self, dt, mu, v0, Dr, seed):
-        msgs = self.store.late_end(self.geo, self._caps()[0], self._xs.cuda_stream, dt, mu, v0, Dr, seed, self._step_index)
+        cap = self._caps()[0]
+        msgs = self.store.late_end(self.geo, cap, self._xs.cuda_stream, dt, mu, v0, Dr, seed, self._step_index,
+                                   self.comm.outbox(cap) if hasattr(self.comm, "outbox") else None)
         self._step_index += 1
         self.overlapped_steps += 1
         self._halo_fresh = False

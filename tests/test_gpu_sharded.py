@@ -135,3 +135,18 @@ def test_late_cell_exchange_follows_single_gpu():
     b = sh.build()
     assert np.array_equal(b["pts"], ref.pts) and np.array_equal(b["theta"], ref.theta)
     ref.close(); sh.close()
+
+
+def test_peer_memory_exchange_across_two_processes():
+    """One process per GPU: the pack kernel writes into the neighbours' inboxes over NVLink (CUDA IPC + flag words,
+    ``NvlinkPeerComm``) -- same bits as NCCL send / receive and as one handle, plain and overlapped.  Needs two GPUs."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    worker = Path(__file__).with_name("_peer_exchange_worker.py")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", str(worker)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "PEER-EXCHANGE-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
