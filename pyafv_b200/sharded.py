@@ -240,11 +240,30 @@ def default_comm(rank: int, world: int, device: torch.device, handle):
                     ok = 0
     except Exception:
         ok = 0
+    # a trial run of the set-up itself (a 4 KB buffer per rank, mapped by its neighbours): CUDA IPC can be unavailable even where
+    # peer access is not (containers without a shared IPC namespace)
+    everyone = [None] * world
+    mine, ipc = C.c_void_p(), (C.c_ubyte * 64)()
+    if ok:
+        try:
+            handle.call("afv_peer_buffer_create", 4096, C.byref(mine), ipc)
+        except Exception:
+            ok = 0
+    dist.all_gather_object(everyone, bytes(ipc) if ok else None)
+    if ok and all(e is not None for e in everyone):
+        try:
+            for r in {(rank - 1) % world, (rank + 1) % world} - {rank}:
+                q = C.c_void_p()
+                handle.call("afv_peer_buffer_open", (C.c_ubyte * 64).from_buffer_copy(everyone[r]), C.byref(q))
+        except Exception:
+            ok = 0
+    else:
+        ok = 0
     t = torch.tensor([ok], device=device, dtype=torch.int32)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if int(t.item()) == 0:
         if want == "peer":
-            raise RuntimeError("AFV_EXCHANGE=peer, but not every rank has peer access to its ring neighbours")
+            raise RuntimeError("AFV_EXCHANGE=peer, but not every rank can map the inboxes of its ring neighbours")
         return TorchDistComm(rank, world)
     return NvlinkPeerComm(rank, world, device, handle)
 
