@@ -222,8 +222,9 @@ int afv_stream_wait(AfvHandle h, void *other_stream);
  * the GPUs of one node.  The caller maps the inboxes of the two ring neighbours into its address space (CUDA IPC) and
  * passes them to afv_pack_exchange / afv_late_step_end as msg_left_dev / msg_right_dev: the pack kernel then writes
  * its messages straight into the neighbours' memory.  afv_flag_signal, issued behind the pack on the same stream,
- * publishes a sequence number in the neighbour's memory once those writes are complete; afv_flag_wait holds a stream
- * until the number in this rank's own flag word has reached `value` (sequence numbers compare wrap-safe).  Two
+ * publishes a sequence number in the neighbours' memory (two flag words per launch: a rank has two ring neighbours) once
+ * those writes are complete; afv_flag_wait holds a stream until the numbers in this rank's own flag words have reached
+ * `value` (sequence numbers compare wrap-safe).  Two
  * inboxes per side, used alternately, are enough: a rank cannot be more than one exchange ahead of a neighbour it also
  * receives from.  A wait that lasts longer than 20 s gives up: the next status read reports AFV_ERR_CAPACITY with
  * "... did not arrive", and the cells are not moved.
@@ -233,8 +234,8 @@ int afv_stream_wait(AfvHandle h, void *other_stream);
  * stream: NULL = the handle's stream. */
 int afv_peer_buffer_create(AfvHandle h, int64_t bytes, void **dev_out, unsigned char ipc_handle_out[64]);
 int afv_peer_buffer_open(AfvHandle h, const unsigned char ipc_handle[64], void **dev_out);
-int afv_flag_signal(AfvHandle h, void *stream, unsigned *flag_dev, unsigned value);
-int afv_flag_wait(AfvHandle h, void *stream, const unsigned *flag_dev, unsigned value);
+int afv_flag_signal(AfvHandle h, void *stream, unsigned *flag_a_dev, unsigned *flag_b_dev, unsigned value);       /* flag_b_dev may be NULL */
+int afv_flag_wait(AfvHandle h, void *stream, const unsigned *flag_a_dev, const unsigned *flag_b_dev, unsigned value);
 /* after afv_build: rows (count,11) of the OWNED cells in device memory:
  * x, y, theta, A0, gid, fx, fy, area, perimeter, arclen, coord_num */
 int afv_pack_owned(AfvHandle h, double *rows_dev_out, int64_t capacity, int64_t *count);

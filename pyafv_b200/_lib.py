@@ -104,8 +104,8 @@ def load() -> C.CDLL:
         "afv_stream_wait": (C.c_int, [H, P]),
         "afv_peer_buffer_create": (C.c_int, [H, I64, C.POINTER(P), P]),
         "afv_peer_buffer_open": (C.c_int, [H, P, C.POINTER(P)]),
-        "afv_flag_signal": (C.c_int, [H, P, P, C.c_uint]),
-        "afv_flag_wait": (C.c_int, [H, P, P, C.c_uint]),
+        "afv_flag_signal": (C.c_int, [H, P, P, P, C.c_uint]),
+        "afv_flag_wait": (C.c_int, [H, P, P, P, C.c_uint]),
         "afv_get_exchange_stats": (C.c_int, [H, P]),
         "afv_pack_owned": (C.c_int, [H, P, I64, C.POINTER(I64)]),
         "afv_cluster_analysis": (C.c_int, [H, C.POINTER(I64)]),

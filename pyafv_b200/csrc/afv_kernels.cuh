@@ -597,21 +597,26 @@ __global__ void k_ring_emit(RingView rv, const int64_t *__restrict__ gid, const 
 // ------------------------------------------------------------------------------------------------------
 constexpr int FLAG_TIMEOUT_MARK = 1 << 20;                  // added to flags[3]: told apart from capacity overflows
 constexpr unsigned long long FLAG_WAIT_NS = 20000000000ull; // 20 s
-__global__ void k_flag_signal(unsigned *flag, unsigned value) {
+// (two flag words per launch: a rank has two ring neighbours; flag_b may be null)
+__global__ void k_flag_signal(unsigned *flag_a, unsigned *flag_b, unsigned value) {
     __threadfence_system();
-    *reinterpret_cast<volatile unsigned *>(flag) = value;
+    *reinterpret_cast<volatile unsigned *>(flag_a) = value;
+    if (flag_b) *reinterpret_cast<volatile unsigned *>(flag_b) = value;
     __threadfence_system();
 }
-__global__ void k_flag_wait(const unsigned *flag, unsigned value, int *flags) {
-    unsigned long long t0, t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
-        unsigned cur;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(flag) : "memory");
-        if ((int)(cur - value) >= 0) break;                 // (sequence numbers: wrap-safe)
-        __nanosleep(100);
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (t - t0 > FLAG_WAIT_NS) { atomicAdd(&flags[3], FLAG_TIMEOUT_MARK); break; }
+__global__ void k_flag_wait(const unsigned *flag_a, const unsigned *flag_b, unsigned value, int *flags) {
+    const unsigned *const flag = (threadIdx.x == 0) ? flag_a : flag_b;      // one thread per flag word
+    if (flag) {
+        unsigned long long t0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            unsigned cur;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(flag) : "memory");
+            if ((int)(cur - value) >= 0) break;                 // (sequence numbers: wrap-safe)
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > FLAG_WAIT_NS) { atomicAdd(&flags[3], FLAG_TIMEOUT_MARK); break; }
+        }
     }
     __threadfence_system();
 }

@@ -156,7 +156,7 @@ class NvlinkPeerComm:
     the messages are written straight into the other GPU's memory; ``exchange_fixed`` then only publishes the sequence
     number of the exchange in the neighbours' flag words (``afv_flag_signal``, behind the pack on the same stream) and
     makes the stream wait for the neighbours' numbers in its own (``afv_flag_wait``).  No NCCL call, no staging copy and
-    no host work beyond four tiny launches per exchange.  ``torch.distributed`` is used once, to pass the IPC handles
+    no host work beyond two tiny launches per exchange.  ``torch.distributed`` is used once, to pass the IPC handles
     around."""
 
     def __init__(self, rank: int, world: int, device: torch.device, handle):
@@ -202,10 +202,8 @@ class NvlinkPeerComm:
         self._seq += 1
         seq, par = self._seq & 0x7FFFFFFF, self._seq & 1
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        self.h.call("afv_flag_signal", st, self._flag(self.left, 1), seq)
-        self.h.call("afv_flag_signal", st, self._flag(self.right, 0), seq)
-        self.h.call("afv_flag_wait", st, self._flag(self.rank, 0), seq)
-        self.h.call("afv_flag_wait", st, self._flag(self.rank, 1), seq)
+        self.h.call("afv_flag_signal", st, self._flag(self.left, 1), self._flag(self.right, 0), seq)
+        self.h.call("afv_flag_wait", st, self._flag(self.rank, 0), self._flag(self.rank, 1), seq)
         return self._msg(self.rank, par, 0), self._msg(self.rank, par, 1)
 
 
