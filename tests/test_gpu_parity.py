@@ -206,6 +206,35 @@ def test_many_neighbour_cell_uses_overflow_pool(n_ring, radius):
     sim.close()
 
 
+@pytest.mark.parametrize("n_ring", [5, 6, 7, 8])
+def test_cell_with_five_to_eight_arcs_stays_on_the_fast_path(n_ring):
+    """n_ring neighbours whose bisectors each cut the disk separately: n_ring contact edges with n_ring arcs in between, a
+    ring of 2 n_ring <= 16 entries.  The fast path stores RS/2 = 8 arcs per cell (it stored four, and such cells were
+    the whole population of the slow path at rho l^2 = 1); the neighbours look their arc ends up in the second half of
+    the cell's arc table."""
+    import pyafv_b200 as afv
+    from afv_oracle import oracle_build
+    rng = np.random.default_rng(200 + n_ring)
+    ang = 2 * np.pi * (np.arange(n_ring) + 0.05 * rng.random(n_ring)) / n_ring
+    ringpts = (1.9 + 0.05 * rng.random(n_ring))[:, None] * np.column_stack((np.cos(ang), np.sin(ang)))
+    filler = (rng.random((400, 2)) - 0.5) * 30.0
+    filler = filler[np.hypot(filler[:, 0], filler[:, 1]) > 4.2]
+    pts = np.vstack([[0.0, 0.0], ringpts, filler]) + 15.0
+    sim = afv.FiniteVoronoiSimulator(pts, afv.PhysicalParams())
+    d = sim.build()
+    o = oracle_build(pts, rings=True)
+    assert int(o["ring_off"][1] - o["ring_off"][0]) == 2 * n_ring and o["coord_nums"][0] == n_ring
+    for k in ("areas", "perimeters", "arclens", "forces"):
+        _close(d[k], o[k], k)
+    assert np.array_equal(d["coord_nums"], o["coord_nums"]) and np.array_equal(d["connections"], o["connections"])
+    diag = sim.diagnostics()
+    assert diag["slow_path_cells"] == 0 and diag["lookup_misses"] == 0
+    sim.step(1e-3, 1.0, 0.0, 0.0, n_steps=3)
+    _close(sim.build(connect=False, rings=False)["forces"], oracle_build(sim.pts)["forces"], "forces after 3 steps")
+    assert sim.diagnostics()["lookup_misses"] == 0
+    sim.close()
+
+
 @pytest.mark.parametrize("n_ring", [9, 12, 15])
 def test_long_ring_with_short_polygon_is_emitted_into_the_pool(n_ring):
     """n_ring <= 16 neighbours whose bisectors each cut the disk separately: the polygon fits the fast path but the ring
