@@ -109,6 +109,12 @@ struct AfvContext {
     double pair_rng[4] = {0, 0, 0, 0};
     // profiling
     bool profiling = false;
+    // time loop of afv_step replayed as a CUDA graph (two steps per replay: the double buffers are back where they started)
+    long long *step_dev = nullptr;     // the step index on the device: k_bin_count advances it, k_force reads it
+    bool step_on_device = false;       // the launches being issued take the step index from step_dev
+    uint64_t alloc_epoch = 0;          // bumped by every (re)allocation: a captured graph holds the old pointers
+    cudaGraphExec_t step_graph = nullptr;
+    std::string step_graph_key;
     struct Span { int stage; cudaEvent_t a, b; };
     std::vector<void *> peer_own, peer_open;   // exchange over peer memory: this rank's inboxes; the neighbours' (CUDA IPC mappings)
     std::vector<Span> spans;
@@ -141,6 +147,7 @@ template <typename T>
 int dev_alloc(AfvHandle h, T **p, size_t count) {
     if (*p) { cudaFree(*p); *p = nullptr; }
     if (count == 0) count = 1;
+    ++h->alloc_epoch;
     CK(cudaMalloc((void **)p, count * sizeof(T)));
     return AFV_OK;
 }
@@ -149,6 +156,7 @@ int ensure_buf(AfvHandle h, DevBuf &b, size_t bytes) {
     if (b.bytes >= bytes && b.p) return AFV_OK;
     if (b.p) cudaFree(b.p);
     b.p = nullptr; b.bytes = 0;
+    ++h->alloc_epoch;
     size_t want = std::max(bytes, (size_t)256);
     CK(cudaMalloc(&b.p, want));
     b.bytes = want;
@@ -371,7 +379,8 @@ int stage_sort(AfvHandle h, const int *n_dev = nullptr, int64_t n_upper = 0) {
         h->bin_cnt_zero = true;
     }
     // (thread 0 also restarts the queue of the slow path: flags[0])
-    k_bin_count<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->xy[c], h->owned[c], n_all, n_dev, h->d_grid, dead_key, h->keys, h->bin_cnt, h->flags);
+    k_bin_count<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->xy[c], h->owned[c], n_all, n_dev, h->d_grid, dead_key, h->keys, h->bin_cnt, h->flags,
+                                                          h->step_on_device ? h->step_dev : nullptr);
     size_t tmp = h->cub_tmp_bytes;
     CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp, tmp, h->bin_cnt, h->bin_start, nbins + 2, h->stream));
     k_bin_scatter<<<nblk(n_all, 256), 256, 0, h->stream>>>(h->keys, n_all, n_dev, dead_key, h->bin_start, h->bin_cnt, h->xy[c], h->th[c], h->a0[c],
@@ -465,6 +474,7 @@ int stage_force(AfvHandle h, bool do_step, double dt, double mu, double v0, doub
     a.ph = phys_dev(h->prm); a.fx = h->fx; a.fy = h->fy; a.flags = h->flags;
     a.do_step = do_step ? 1 : 0; a.xy = h->xy[c]; a.theta = h->th[c];
     a.dt = dt; a.mu = mu; a.v0 = v0; a.noise_amp = std::sqrt(2.0 * Dr * dt); a.seed = seed; a.step = step;
+    a.step_dev = h->step_on_device ? h->step_dev : nullptr;
     a.noise = noise_row; a.Lx = h->L; a.Ly = h->L;   // a slab keeps the box's own coordinates, wrapped like the single-GPU run
     // (a periodic box -- whole or an x-slab of it -- takes the minimum image in both directions; an open system in none)
     a.mi_Lx = a.mi_Ly = h->L > 0.0 ? h->L : 0.0; a.mi_hx = a.mi_hy = 0.5 * a.mi_Lx;
@@ -608,6 +618,8 @@ void afv_destroy(AfvHandle h) {
                       &h->sums_partial, &h->fire_state, &h->fire_vel}) cudaFree(b->p);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
+    if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+    cudaFree(h->step_dev);
     for (void *q : h->peer_open) cudaIpcCloseMemHandle(q);
     for (void *q : h->peer_own) cudaFree(q);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -760,7 +772,52 @@ int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t s
     }
     const bool deferred = h->defer_checks && !noise_host;
     if (!deferred) CK(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
-    for (int s = 0; s < n_steps; ++s) {
+    int s_first = 0;
+    // A periodic time loop issues the same launches every step and never asks the host anything: after two plain steps
+    // (which settle every buffer) the rest is replayed as a CUDA graph of two steps -- the double buffers are back where
+    // they started -- with the step index kept on the device.  What it saves is the idle time in front of every launch
+    // (8 launches, ~2 us each, per step at N = 10^6; most of the step at N = 10^4).
+    static const bool no_graph = getenv("AFV_NO_GRAPH") != nullptr;
+    if (!no_graph && h->L > 0.0 && !noise_host && !deferred && !h->slab && !h->profiling && n_steps >= 6) {
+        for (; s_first < 2; ++s_first) {
+            if ((rc = stage_sort(h))) return rc;
+            if ((rc = stage_geometry(h))) return rc;
+            if ((rc = stage_force(h, true, dt, mu, v0, Dr, seed, step0 + s_first, nullptr))) return rc;
+        }
+        char key[512];
+        snprintf(key, sizeof key, "%lld %lld %d %d %d %llu %a %a %a %a %llu %a %a %a %a %a %a %a %a", (long long)h->n, (long long)h->cap, h->cur, h->cmax_hint, (int)h->gid_is_perm,
+                 (unsigned long long)h->alloc_epoch, dt, mu, v0, Dr, (unsigned long long)seed, h->L, h->prm.r, h->prm.A0, h->prm.P0, h->prm.KA, h->prm.KP,
+                 h->prm.Lambda, h->prm.delta);
+        if (!h->step_dev) CK(cudaMalloc((void **)&h->step_dev, sizeof(long long)));
+        if (!h->step_graph || h->step_graph_key != key) {
+            if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            const int64_t launches0 = h->launches;
+            h->step_on_device = true;
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            rc = AFV_OK;
+            for (int k = 0; k < 2 && rc == AFV_OK; ++k) {
+                if ((rc = stage_sort(h)) == AFV_OK && (rc = stage_geometry(h)) == AFV_OK) rc = stage_force(h, true, dt, mu, v0, Dr, seed, 0, nullptr);
+            }
+            const cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+            h->step_on_device = false;
+            h->launches = launches0;                   // (nothing has run yet)
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            CK(ce);
+            const cudaError_t ci = cudaGraphInstantiate(&h->step_graph, g, 0);
+            cudaGraphDestroy(g);
+            CK(ci);
+            h->step_graph_key = key;
+        }
+        const int pairs = (n_steps - s_first) / 2;
+        const long long before = step0 + s_first - 1;  // k_bin_count advances the index at the start of every step
+        CK(cudaMemcpyAsync(h->step_dev, &before, sizeof before, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));          // (`before` lives on this stack frame)
+        for (int p = 0; p < pairs; ++p) CK(cudaGraphLaunch(h->step_graph, h->stream));
+        h->launches += (int64_t)pairs * 2 * 7;         // per step, as counted outside the graph: cell list 3, k_nbrs, k_clip, k_geometry_slow, k_force
+        s_first += 2 * pairs;
+    }
+    for (int s = s_first; s < n_steps; ++s) {
         // (the slow-path queue, flags[0], restarts with every cell list: k_bin_count; the error counters run on)
         if ((rc = stage_sort(h))) return rc;
         // open boundaries: the local density is unknown, so the capacity is checked (and grown) before the positions move

@@ -81,9 +81,12 @@ __global__ void k_bbox_final(const double *__restrict__ part, int nblocks, doubl
 // n_dev (may be null): the cell count lives on the device (the host launched for an upper bound and has not read it yet)
 __global__ void k_bin_count(const double2 *__restrict__ xy, const unsigned char *__restrict__ owned, int n, const int *__restrict__ n_dev,
                             const GridDesc *__restrict__ gp, unsigned dead_key, unsigned *__restrict__ keys, int *__restrict__ bin_cnt,
-                            int *__restrict__ queue_count) {
+                            int *__restrict__ queue_count, long long *__restrict__ step_counter) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *queue_count = 0;            // the queue of the slow path restarts with every cell list
+    if (i == 0) {
+        *queue_count = 0;                    // the queue of the slow path restarts with every cell list
+        if (step_counter) *step_counter += 1;   // replayed time loops (CUDA graph): the step index lives on the device; k_force reads it
+    }
     if (n_dev) n = *n_dev;
     if (i >= n) return;
     unsigned key = dead_key;
@@ -181,6 +184,7 @@ struct ForceArgs {
     double dt, mu, v0, noise_amp;  // noise_amp = sqrt(2 Dr dt)
     uint64_t seed;
     int64_t step;
+    const long long *step_dev;     // not null: the step index is read from the device (time loop replayed as a CUDA graph)
     const double *noise;           // nullptr -> Philox; else row of this step, indexed by gid
     double Lx, Ly;                 // periodic wrap of the updated positions per direction (0 = none)
     // minimum image of the displacements per direction (period, half period; 0 = none).  By value: the kernel reads them
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(FB_THREADS, FORCE_MIN_BLOCKS) k_force(ForceArg
         th = a.theta[s]; pos = a.xy[s];
         if (a.noise_amp != 0.0) {
             const int64_t id = a.gid[s];
-            xi_ = a.noise ? a.noise[id] : philox_normal(a.seed, id, a.step);
+            xi_ = a.noise ? a.noise[id] : philox_normal(a.seed, id, a.step_dev ? (int64_t)*a.step_dev : a.step);
         }
     }
     __syncthreads();
