@@ -96,7 +96,9 @@ int afv_build(AfvHandle h, unsigned flags);
  * noise_host: NULL -> xi from Philox4x32-10 keyed by (seed, cell id, step0 + s);
  *             else (n_steps, N) float64 in the caller's cell order (parity runs with a recorded stream).
  * Positions are wrapped into [0,L) when the handle is periodic.  The geometry left on the device afterwards is
- * that of the LAST build, i.e. of the positions before the last update. */
+ * that of the LAST build, i.e. of the positions before the last update.
+ * Periodic handles with the built-in generator replay calls of n_steps >= 6 as a CUDA graph of two steps (kept in the
+ * handle; environment AFV_NO_GRAPH=1 turns that off): same results, less idle time between the launches. */
 int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t seed, int64_t step0, int n_steps,
              const double *noise_host);
 /* the xi the device generator produces for (seed, cell id, step): for host-side verification of the stream */
