@@ -114,6 +114,7 @@ struct AfvContext {
     bool step_on_device = false;       // the launches being issued take the step index from step_dev
     uint64_t alloc_epoch = 0;          // bumped by every (re)allocation: a captured graph holds the old pointers
     cudaGraphExec_t step_graph = nullptr;
+    bool step_graph_off = false;       // capturing failed once on this handle's stream: plain launches from then on
     std::string step_graph_key;
     struct Span { int stage; cudaEvent_t a, b; };
     std::vector<void *> peer_own, peer_open;   // exchange over peer memory: this rank's inboxes; the neighbours' (CUDA IPC mappings)
@@ -778,7 +779,7 @@ int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t s
     // they started -- with the step index kept on the device.  What it saves is the idle time in front of every launch
     // (8 launches, ~2 us each, per step at N = 10^6; most of the step at N = 10^4).
     static const bool no_graph = getenv("AFV_NO_GRAPH") != nullptr;
-    if (!no_graph && h->L > 0.0 && !noise_host && !deferred && !h->slab && !h->profiling && n_steps >= 6) {
+    if (!no_graph && !h->step_graph_off && h->L > 0.0 && !noise_host && !deferred && !h->slab && !h->profiling && n_steps >= 6) {
         for (; s_first < 2; ++s_first) {
             if ((rc = stage_sort(h))) return rc;
             if ((rc = stage_geometry(h))) return rc;
@@ -793,26 +794,31 @@ int afv_step(AfvHandle h, double dt, double mu, double v0, double Dr, uint64_t s
             if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
             cudaGraph_t g = nullptr;
             const int64_t launches0 = h->launches;
-            h->step_on_device = true;
-            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            rc = AFV_OK;
-            for (int k = 0; k < 2 && rc == AFV_OK; ++k) {
-                if ((rc = stage_sort(h)) == AFV_OK && (rc = stage_geometry(h)) == AFV_OK) rc = stage_force(h, true, dt, mu, v0, Dr, seed, 0, nullptr);
+            cudaError_t ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+            if (ce == cudaSuccess) {
+                h->step_on_device = true;
+                rc = AFV_OK;
+                for (int k = 0; k < 2 && rc == AFV_OK; ++k) {
+                    if ((rc = stage_sort(h)) == AFV_OK && (rc = stage_geometry(h)) == AFV_OK) rc = stage_force(h, true, dt, mu, v0, Dr, seed, 0, nullptr);
+                }
+                ce = cudaStreamEndCapture(h->stream, &g);
+                h->step_on_device = false;
+                h->launches = launches0;               // (nothing has run yet)
+                if (ce == cudaSuccess && rc == AFV_OK) ce = cudaGraphInstantiate(&h->step_graph, g, 0);
+                if (g) cudaGraphDestroy(g);
             }
-            const cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
-            h->step_on_device = false;
-            h->launches = launches0;                   // (nothing has run yet)
-            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-            CK(ce);
-            const cudaError_t ci = cudaGraphInstantiate(&h->step_graph, g, 0);
-            cudaGraphDestroy(g);
-            CK(ci);
-            h->step_graph_key = key;
+            if (rc != AFV_OK) return rc;               // (a stage refused while being captured: its message stands)
+            if (ce != cudaSuccess) {                   // a stream that cannot be captured, ...: this handle steps the plain way from now on
+                cudaGetLastError();
+                h->step_graph = nullptr; h->step_graph_off = true;
+            } else h->step_graph_key = key;
         }
-        const int pairs = (n_steps - s_first) / 2;
-        const long long before = step0 + s_first - 1;  // k_bin_count advances the index at the start of every step
-        CK(cudaMemcpyAsync(h->step_dev, &before, sizeof before, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));          // (`before` lives on this stack frame)
+        const int pairs = h->step_graph ? (n_steps - s_first) / 2 : 0;
+        if (pairs > 0) {
+            const long long before = step0 + s_first - 1;  // k_bin_count advances the index at the start of every step
+            CK(cudaMemcpyAsync(h->step_dev, &before, sizeof before, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));      // (`before` lives on this stack frame)
+        }
         for (int p = 0; p < pairs; ++p) CK(cudaGraphLaunch(h->step_graph, h->stream));
         h->launches += (int64_t)pairs * 2 * 7;         // per step, as counted outside the graph: cell list 3, k_nbrs, k_clip, k_geometry_slow, k_force
         s_first += 2 * pairs;
