@@ -144,6 +144,31 @@ def test_determinism_and_order_independence():
     sim.close()
 
 
+def test_graph_replayed_time_loop_equals_single_step_calls():
+    """A periodic ``step(n_steps >= 6)`` is replayed as a CUDA graph with the step index of the noise stream kept on the
+    device; one-step calls take the plain launches with the index passed by the host.  Same bits either way, also across
+    several long calls (the graph is kept in the handle) and after a parameter change (it is captured again)."""
+    import pyafv_b200 as afv
+    N = 20000
+    L = float(np.sqrt(N))
+    rng = np.random.default_rng(77)
+    pts, theta = rng.random((N, 2)) * L, 2 * np.pi * rng.random(N) - np.pi
+    phys = afv.PhysicalParams()
+    a = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
+    b = afv.FiniteVoronoiSimulator(pts, phys, periodic=L)
+    a.step(0.01, 1.0, 2.4, 0.3, theta=theta, seed=5, n_steps=25)      # 2 plain steps + 11 replays + 1 plain step
+    a.step(0.01, 1.0, 2.4, 0.3, seed=5, n_steps=16)                   # the kept graph (odd start parity: captured again)
+    a.step(0.02, 1.0, 1.0, 0.1, seed=6, n_steps=10)                   # other parameters
+    b.step(0.01, 1.0, 2.4, 0.3, theta=theta, seed=5, n_steps=1)
+    for _ in range(40):
+        b.step(0.01, 1.0, 2.4, 0.3, seed=5, n_steps=1)
+    for _ in range(10):
+        b.step(0.02, 1.0, 1.0, 0.1, seed=6, n_steps=1)
+    assert np.array_equal(a.pts, b.pts) and np.array_equal(a.theta, b.theta)
+    assert a.diagnostics()["lookup_misses"] == 0
+    a.close(); b.close()
+
+
 def test_philox_stream_matches_host_formula():
     """The device noise stream equals the host evaluation of the same counter-based generator."""
     import ctypes as C
